@@ -1,0 +1,207 @@
+/*
+ * mctsb.h — C ABI of the B200 rollout backend (the MCTS *Simulation* phase).
+ *
+ * This is the drop-in boundary.  In the reference there is no FFI; the boundary is the pure
+ * virtual `double MCTS_state::rollout() const` (reference mcts/include/state.h:29) and its
+ * single call site `MCTS_node::rollout()` (reference mcts/src/mcts.cpp:57-81), which fans
+ * `NUMBER_OF_THREADS` `RolloutJob`s (reference mcts/include/mcts.h:82-91) out to the pthread
+ * `JobScheduler` (reference mcts/include/JobScheduler.h:42-63) and sums the doubles.  Every
+ * entry point below names the reference code it replaces.
+ *
+ * Rules of the boundary: plain C types, caller owns every host buffer, the backend owns all
+ * device memory and streams, no exceptions, nothing is printed, every function returns an
+ * `mctsb_status` (0 = ok).  There is NO CPU fallback: without a CUDA device every compute
+ * entry point returns MCTSB_ERR_NO_DEVICE.
+ */
+#ifndef MCTSB_H
+#define MCTSB_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MCTSB_ABI_VERSION 1
+
+typedef enum {
+    MCTSB_OK = 0,
+    MCTSB_ERR_NO_DEVICE = 1,   /* no CUDA device / driver: the product path refuses to run        */
+    MCTSB_ERR_CUDA = 2,        /* a CUDA runtime call failed, see mctsb_last_cuda_error           */
+    MCTSB_ERR_BAD_ARG = 3,     /* NULL pointer, negative size, unknown game / policy id           */
+    MCTSB_ERR_BAD_STATE = 4,   /* a packed state record is not a reachable position               */
+    MCTSB_ERR_NOT_SUBMITTED = 5, /* wait without a pending submit                                 */
+    MCTSB_ERR_BUSY = 6,        /* submit while a previous submit has not been waited for          */
+    MCTSB_ERR_OOM = 7
+} mctsb_status;
+
+/* ---- games and rollout policies ------------------------------------------------------- */
+#define MCTSB_GAME_QUORIDOR  0   /* reference examples/Quoridor/Quoridor.{h,cpp}                   */
+#define MCTSB_GAME_TICTACTOE 1   /* reference examples/TicTacToe/TicTacToe.{h,cpp}                 */
+
+/* Quoridor policies.  REF = bug-faithful `Quoridor_state::rollout()` (Quoridor.cpp:809-855):
+ * <= 50 plies of pick_semirandom_move (Quoridor.cpp:680-803), then evaluate_position
+ * (Quoridor.cpp:629-664).  UNI = uniformly random legal move per ply over the reference's
+ * generate_all_moves order (Quoridor.cpp:594-616); no reference function implements it, the
+ * oracle is a loop over the reference's public API. */
+#define MCTSB_POLICY_REF 0
+#define MCTSB_POLICY_UNI 1
+#define MCTSB_UNI_MAX_PLIES 4096   /* UNI ply cap; a capped playout scores 0.5                     */
+
+/* ---- wire formats ------------------------------------------------------------------------
+ * Quoridor position, 32 bytes, little endian.  Replaces the 192-byte `Quoridor_state` object
+ * (Quoridor.h:32-50).  Coordinates as in the reference: x = row 0..8, y = column 0..8; White
+ * (player 1) starts on (0,4) and wins on row 8, Black starts on (8,4) and wins on row 0.
+ * A 2-long wall is stored once, by its anchor (x,y), 0 <= x,y < 8, bit 8*x+y:
+ *   horizontal anchor (x,y): segments under cells (x,y),(x,y+1)  => walls[x][y], walls[x][y+1] get 'h'
+ *   vertical   anchor (x,y): segments right of cells (x,y),(x+1,y) => walls[x][y], walls[x+1][y] get 'v'
+ *   wall_connections[x][y] = h_anchor bit | v_anchor bit            (Quoridor.cpp:351-357)        */
+typedef struct mctsb_qstate {
+    uint64_t h_anchor;
+    uint64_t v_anchor;
+    uint8_t  wx, wy, bx, by;      /* pawn rows / columns                                          */
+    uint8_t  wwalls, bwalls;      /* walls left in hand (wwallsno, bwallsno)                      */
+    uint8_t  turn;                /* 0 = White ('W', player 1) to move, 1 = Black ('B')           */
+    uint8_t  flags;               /* must be 0                                                    */
+    uint32_t move_counter;        /* Quoridor_state::move_counter (Quoridor.h:48)                 */
+    uint32_t reserved;            /* must be 0                                                    */
+} mctsb_qstate;
+
+/* Tic-Tac-Toe position, 4 bytes: bit c (c = 3*row+col) of x_mask / o_mask.  Replaces
+ * `TicTacToe_state` (TicTacToe.h:7-24). */
+typedef struct mctsb_tstate {
+    uint16_t x_mask;              /* low 9 bits                                                   */
+    uint16_t o_mask;              /* low 9 bits; bit 15 = 1 when 'o' is to move                   */
+} mctsb_tstate;
+
+/* Canonical Quoridor move ids (209 slots): 0..80 pawn to cell 9*x+y; 81..144 horizontal wall
+ * anchored at 8*x+y; 145..208 vertical wall anchored at 8*x+y. */
+#define MCTSB_Q_NUM_MOVES 209
+#define MCTSB_Q_MOVE_STEP(x, y)  ((x) * 9 + (y))
+#define MCTSB_Q_MOVE_HWALL(x, y) (81 + (x) * 8 + (y))
+#define MCTSB_Q_MOVE_VWALL(x, y) (145 + (x) * 8 + (y))
+
+/* Per-rollout outcome record (parity mode), 16 bytes.  `score` is the double the reference
+ * rollout() would return, computed on the device with round-to-nearest IEEE ops only.
+ *   kind: 0 White reached row 8 (1.0) | 1 Black reached row 0 (0.0) | 2 heuristic eval after
+ *         the ply budget (Quoridor.cpp:854) | 3 eval after a failed move pick (Quoridor.cpp:846-849)
+ *         | 4 UNI ply cap (0.5).  Tic-Tac-Toe: 0 x won, 1 o won, 2 draw.                         */
+typedef struct mctsb_outcome {
+    double   score;
+    uint16_t plies;               /* moves actually played in the playout                         */
+    uint8_t  kind;
+    uint8_t  reserved;
+    uint32_t draws;               /* u32 random draws consumed                                    */
+} mctsb_outcome;
+
+/* Exact per-leaf accumulator.  Every rollout score is a multiple of 2^-57 in [0,1], so the
+ * device accumulates the integer score*2^57 split in two 29-bit limbs; sums are exact and
+ * independent of thread / block / GPU order.  score_sum = (hi * 2^29 + lo) * 2^-57. */
+typedef struct mctsb_leaf_sum {
+    uint64_t lo;                  /* sum of (score*2^57) & (2^29-1)                               */
+    uint64_t hi;                  /* sum of (score*2^57) >> 29                                    */
+    uint64_t n;                   /* rollouts accumulated                                         */
+} mctsb_leaf_sum;
+
+typedef struct mctsb_backend mctsb_backend;   /* opaque; not thread-safe, distinct handles are independent */
+
+/* ---- lifetime ------------------------------------------------------------------------------
+ * Replaces the function-local `static JobScheduler scheduler` (mcts.cpp:60) and its
+ * constructor/destructor (JobScheduler.cpp:10-34).  `seed` keys the Philox4x32-10 streams. */
+int mctsb_create(mctsb_backend **out, int device, uint64_t seed);
+int mctsb_destroy(mctsb_backend *b);
+int mctsb_abi_version(void);
+const char *mctsb_strerror(int status);
+const char *mctsb_last_cuda_error(const mctsb_backend *b);
+int mctsb_device_count(int *count);
+
+/* ---- the hot path ---------------------------------------------------------------------------
+ * mctsb_submit replaces `scheduler.schedule(new RolloutJob(state, &results[i]))` for
+ * i < NUMBER_OF_THREADS (mcts.cpp:62-64): `n_leaves` packed leaf states (host memory, copied
+ * before return), `rollouts_per_leaf` independent playouts of each.  Rollout j of leaf i draws
+ * from Philox stream id `first_rollout_id + i*rollouts_per_leaf + j`, so a result does not
+ * depend on how rollouts are placed on threads, blocks or GPUs.
+ * mctsb_wait replaces `scheduler.waitUntilJobsHaveFinished()` plus the aggregation loop
+ * (mcts.cpp:66-75): it blocks, then fills `score_sum[i]` (double, correctly rounded exact sum)
+ * and/or `sums[i]` (exact integers); both may be NULL.  The caller then runs
+ * backpropagate(score_sum[i], rollouts_per_leaf) (mcts.cpp:76,83-90) on the host. */
+int mctsb_submit(mctsb_backend *b, int game, int policy,
+                 const void *leaf_states, int n_leaves,
+                 uint32_t rollouts_per_leaf, uint64_t first_rollout_id);
+int mctsb_wait(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums);
+
+/* Synchronous convenience: submit + wait (the shape of MCTS_node::rollout(), mcts.cpp:57-81). */
+int mctsb_rollout_batch(mctsb_backend *b, int game, int policy,
+                        const void *leaf_states, int n_leaves,
+                        uint32_t rollouts_per_leaf, uint64_t first_rollout_id,
+                        double *score_sum, mctsb_leaf_sum *sums);
+
+/* Parity mode: one outcome record per rollout (n_leaves*rollouts_per_leaf records, leaf-major),
+ * and optionally the final position of every Quoridor playout.  Replaces `*score =
+ * state->rollout()` of RolloutJob::run (mcts.h:87-90) one to one. */
+int mctsb_rollout_outcomes(mctsb_backend *b, int game, int policy,
+                           const void *leaf_states, int n_leaves,
+                           uint32_t rollouts_per_leaf, uint64_t first_rollout_id,
+                           mctsb_outcome *outcomes, void *final_states /* nullable */);
+
+/* Replay mode: the random draws come from caller-supplied u32 streams instead of Philox
+ * (stream i has `stream_len` words starting at streams + i*stream_stride, read modulo
+ * stream_len).  One rollout per (state, stream) pair; used for the bit-exact comparison with the
+ * reference compiled against the same pre-drawn stream. */
+int mctsb_rollout_replay(mctsb_backend *b, int game, int policy,
+                         const void *states, int n,
+                         const uint32_t *streams, uint32_t stream_len, uint32_t stream_stride,
+                         mctsb_outcome *outcomes, void *final_states /* nullable */);
+
+/* ---- rule primitives (corpus parity; later: batched node expansion) ----------------------
+ * For each Quoridor state: legal[i*4..i*4+3] = 209-bit mask of legal canonical moves for the
+ * side to move (legal_move, Quoridor.cpp:331-342 with check_blocking=true), i.e. the set
+ * generate_all_moves enumerates (Quoridor.cpp:594-616); info[i] = {winner 0 none/1 W/2 B
+ * (check_winner, Quoridor.cpp:40-44), shortest path W, shortest path B (get_shortest_path,
+ * Quoridor.cpp:108-174; -1 unreachable), force_playwall (Quoridor.cpp:666-678)};
+ * eval[i] = evaluate_position (Quoridor.cpp:629-664).  Any output pointer may be NULL. */
+typedef struct mctsb_qinfo {
+    int8_t winner;
+    int8_t sp_white;
+    int8_t sp_black;
+    int8_t force_playwall;
+} mctsb_qinfo;
+int mctsb_q_movegen(mctsb_backend *b, const mctsb_qstate *states, int n,
+                    uint64_t *legal /* n*4 */, mctsb_qinfo *info /* n */, double *eval /* n */);
+
+/* Batched next_state (Quoridor.cpp:506-510 -> play_move, Quoridor.cpp:344-392): out[i] =
+ * states[i] after canonical move ids[i]; ok[i] = 0 when the move is illegal (state unchanged). */
+int mctsb_q_play(mctsb_backend *b, const mctsb_qstate *states, const int32_t *move_ids, int n,
+                 mctsb_qstate *out, uint8_t *ok);
+
+/* ---- device-resident throughput path (bench `value`, no host copies in the timed region) ---
+ * Runs `n_leaves*rollouts_per_leaf` rollouts from states already uploaded with
+ * mctsb_upload_states; results stay on the device until mctsb_wait.  `elapsed_ms` (nullable)
+ * receives the CUDA-event time of the kernel(s) on the backend stream. */
+int mctsb_upload_states(mctsb_backend *b, int game, const void *leaf_states, int n_leaves);
+int mctsb_run_resident(mctsb_backend *b, int game, int policy, uint32_t rollouts_per_leaf,
+                       uint64_t first_rollout_id, float *elapsed_ms);
+
+/* Integer-issue peak microbenchmark (the roofline denominator): independent
+ * LOP3/IADD3 chains on every SM.  Returns thread-level integer ops per second. */
+int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms);
+
+/* Counters of the last kernel launch(es): launches issued by this backend since creation, and
+ * the executed-work counters the rollout kernel accumulates (flood-fill steps, plies). */
+typedef struct mctsb_counters {
+    uint64_t kernel_launches;
+    uint64_t rollouts;
+    uint64_t plies;
+    uint64_t flood_steps;      /* frontier-expansion iterations executed                         */
+    uint64_t flood_queries;    /* shortest-path / reachability queries executed                  */
+} mctsb_counters;
+int mctsb_get_counters(mctsb_backend *b, mctsb_counters *out);
+
+/* Helpers shared by hosts: exact sum -> double, and the reference's score for one record. */
+double mctsb_leaf_sum_to_double(const mctsb_leaf_sum *s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MCTSB_H */
