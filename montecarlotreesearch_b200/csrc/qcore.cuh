@@ -1,0 +1,511 @@
+// qcore.cuh — Quoridor rules and the reference rollout policy on register-resident bitboards.
+//
+// One rollout keeps its whole position in registers: two pawn cells, two wall counts, two 64-bit
+// wall-anchor masks and two 81-bit "edge open" boards (3 x u32 each).  Shortest paths — the
+// reference's per-move BFS with ten heap allocations (reference examples/Quoridor/Quoridor.cpp:
+// 46-106) — become a bitboard flood fill: one frontier expansion of the whole 9x9 board is ~27
+// integer instructions, and the BFS distance is the number of expansions until the goal row is hit.
+//
+// Everything here is `__host__ __device__` so that the host game class (host/Quoridor.cpp: move
+// generation for the tree) and the kernels share one definition of the rules.  Rollouts themselves
+// are only ever executed by the kernels (rollout_kernels.cu); there is no CPU rollout path in the
+// product.
+//
+// Board geometry (identical to the reference, Quoridor.cpp:18,41-42): cell (x,y) = row x, column y,
+// bit index 9*x+y.  White starts (0,4), goal row 8; Black starts (8,4), goal row 0.
+#pragma once
+#include <stdint.h>
+#include "../../include/mctsb.h"
+#include "philox.cuh"
+
+namespace mctsb {
+
+// ------------------------------------------------------------------------------------------------
+// 81-bit board in three 32-bit words: a = cells 0..31, b = 32..63, c = 64..80.
+// ------------------------------------------------------------------------------------------------
+struct B81 { uint32_t a, b, c; };
+
+MC_HD uint32_t fsl(uint32_t lo, uint32_t hi, int n) {   // high word of (hi:lo) << n, 0 < n < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_l(lo, hi, n);
+#else
+    return (hi << n) | (lo >> (32 - n));
+#endif
+}
+MC_HD uint32_t fsr(uint32_t lo, uint32_t hi, int n) {   // low word of (hi:lo) >> n, 0 < n < 32
+#if defined(__CUDA_ARCH__)
+    return __funnelshift_r(lo, hi, n);
+#else
+    return (lo >> n) | (hi << (32 - n));
+#endif
+}
+MC_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+MC_HD int ctz32(uint32_t v) {   // v != 0
+#if defined(__CUDA_ARCH__)
+    return __ffs((int)v) - 1;
+#else
+    return __builtin_ctz(v);
+#endif
+}
+
+MC_HD B81 b81(uint32_t a, uint32_t b, uint32_t c) { B81 r; r.a = a; r.b = b; r.c = c; return r; }
+MC_HD B81 operator&(B81 x, B81 y) { return b81(x.a & y.a, x.b & y.b, x.c & y.c); }
+MC_HD B81 operator|(B81 x, B81 y) { return b81(x.a | y.a, x.b | y.b, x.c | y.c); }
+MC_HD B81 andn(B81 x, B81 y) { return b81(x.a & ~y.a, x.b & ~y.b, x.c & ~y.c); }
+MC_HD bool b81_eq(B81 x, B81 y) { return ((x.a ^ y.a) | (x.b ^ y.b) | (x.c ^ y.c)) == 0; }
+MC_HD bool b81_any(B81 x) { return (x.a | x.b | x.c) != 0; }
+template <int N> MC_HD B81 shl(B81 v) { return b81(v.a << N, fsl(v.a, v.b, N), fsl(v.b, v.c, N)); }
+template <int N> MC_HD B81 shr(B81 v) { return b81(fsr(v.a, v.b, N), fsr(v.b, v.c, N), v.c >> N); }
+
+// `bits` (< 2^18) shifted to cell `pos` (0..80) as a board; bits running past cell 95 are dropped
+MC_HD B81 b81_shifted(uint32_t bits, int pos) {
+    int w = pos >> 5, sh = pos & 31;
+    uint32_t lo = bits << sh, hi = sh ? bits >> (32 - sh) : 0u;
+    return w == 0 ? b81(lo, hi, 0u) : w == 1 ? b81(0u, lo, hi) : b81(0u, 0u, lo);
+}
+MC_HD B81 b81_bit(int pos) { return b81_shifted(1u, pos); }
+MC_HD bool b81_test(B81 v, int pos) {
+    uint32_t w = pos < 32 ? v.a : pos < 64 ? v.b : v.c;
+    return (w >> (pos & 31)) & 1u;
+}
+
+// cells 0..71 (rows 0..7) and all cells whose column is not 8
+#define MCTSB_ROWS07 b81(0xffffffffu, 0xffffffffu, 0x000000ffu)
+#define MCTSB_COLS07 b81(0xfbfdfeffu, 0xbfdfeff7u, 0x0000ff7fu)
+#define MCTSB_GOAL_W_C 0x0001ff00u   // row 8 lives in word c, bits 8..16
+#define MCTSB_GOAL_B_A 0x000001ffu   // row 0 lives in word a, bits 0..8
+
+// ------------------------------------------------------------------------------------------------
+// Working position.  Replaces Quoridor_state's members (Quoridor.h:32-48): walls[9][9] and
+// wall_connections[8][8] are implied by the two anchor masks; the lazily cached BFS maps
+// wdists/bdists shrink to two cached path lengths (only the scalar is ever consumed).
+// ------------------------------------------------------------------------------------------------
+struct QState {
+    uint64_t hanc, vanc;   // wall anchors, bit 8*x+y
+    B81 openS;             // cell c may step to c+9 (no 'h' segment under it, not the last row)
+    B81 openE;             // cell c may step to c+1 (no 'v' segment right of it, not the last column)
+    int8_t cell[2];        // pawn cells: [0] White, [1] Black
+    int8_t nwalls[2];      // wwallsno, bwallsno
+    int8_t turn;           // 0 White to move, 1 Black
+    int8_t sp[2];          // cached shortest paths (get_shortest_path(player), Quoridor.cpp:111-131); -2 = stale
+    uint32_t move_counter;
+};
+
+struct QWork {             // executed-work counters
+    uint32_t flood_steps, flood_queries, plies;
+};
+
+MC_HD void q_add_wall_edges(QState &s, int anchor, bool horizontal) {
+    int x = anchor >> 3, y = anchor & 7, pos = 9 * x + y;
+    if (horizontal) s.openS = andn(s.openS, b81_shifted(0x3u, pos));      // cells (x,y),(x,y+1) lose their south edge
+    else            s.openE = andn(s.openE, b81_shifted(0x201u, pos));    // cells (x,y),(x+1,y) lose their east edge
+}
+
+MC_HD bool q_unpack(QState &s, const mctsb_qstate &p) {
+    s.hanc = p.h_anchor; s.vanc = p.v_anchor;
+    s.openS = MCTSB_ROWS07; s.openE = MCTSB_COLS07;
+    for (int x = 0; x < 8; x++) {
+        uint32_t hrow = (uint32_t)(p.h_anchor >> (8 * x)) & 0xffu;
+        uint32_t vrow = (uint32_t)(p.v_anchor >> (8 * x)) & 0xffu;
+        s.openS = andn(s.openS, b81_shifted(hrow | (hrow << 1), 9 * x));
+        s.openE = andn(s.openE, b81_shifted(vrow | (vrow << 9), 9 * x));
+    }
+    s.cell[0] = (int8_t)(p.wx * 9 + p.wy); s.cell[1] = (int8_t)(p.bx * 9 + p.by);
+    s.nwalls[0] = (int8_t)p.wwalls; s.nwalls[1] = (int8_t)p.bwalls;
+    s.turn = p.turn ? 1 : 0;
+    s.sp[0] = s.sp[1] = -2;
+    s.move_counter = p.move_counter;
+    return p.wx < 9 && p.wy < 9 && p.bx < 9 && p.by < 9 && p.wwalls <= 10 && p.bwalls <= 10 &&
+           !(p.wx == p.bx && p.wy == p.by) && p.flags == 0;
+}
+
+MC_HD void q_pack(const QState &s, mctsb_qstate &p) {
+    p.h_anchor = s.hanc; p.v_anchor = s.vanc;
+    p.wx = (uint8_t)(s.cell[0] / 9); p.wy = (uint8_t)(s.cell[0] % 9);
+    p.bx = (uint8_t)(s.cell[1] / 9); p.by = (uint8_t)(s.cell[1] % 9);
+    p.wwalls = (uint8_t)s.nwalls[0]; p.bwalls = (uint8_t)s.nwalls[1];
+    p.turn = (uint8_t)s.turn; p.flags = 0; p.move_counter = s.move_counter; p.reserved = 0;
+}
+
+// check_winner, Quoridor.cpp:40-44 (White tested first): 0 none, 1 White, 2 Black
+MC_HD int q_winner(const QState &s) {
+    if (s.cell[0] >= 72) return 1;
+    if (s.cell[1] < 9) return 2;
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Flood fill.  One call = one frontier expansion of all 81 cells in the four directions; replaces
+// one BFS level of calculate_dists_from (Quoridor.cpp:80-104).
+// ------------------------------------------------------------------------------------------------
+MC_HD B81 q_flood_step(B81 r, B81 oS, B81 oE) {
+    B81 south = shl<9>(r & oS);           // x -> x+1
+    B81 north = shr<9>(r) & oS;           // x -> x-1 : the cell above must have an open south edge
+    B81 east  = shl<1>(r & oE);           // y -> y+1
+    B81 west  = shr<1>(r) & oE;           // y -> y-1
+    return b81(r.a | south.a | north.a | east.a | west.a,
+               r.b | south.b | north.b | east.b | west.b,
+               r.c | south.c | north.c | east.c | west.c);
+}
+
+// Shortest path length from `start` to `player`'s goal row ignoring pawns, -1 if walled off:
+// get_shortest_path / calculate_dists_from(stop_at_goal=true), Quoridor.cpp:46-106,161-169.
+MC_HD int q_flood_dist(B81 oS, B81 oE, int start, int player, QWork *wk) {
+    B81 r = b81_bit(start);
+    const uint32_t ga = player ? MCTSB_GOAL_B_A : 0u, gc = player ? 0u : MCTSB_GOAL_W_C;
+    if (wk) wk->flood_queries++;
+    if ((r.a & ga) | (r.c & gc)) return 0;
+    for (int d = 1;; d++) {
+        B81 n = q_flood_step(r, oS, oE);
+        if (wk) wk->flood_steps++;
+        if ((n.a & ga) | (n.c & gc)) return d;
+        if (b81_eq(n, r)) return -1;
+        r = n;
+    }
+}
+
+// get_shortest_path(player) with the wdists/bdists cache semantics (Quoridor.cpp:111-131)
+MC_HD int q_sp(QState &s, int player, QWork *wk) {
+    if (s.sp[player] == -2) s.sp[player] = (int8_t)q_flood_dist(s.openS, s.openE, s.cell[player], player, wk);
+    return s.sp[player];
+}
+
+// get_shortest_path(player, extra wall), Quoridor.cpp:138-156: the wall is added to a register copy
+// of the edge boards, nothing to undo.  k = 2*anchor + (0 horizontal | 1 vertical).
+MC_HD int q_sp_with_wall(const QState &s, int player, int k, QWork *wk) {
+    int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
+    B81 oS = s.openS, oE = s.openE;
+    if (k & 1) oE = andn(oE, b81_shifted(0x201u, pos));
+    else       oS = andn(oS, b81_shifted(0x3u, pos));
+    return q_flood_dist(oS, oE, s.cell[player], player, wk);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Wall legality without the path test: legal_wall(..., check_blocking=false), Quoridor.cpp:291-303,
+// for all 64 anchors of one orientation at once.  A horizontal wall at (x,y) needs segments (x,y)
+// and (x,y+1) free and no vertical wall anchored at the same lattice point; in anchor terms: no
+// horizontal anchor at (x,y-1),(x,y),(x,y+1) and no vertical anchor at (x,y).  Mirror for vertical.
+// ------------------------------------------------------------------------------------------------
+MC_HD void q_cheap_wall_masks(const QState &s, uint64_t &legal_h, uint64_t &legal_v) {
+    if (s.nwalls[s.turn] <= 0) { legal_h = legal_v = 0; return; }
+    const uint64_t col0 = 0x0101010101010101ull, col7 = 0x8080808080808080ull;
+    uint64_t H = s.hanc, V = s.vanc;
+    legal_h = ~(H | ((H << 1) & ~col0) | ((H >> 1) & ~col7) | V);
+    legal_v = ~(V | (V << 8) | (V >> 8) | H);
+}
+
+// Pawn steps.  The 12 candidates in the order of get_legal_step_moves2 (Quoridor.cpp:461-472):
+// (-1,0),(-2,0),(+1,0),(+2,0),(0,-1),(0,-2),(0,+1),(0,+2),(-1,-1),(-1,+1),(+1,-1),(+1,+1); target
+// cell of candidate i = mover cell + q_step_delta(i).  Returns the 12-bit mask of legal ones
+// (legal_step, Quoridor.cpp:200-287) for the side to move.
+MC_HD int q_step_delta(int i) {
+    // 9*dx+dy for the 12 candidates
+    const int d[12] = {-9, -18, 9, 18, -1, -2, 1, 2, -10, -8, 8, 10};
+    return d[i];
+}
+
+// 4-bit mask N,S,W,E of the directions a pawn on cell c can move in (board edge or wall blocks)
+MC_HD uint32_t q_moves_from(const QState &s, int c) {
+    uint32_t m = 0;
+    if (c >= 9 && b81_test(s.openS, c - 9)) m |= 1u;   // north
+    if (b81_test(s.openS, c)) m |= 2u;                  // south
+    if (c >= 1 && b81_test(s.openE, c - 1)) m |= 4u;   // west (openE is 0 on column 8, so no wrap)
+    if (b81_test(s.openE, c)) m |= 8u;                  // east
+    return m;
+}
+
+MC_HD uint32_t q_step_mask(const QState &s) {
+    int me = s.cell[s.turn], en = s.cell[1 - s.turn];
+    uint32_t mm = q_moves_from(s, me), em = q_moves_from(s, en);
+    bool aN = (mm & 1u) && en == me - 9, aS = (mm & 2u) && en == me + 9;
+    bool aW = (mm & 4u) && en == me - 1, aE = (mm & 8u) && en == me + 1;
+    bool eN = em & 1u, eS = em & 2u, eW = em & 4u, eE = em & 8u;
+    uint32_t r = 0;
+    if ((mm & 1u) && !aN) r |= 1u << 0;
+    if (aN && eN)         r |= 1u << 1;
+    if ((mm & 2u) && !aS) r |= 1u << 2;
+    if (aS && eS)         r |= 1u << 3;
+    if ((mm & 4u) && !aW) r |= 1u << 4;
+    if (aW && eW)         r |= 1u << 5;
+    if ((mm & 8u) && !aE) r |= 1u << 6;
+    if (aE && eE)         r |= 1u << 7;
+    // diagonal jumps: the enemy is adjacent, the square behind it is closed, the sidestep is open
+    if ((aN && !eN && eW) || (aW && !eW && eN)) r |= 1u << 8;    // (-1,-1)
+    if ((aN && !eN && eE) || (aE && !eE && eN)) r |= 1u << 9;    // (-1,+1)
+    if ((aS && !eS && eW) || (aW && !eW && eS)) r |= 1u << 10;   // (+1,-1)
+    if ((aS && !eS && eE) || (aE && !eE && eS)) r |= 1u << 11;   // (+1,+1)
+    return r;
+}
+
+// Full wall legality (legal_wall with check_blocking=true, Quoridor.cpp:289-329): cheap test and
+// both pawns keep a path.  The reference skips the path test for "isolated" walls; that shortcut
+// never changes the answer (a wall touching nothing cannot close a region), so the flood fill may
+// simply be run on every cheap-legal candidate.
+MC_HD bool q_wall_keeps_paths(const QState &s, int k, QWork *wk) {
+    return q_sp_with_wall(s, 0, k, wk) >= 0 && q_sp_with_wall(s, 1, k, wk) >= 0;
+}
+
+// get_best_step_move, Quoridor.cpp:476-497: candidates in REVERSED list order (push_front), first
+// strict minimum of the shortest path from the target; -1 when no legal step exists.
+MC_HD int q_best_step(const QState &s, uint32_t steps, QWork *wk) {
+    int me = s.cell[s.turn], best = -1, mn = 9999999;
+    for (int i = 11; i >= 0; i--) {
+        if (!((steps >> i) & 1u)) continue;
+        int t = me + q_step_delta(i);
+        int path = q_flood_dist(s.openS, s.openE, t, s.turn, wk);
+        if (path >= 0 && path < mn) { mn = path; best = t; }
+    }
+    return best;
+}
+
+// play_move, Quoridor.cpp:344-392, for a move already known to be legal.
+MC_HD void q_play_step(QState &s, int target_cell) {
+    s.cell[s.turn] = (int8_t)target_cell;
+    s.sp[s.turn] = -2;
+    s.turn ^= 1; s.move_counter++;
+}
+MC_HD void q_play_wall(QState &s, int k) {
+    int anchor = k >> 1;
+    if (k & 1) s.vanc |= 1ull << anchor; else s.hanc |= 1ull << anchor;
+    q_add_wall_edges(s, anchor, !(k & 1));
+    s.nwalls[s.turn]--;
+    s.sp[0] = s.sp[1] = -2;
+    s.turn ^= 1; s.move_counter++;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp64 without contraction: the host reference is compiled without FMA, so every product and sum
+// is rounded separately; on the device that has to be spelled out.
+// ------------------------------------------------------------------------------------------------
+MC_HD double d_mul(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dmul_rn(a, b);
+#else
+    volatile double r = a * b; return r;
+#endif
+}
+MC_HD double d_add(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __dadd_rn(a, b);
+#else
+    volatile double r = a + b; return r;
+#endif
+}
+MC_HD double d_div(double a, double b) {
+#if defined(__CUDA_ARCH__)
+    return __ddiv_rn(a, b);
+#else
+    volatile double r = a / b; return r;
+#endif
+}
+
+// evaluate_position, Quoridor.cpp:629-664, bug-faithful (MAX instead of MIN at :661).
+MC_HD double q_eval_from(int wp, int bp, int w, int b, int turn) {
+    bool white_ahead = wp + (turn != 0) <= bp - 1;
+    bool black_ahead = bp + (turn != 1) <= wp - 1;
+    if (b <= 0 && white_ahead) return 0.95;
+    if (w <= 0 && black_ahead) return 1.0 - 0.95;
+    if (b <= 1 && w >= 2 && white_ahead) return 0.95 - 0.1;
+    if (w <= 1 && b >= 2 && black_ahead) return 1.0 - (0.95 - 0.1);
+    double wallsdiff = 0.0;
+    int mx = w > b ? w : b;
+    if (mx > 0) {
+        double q = d_div((double)((w - b) * (w - b)), (double)(mx * mx));
+        wallsdiff = (w > b) ? q : -q;
+    }
+    double path_diff = (double)(bp - wp) + (turn == 0 ? 0.5 : -0.5);     // exact
+    double distance = d_div(path_diff > 10.0 ? path_diff : 10.0, 10.0);
+    return d_add(d_add(0.5, d_mul(0.2, wallsdiff)), d_mul(0.2, distance));
+}
+MC_HD double q_eval(QState &s, QWork *wk) {
+    int wp = q_sp(s, 0, wk), bp = q_sp(s, 1, wk);
+    return q_eval_from(wp, bp, s.nwalls[0], s.nwalls[1], s.turn);
+}
+
+// force_playwall, Quoridor.cpp:666-678
+MC_HD bool q_force_playwall(QState &s, QWork *wk) {
+    int p = s.turn, e = 1 - p;
+    int ours = q_sp(s, p, wk), theirs = q_sp(s, e, wk), ow = s.nwalls[p], ew = s.nwalls[e];
+    if (theirs <= 1 && ours > theirs) return true;
+    if (theirs <= 2 && ours > theirs + 1 && ow >= ew) return true;
+    if (theirs <= 3 && ours > theirs + 2 && ow > ew) return true;
+    return false;
+}
+
+// U() < p for p in {0.1, 0.75, 0.8}: u32*2^-32 < p  <=>  u32 < ceil(p*2^32) (p taken as the double)
+#define MCTSB_THR_0_10 429496730u
+#define MCTSB_THR_0_75 3221225472u
+#define MCTSB_THR_0_80 3435973837u
+
+// "Does this wall hurt the enemy more than the mover", shared by the best-wall and the guided
+// branch (Quoridor.cpp:728-733, 756-761).  Returns enemy_enc - our_enc (> 0) or 0 if rejected.
+MC_HD int q_wall_gain(QState &s, int k, QWork *wk) {
+    int p = s.turn, e = 1 - p;
+    int ep = q_sp_with_wall(s, e, k, wk);
+    int ee = ep - q_sp(s, e, wk);
+    if (!(ep >= 0 && ee > 0)) return 0;
+    int op = q_sp_with_wall(s, p, k, wk);
+    int oe = op - q_sp(s, p, wk);
+    if (!(op >= 0 && ee > oe)) return 0;
+    return ee - oe;
+}
+
+// Encoded move: 0..80 pawn target cell; 128 + k wall (k = 2*anchor + orientation); -1 none.
+MC_HD int q_move_to_id(int mv) {
+    if (mv < 0) return -1;
+    if (mv < 81) return mv;
+    int k = mv - 128;
+    return ((k & 1) ? 145 : 81) + (k >> 1);
+}
+
+// pick_semirandom_move, Quoridor.cpp:680-803, bug-faithful: the wall branch is
+// entered iff Black still has walls, one draw is consumed iff force_playwall() is false.
+template <class Draws>
+MC_HD int q_pick_semirandom(QState &s, Draws &d, uint8_t *pool, QWork *wk) {
+    int e = 1 - s.turn;
+    if (!q_force_playwall(s, wk)) (void)d.next();
+    if (s.nwalls[1] != 0) {
+        uint64_t lh, lv;
+        q_cheap_wall_masks(s, lh, lv);
+        int n = 0;
+        for (int a = 0; a < 64; a++) {                       // pool order: i, j, (h, v)  (:709-718)
+            if ((lh >> a) & 1ull) pool[n++] = (uint8_t)(2 * a);
+            if ((lv >> a) & 1ull) pool[n++] = (uint8_t)(2 * a + 1);
+        }
+        for (int i = 0; i + 1 < n; i++) {                    // our shuffle (:720)
+            int j = i + (int)mulhi_u32(d.next(), (uint32_t)(n - i));
+            uint8_t t = pool[i]; pool[i] = pool[j]; pool[j] = t;
+        }
+        if (d.next() < MCTSB_THR_0_10) {                     // best wall (:721-746)
+            int best = -1, maxdiff = 0;
+            for (int i = 0; i < n; i++) { int g = q_wall_gain(s, pool[i], wk); if (g > maxdiff) { maxdiff = g; best = pool[i]; } }
+            if (best >= 0) return 128 + best;
+        } else if (d.next() < MCTSB_THR_0_75) {              // guided (:748-772)
+            for (int i = 0; i < n; i++) if (q_wall_gain(s, pool[i], wk) > 0) return 128 + pool[i];
+        } else {                                             // first fully legal (:773-788)
+            for (int i = 0; i < n; i++) if (q_wall_keeps_paths(s, pool[i], wk)) return 128 + pool[i];
+        }
+    }
+    uint32_t steps = q_step_mask(s);
+    if (s.nwalls[e] == 0 || d.next() < MCTSB_THR_0_80) return q_best_step(s, steps, wk);   // :792-793
+    uint32_t r = d.next() & 0x7fffffffu;                     // rand() (:796)
+    int n = popc32(steps);
+    if (n == 0) return -1;                                   // the reference divides by zero here
+    int idx = (int)(r % (uint32_t)n);
+    for (int i = 0; i < 12; i++) if ((steps >> i) & 1u) { if (idx == 0) return s.cell[s.turn] + q_step_delta(i); idx--; }
+    return -1;
+}
+
+MC_HD void q_play_encoded(QState &s, int mv) {
+    if (mv < 81) q_play_step(s, mv); else q_play_wall(s, mv - 128);
+}
+
+// Quoridor_state::rollout, Quoridor.cpp:809-855: at most 50 plies of the policy above, terminal
+// test at the top of each ply only, heuristic evaluation afterwards.  The evaluation inside the
+// loop (:826-829) can never stop the playout and has no side effect besides filling the path
+// cache, so it is not computed here.
+template <class Draws>
+MC_HD double q_rollout_ref(QState &s, Draws &d, uint8_t *pool, int &plies, int &kind, QWork *wk) {
+    plies = 0; kind = 2;
+    for (int i = 0; i < 50; i++) {
+        int w = q_winner(s);
+        if (w) { kind = w == 1 ? 0 : 1; return w == 1 ? 1.0 : 0.0; }
+        int mv = q_pick_semirandom(s, d, pool, wk);
+        if (mv < 0) { kind = 3; break; }
+        q_play_encoded(s, mv);
+        plies++;
+    }
+    return q_eval(s, wk);
+}
+
+// ------------------------------------------------------------------------------------------------
+// All legal moves of the side to move: the set generate_all_moves enumerates (Quoridor.cpp:594-616),
+// as the 12-bit step mask plus one 64-bit anchor mask per wall orientation.  Thread-serial version
+// (host class, UNI policy); the movegen kernel spreads the 128 wall candidates over a warp.
+// ------------------------------------------------------------------------------------------------
+MC_HD void q_legal_parts(const QState &s, uint32_t &steps, uint64_t &legal_h, uint64_t &legal_v, QWork *wk) {
+    steps = q_step_mask(s);
+    uint64_t lh, lv;
+    q_cheap_wall_masks(s, lh, lv);
+    legal_h = legal_v = 0;
+    for (int a = 0; a < 64; a++) {
+        if (((lh >> a) & 1ull) && q_wall_keeps_paths(s, 2 * a, wk)) legal_h |= 1ull << a;
+        if (((lv >> a) & 1ull) && q_wall_keeps_paths(s, 2 * a + 1, wk)) legal_v |= 1ull << a;
+    }
+}
+
+// the same set as a 209-bit mask over canonical move ids (include/mctsb.h)
+MC_HD void q_parts_to_mask(const QState &s, uint32_t steps, uint64_t legal_h, uint64_t legal_v, uint64_t *mask4) {
+    mask4[0] = mask4[1] = mask4[2] = mask4[3] = 0;
+    for (int i = 0; i < 12; i++) if ((steps >> i) & 1u) { int id = s.cell[s.turn] + q_step_delta(i); mask4[id >> 6] |= 1ull << (id & 63); }
+    // ids 81..144 = horizontal anchors, 145..208 = vertical anchors
+    mask4[1] |= legal_h << 17; mask4[2] |= legal_h >> 47;
+    mask4[2] |= legal_v << 17; mask4[3] |= legal_v >> 47;
+}
+
+MC_HD void q_legal_moves(const QState &s, uint64_t *mask4) {
+    uint32_t steps; uint64_t lh, lv;
+    q_legal_parts(s, steps, lh, lv, nullptr);
+    q_parts_to_mask(s, steps, lh, lv, mask4);
+}
+
+// idx-th move in generate_all_moves order: steps in reversed candidate order (push_front,
+// Quoridor.cpp:442-453), then anchors row-major with horizontal before vertical (:604-612).
+// Returns the encoded move (cell, or 128 + k).
+MC_HD int q_nth_move(const QState &s, uint32_t steps, uint64_t legal_h, uint64_t legal_v, int idx) {
+    for (int i = 11; i >= 0; i--) if ((steps >> i) & 1u) { if (idx == 0) return s.cell[s.turn] + q_step_delta(i); idx--; }
+    for (int a = 0; a < 64; a++) {
+        if ((legal_h >> a) & 1ull) { if (idx == 0) return 128 + 2 * a; idx--; }
+        if ((legal_v >> a) & 1ull) { if (idx == 0) return 128 + 2 * a + 1; idx--; }
+    }
+    return -1;
+}
+
+MC_HD int popc64(uint64_t v) { return popc32((uint32_t)v) + popc32((uint32_t)(v >> 32)); }
+
+// UNI policy (no reference function; oracle = loop over the reference's public API): uniformly
+// random legal move per ply, idx = mulhi(draw, |L|), ply cap MCTSB_UNI_MAX_PLIES scoring 0.5.
+template <class Draws>
+MC_HD double q_rollout_uni(QState &s, Draws &d, int &plies, int &kind, QWork *wk) {
+    plies = 0; kind = 4;
+    for (;;) {
+        int w = q_winner(s);
+        if (w) { kind = w == 1 ? 0 : 1; return w == 1 ? 1.0 : 0.0; }
+        if (plies >= MCTSB_UNI_MAX_PLIES) return 0.5;
+        uint32_t steps; uint64_t lh, lv;
+        q_legal_parts(s, steps, lh, lv, wk);
+        int n = popc32(steps) + popc64(lh) + popc64(lv);
+        if (n == 0) { kind = 3; return 0.5; }
+        int mv = q_nth_move(s, steps, lh, lv, (int)mulhi_u32(d.next(), (uint32_t)n));
+        if (mv < 81) q_play_step(s, mv); else q_play_wall(s, mv - 128);
+        plies++;
+    }
+}
+
+// legal_move, Quoridor.cpp:331-342, for one canonical id
+MC_HD bool q_legal_move(const QState &s, int id) {
+    if (id < 0 || id >= MCTSB_Q_NUM_MOVES) return false;
+    if (id < 81) {
+        uint32_t steps = q_step_mask(s);
+        for (int i = 0; i < 12; i++) if (((steps >> i) & 1u) && s.cell[s.turn] + q_step_delta(i) == id) return true;
+        return false;
+    }
+    uint64_t lh, lv;
+    q_cheap_wall_masks(s, lh, lv);
+    int a = id < 145 ? id - 81 : id - 145, k = 2 * a + (id < 145 ? 0 : 1);
+    if (!(((id < 145 ? lh : lv) >> a) & 1ull)) return false;
+    return q_wall_keeps_paths(s, k, nullptr);
+}
+
+MC_HD void q_play_id(QState &s, int id) {    // canonical id, already known legal
+    if (id < 81) q_play_step(s, id);
+    else q_play_wall(s, id < 145 ? 2 * (id - 81) : 2 * (id - 145) + 1);
+}
+
+}  // namespace mctsb

@@ -1,0 +1,92 @@
+"""ctypes bindings of the TEST-ONLY host compile of the device core (tests/hostemu/hostemu.cpp)."""
+import ctypes as C
+
+import numpy as np
+
+from oracle.reflib import OUTCOME_DTYPE, QSTATE_DTYPE
+from oracle.portlib import TSTATE_DTYPE
+from .build import build
+
+
+class EmuLib:
+    def __init__(self):
+        self.lib = L = C.CDLL(build())
+        vp = C.c_void_p
+        L.emu_q_primitives.argtypes = [vp] * 6
+        L.emu_q_sp_with_wall.argtypes = [vp, C.c_int, C.c_int]
+        L.emu_q_sp_from.argtypes = [vp, C.c_int, C.c_int]
+        L.emu_q_best_step.argtypes = [vp]
+        L.emu_q_play.argtypes = [vp, C.c_int, vp]
+        L.emu_q_rollout_streams.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, C.c_uint32, vp, vp, vp]
+        L.emu_q_rollout_philox.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]
+        L.emu_t_rollout_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, vp]
+        L.emu_t_rollout_streams.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]
+        L.emu_t_winner.argtypes = [C.c_uint32, C.c_uint32]
+
+    def q_primitives(self, s):
+        a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
+        info = np.zeros(4, dtype=np.int32)
+        legal4 = np.zeros(4, dtype=np.uint64)
+        ev = C.c_double(0)
+        cheap2 = np.zeros(2, dtype=np.uint64)
+        steps = np.zeros(12, dtype=np.int32)
+        self.lib.emu_q_primitives(a.ctypes.data, info.ctypes.data, legal4.ctypes.data, C.addressof(ev),
+                                  cheap2.ctypes.data, steps.ctypes.data)
+        legal = np.array([(int(legal4[i >> 6]) >> (i & 63)) & 1 for i in range(209)], dtype=np.uint8)
+        cheap = np.zeros(128, dtype=np.uint8)
+        for a_ in range(64):
+            cheap[2 * a_] = (int(cheap2[0]) >> a_) & 1
+            cheap[2 * a_ + 1] = (int(cheap2[1]) >> a_) & 1
+        return {"winner": int(info[0]), "sp_white": int(info[1]), "sp_black": int(info[2]),
+                "force_playwall": int(info[3]), "eval": ev.value, "legal": legal, "cheap": cheap,
+                "steps2": steps[steps >= 0].copy()}
+
+    def q_sp_with_wall(self, s, black, wall_id):
+        a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
+        k = 2 * (wall_id - 81) if wall_id < 145 else 2 * (wall_id - 145) + 1
+        return self.lib.emu_q_sp_with_wall(a.ctypes.data, int(black), k)
+
+    def q_sp_from(self, s, black, x, y):
+        a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
+        return self.lib.emu_q_sp_from(a.ctypes.data, int(black), 9 * x + y)
+
+    def q_best_step(self, s):
+        a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
+        return self.lib.emu_q_best_step(a.ctypes.data)
+
+    def q_play(self, s, move_id):
+        a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
+        out = np.zeros((), dtype=QSTATE_DTYPE)
+        ok = self.lib.emu_q_play(a.ctypes.data, int(move_id), out.ctypes.data)
+        return bool(ok), out
+
+    def q_rollout_streams(self, states, streams, policy=0):
+        a = np.ascontiguousarray(states, dtype=QSTATE_DTYPE).reshape(-1)
+        st = np.ascontiguousarray(streams, dtype=np.uint32)
+        out = np.zeros(a.size, dtype=OUTCOME_DTYPE)
+        fin = np.zeros(a.size, dtype=QSTATE_DTYPE)
+        work = np.zeros(3, dtype=np.uint64)
+        self.lib.emu_q_rollout_streams(a.ctypes.data, policy, a.size, st.ctypes.data, st.shape[1], st.shape[1],
+                                       out.ctypes.data, fin.ctypes.data, work.ctypes.data)
+        return out, fin, work
+
+    def q_rollout_philox(self, s, seed, first_id, n, policy=0):
+        a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        fin = np.zeros(n, dtype=QSTATE_DTYPE)
+        work = np.zeros(3, dtype=np.uint64)
+        self.lib.emu_q_rollout_philox(a.ctypes.data, policy, seed, first_id, n, out.ctypes.data, fin.ctypes.data,
+                                      work.ctypes.data)
+        return out, fin, work
+
+    def t_rollout_philox(self, x, o, seed, first_id, n):
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        self.lib.emu_t_rollout_philox(x, o, seed, first_id, n, out.ctypes.data)
+        return out
+
+    def t_rollout_streams(self, states, streams):
+        a = np.ascontiguousarray(states, dtype=TSTATE_DTYPE).reshape(-1)
+        st = np.ascontiguousarray(streams, dtype=np.uint32)
+        out = np.zeros(a.size, dtype=OUTCOME_DTYPE)
+        self.lib.emu_t_rollout_streams(a.ctypes.data, a.size, st.ctypes.data, st.shape[1], st.shape[1], out.ctypes.data)
+        return out

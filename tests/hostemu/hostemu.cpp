@@ -1,0 +1,94 @@
+// hostemu.cpp — TEST-ONLY host compile of the device rule/rollout core (csrc/qcore.cuh, ttt_core.cuh)
+// so that the kernel logic can be checked bit-for-bit against the oracle on a machine without a
+// GPU.  It is built by tests/hostemu/build.py into tests/hostemu/_hostemu.so, is never linked
+// into the product library and is not reachable through the C ABI.
+#include "../../montecarlotreesearch_b200/csrc/qcore.cuh"
+#include "../../montecarlotreesearch_b200/csrc/ttt_core.cuh"
+#include <string.h>
+using namespace mctsb;
+
+extern "C" {
+
+int emu_q_primitives(const mctsb_qstate *p, int32_t *info, uint64_t *legal4, double *eval, uint64_t *cheap2,
+                     int32_t *steps12) {
+    QState s; q_unpack(s, *p);
+    info[0] = q_winner(s);
+    info[1] = q_sp(s, 0, nullptr);
+    info[2] = q_sp(s, 1, nullptr);
+    info[3] = q_force_playwall(s, nullptr);
+    *eval = q_eval(s, nullptr);
+    q_legal_moves(s, legal4);
+    q_cheap_wall_masks(s, cheap2[0], cheap2[1]);
+    uint32_t m = q_step_mask(s);
+    for (int i = 0; i < 12; i++) steps12[i] = ((m >> i) & 1u) ? s.cell[s.turn] + q_step_delta(i) : -1;
+    return 0;
+}
+
+int emu_q_sp_with_wall(const mctsb_qstate *p, int black, int k) { QState s; q_unpack(s, *p); return q_sp_with_wall(s, black, k, nullptr); }
+int emu_q_sp_from(const mctsb_qstate *p, int black, int cell) { QState s; q_unpack(s, *p); return q_flood_dist(s.openS, s.openE, cell, black, nullptr); }
+int emu_q_best_step(const mctsb_qstate *p) { QState s; q_unpack(s, *p); return q_best_step(s, q_step_mask(s), nullptr); }
+int emu_q_play(const mctsb_qstate *p, int id, mctsb_qstate *out) {
+    QState s; q_unpack(s, *p);
+    bool ok = q_legal_move(s, id);
+    if (ok) q_play_id(s, id);
+    q_pack(s, *out);
+    return ok;
+}
+
+int emu_q_rollout_streams(const mctsb_qstate *states, int policy, int n, const uint32_t *streams, uint32_t len,
+                          uint32_t stride, mctsb_outcome *out, mctsb_qstate *finals, uint64_t *work3) {
+    uint8_t pool[128];
+    for (int i = 0; i < n; i++) {
+        QState s; q_unpack(s, states[i]);
+        StreamDraws d; d.init(streams + (size_t)i * stride, len);
+        int plies = 0, kind = 0; QWork wk = {0, 0, 0};
+        double r = policy == MCTSB_POLICY_UNI ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+        memset(out + i, 0, sizeof *out);
+        out[i].score = r; out[i].plies = (uint16_t)plies; out[i].kind = (uint8_t)kind; out[i].draws = d.consumed();
+        if (finals) q_pack(s, finals[i]);
+        if (work3) { work3[0] += wk.flood_steps; work3[1] += wk.flood_queries; work3[2] += plies; }
+    }
+    return 0;
+}
+
+int emu_q_rollout_philox(const mctsb_qstate *state, int policy, uint64_t seed, uint64_t first_id, int n,
+                         mctsb_outcome *out, mctsb_qstate *finals, uint64_t *work3) {
+    uint8_t pool[128];
+    for (int i = 0; i < n; i++) {
+        QState s; q_unpack(s, *state);
+        PhiloxDraws d; d.init(seed, first_id + i);
+        int plies = 0, kind = 0; QWork wk = {0, 0, 0};
+        double r = policy == MCTSB_POLICY_UNI ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+        memset(out + i, 0, sizeof *out);
+        out[i].score = r; out[i].plies = (uint16_t)plies; out[i].kind = (uint8_t)kind; out[i].draws = d.consumed();
+        if (finals) q_pack(s, finals[i]);
+        if (work3) { work3[0] += wk.flood_steps; work3[1] += wk.flood_queries; work3[2] += plies; }
+    }
+    return 0;
+}
+
+int emu_t_rollout_philox(uint32_t x, uint32_t o, uint64_t seed, uint64_t first_id, int n, mctsb_outcome *out) {
+    for (int i = 0; i < n; i++) {
+        PhiloxDraws d; d.init(seed, first_id + i);
+        int plies = 0, kind = 0;
+        double r = t_rollout(x, o, d, plies, kind);
+        memset(out + i, 0, sizeof *out);
+        out[i].score = r; out[i].plies = (uint16_t)plies; out[i].kind = (uint8_t)kind; out[i].draws = d.consumed();
+    }
+    return 0;
+}
+
+int emu_t_rollout_streams(const mctsb_tstate *st, int n, const uint32_t *streams, uint32_t len, uint32_t stride, mctsb_outcome *out) {
+    for (int i = 0; i < n; i++) {
+        StreamDraws d; d.init(streams + (size_t)i * stride, len);
+        int plies = 0, kind = 0;
+        double r = t_rollout(st[i].x_mask, st[i].o_mask, d, plies, kind);
+        memset(out + i, 0, sizeof *out);
+        out[i].score = r; out[i].plies = (uint16_t)plies; out[i].kind = (uint8_t)kind; out[i].draws = d.consumed();
+    }
+    return 0;
+}
+
+int emu_t_winner(uint32_t x, uint32_t o) { return t_winner(x & 0x1ff, o & 0x1ff); }
+
+}
