@@ -1,0 +1,271 @@
+#!/usr/bin/env python
+"""bench.py — Quoridor 9x9 rollouts/sec on N B200s vs the reference's host-core JobScheduler.
+
+A "step" is one pass of the hot path over one batch: `--rollouts` (default 2^20, BASELINE.json
+configs[1]) independent REF-policy playouts (reference Quoridor_state::rollout semantics,
+Quoridor.cpp:809-855) of the opening position per GPU, each keyed by its own Philox stream id.
+
+  value : whole-job rollouts/s, state already resident in HBM, kernel timed with CUDA events on the
+          backend's stream (max over ranks, summed over the K steps).
+  e2e   : the same through the C-ABI call a host tree makes (mctsb_rollout_batch: host state in,
+          H2D, kernel, D2H of the exact per-leaf sums) timed on the host clock around the call.
+  roofline : the path is SM-integer-issue bound (no contraction, ~0 HBM traffic), so the
+          denominator is the measured integer-issue peak (mctsb_int_issue_peak, run live), and
+          `achieved` is algorithmic thread-level integer ops/s (DESIGN.md "Roofline").
+  cpu_baseline / --impl reference : the UNMODIFIED reference compiled in oracle/_ref
+          (RolloutJobs on its JobScheduler with every host core) timed on this box.
+
+N>1 (torchrun): weak scaling, every rank plays its own id range; one NCCL all-reduce of the exact
+integer root statistics per step is inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "quoridor_9x9_ref_policy_rollouts_per_sec"
+UNIT = "rollouts/s"
+# Algorithmic integer work of one REF-policy rollout from the opening position, counted by the
+# oracle (oracle/quoridor_oracle.c work counters, 1500 rollouts): 13 367 flood-fill steps x 24 ops
+# + 4 582 cheap wall tests x 12 ops + 49.1 plies x 200 ops (DESIGN.md "Roofline").
+ALG_OPS_PER_ROLLOUT = 13367 * 24 + 4582 * 12 + 49.1 * 200
+ALG_HBM_BYTES_PER_ROLLOUT = 24.0 / 1.0  # per LEAF: 32 B state in + 24 B sums out; per rollout ~0 at R = 2^20
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for name, v in zip(names, r[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
+                "reasons": sorted(reasons), "samples": len(self.rows),
+                "power_w_max": max((float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()), default=None)}
+
+
+def host_threads():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def reference_rollouts_per_sec(target_seconds, threads):
+    """RolloutJobs on the reference's own JobScheduler (mcts.cpp:60-66), all host threads, opening state."""
+    from oracle.reflib import RefLib
+    ref = RefLib("native")
+    calib_jobs = 200 * threads
+    secs, _ = ref.jobscheduler_bench(0, threads, calib_jobs)
+    rate = calib_jobs / secs
+    jobs = max(calib_jobs, int(rate * target_seconds))
+    secs, mean = ref.jobscheduler_bench(0, threads, jobs)
+    return jobs / secs, jobs, secs, mean
+
+
+def run_reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    threads = host_threads()
+    per_step = []
+    sample_jobs = 0
+    for i in range(args.warmup + args.steps):
+        rate, jobs, secs, mean = reference_rollouts_per_sec(4.0 if i >= args.warmup else 1.0, threads)
+        if i >= args.warmup:
+            per_step.append((jobs, secs))
+            sample_jobs = jobs
+    total_jobs = sum(j for j, _ in per_step)
+    total_secs = sum(s for _, s in per_step)
+    value = total_jobs / total_secs
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total_secs / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: Quoridor 9x9 opening position, REF policy rollouts (reference rollout())",
+                   "sample_rollouts_per_step": sample_jobs, "host_threads": threads},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
+                         "sample": "%d RolloutJobs per step on JobScheduler(%d), opening position, stock RNG" % (sample_jobs, threads)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rollouts", type=int, default=1 << 20, help="rollouts per step per GPU")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU sample for cpu_baseline")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import montecarlotreesearch_b200 as m
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    be = m.RolloutBackend(local_rank, m.DEFAULT_SEED)
+    state = m.quoridor_opening()
+    n = args.rollouts
+    G, P = m.GAME_QUORIDOR, m.POLICY_REF
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def first_id(step):
+        return (step * world + rank) * n
+
+    # ---- measured integer-issue peak (roofline denominator) -----------------------------------------
+    int_peak, _ = be.int_issue_peak()
+
+    # ---- device-resident throughput ("value") -------------------------------------------------------------
+    be.upload_states(G, state)
+    stats_dev = None
+    if dist is not None:
+        import torch
+        stats_dev = torch.zeros(3, dtype=torch.int64, device="cuda")
+    launches0 = be.counters()["kernel_launches"]
+    for w in range(args.warmup):
+        be.run_resident(G, P, n, first_id(w), timed=True)
+        be.wait()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    kernel_ms = []
+    t0 = time.perf_counter()
+    total_score = 0.0
+    for k in range(args.steps):
+        ms = be.run_resident(G, P, n, first_id(args.warmup + k), timed=True)
+        score, sums = be.wait()
+        if dist is not None:
+            import torch
+            stats_dev.copy_(torch.tensor([int(sums["lo"][0]), int(sums["hi"][0]), int(sums["n"][0])], dtype=torch.int64))
+            dist.all_reduce(stats_dev)          # exact integer merge of the root statistics
+            torch.cuda.synchronize()
+        kernel_ms.append(ms)
+        total_score += score[0]
+    barrier()
+    wall_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = be.counters()["kernel_launches"] - launches0 - args.warmup
+
+    dev_ms = float(sum(kernel_ms))
+    if dist is not None:
+        import torch
+        t = torch.tensor([dev_ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, wall_ms = float(t[0]), float(t[1])
+        step_ms = wall_ms            # at N>1 the step includes the all-reduce: use the bracketed wall time
+    else:
+        step_ms = dev_ms
+    total_rollouts = n * args.steps * world
+    value = total_rollouts / (step_ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers ----------------------------------------------------
+    states_host = np.array([state], dtype=m.QSTATE_DTYPE)
+    be.rollout_batch(G, P, states_host, n, first_id(1000))
+    barrier()
+    t0 = time.perf_counter()
+    for k in range(args.steps):
+        be.rollout_batch(G, P, states_host, n, first_id(2000 + k))
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        import torch
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t[0])
+    e2e_value = total_rollouts / e2e_s
+
+    counters = be.counters()
+    if rank != 0:
+        return
+
+    # ---- CPU baseline on this box's host cores (bounded sample) ------------------------------------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            threads = host_threads()
+            rate, jobs, secs, mean = reference_rollouts_per_sec(args.cpu_seconds, threads)
+            cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": "%d RolloutJobs on the reference JobScheduler(%d), opening position, %.1f s" % (jobs, threads, secs)}
+        except Exception as e:  # the compiled reference may be absent
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
+
+    per_gpu_rate = (n * args.steps) / (dev_ms * 1e-3)
+    achieved = per_gpu_rate * ALG_OPS_PER_ROLLOUT
+    exec_steps_per_rollout = counters["flood_steps"] / max(1, counters["rollouts"])
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "int32+f64", "data": "synthetic",
+        "config": {"workload": "configs[1]: Quoridor 9x9 opening position, %d independent REF-policy rollouts per GPU per step" % n,
+                   "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)",
+                   "rollouts_per_step_per_gpu": n, "leaves": 1, "seed": hex(m.DEFAULT_SEED),
+                   "l2": "inputs are one 32-byte state; the path is ALU-bound, nothing to flush; rollout ids differ every step"},
+        "roofline": {"bound": "sm_int_issue", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
+                     "frac": achieved / int_peak, "traffic": None,
+                     "alg_ops_per_rollout": ALG_OPS_PER_ROLLOUT, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
+                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3/IADD3 chains, all SMs)"},
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * world, "d2h_bytes_per_step": 24 * world},
+        "gpu_launches": int(launches),
+        "clocks": sampler.summary(),
+        "mean_score": total_score / (n * args.steps),
+        "kernel_ms_per_step": dev_ms / args.steps,
+    }
+    print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,216 @@
+"""montecarlotreesearch_b200 — B200-native rollout backend for the MCTS Simulation phase.
+
+Python is only the test/bench harness here: the product is the C-ABI shared library
+`libmctsb.so` (include/mctsb.h; CUDA kernels for sm_100a under csrc/) and the C++ host side that
+mirrors the reference's MCTS_state / MCTS_tree API (host/).  This module binds the C ABI with
+ctypes, one method per entry point.  There is no CPU fallback: if the library is missing, or no
+CUDA device is present, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG_DIR, "libmctsb.so")
+
+GAME_QUORIDOR, GAME_TICTACTOE = 0, 1
+POLICY_REF, POLICY_UNI = 0, 1
+NUM_MOVES = 209
+DEFAULT_SEED = 0x2026101900000001
+
+QSTATE_DTYPE = np.dtype(
+    [("h_anchor", "<u8"), ("v_anchor", "<u8"), ("wx", "u1"), ("wy", "u1"), ("bx", "u1"), ("by", "u1"),
+     ("wwalls", "u1"), ("bwalls", "u1"), ("turn", "u1"), ("flags", "u1"), ("move_counter", "<u4"), ("reserved", "<u4")]
+)
+TSTATE_DTYPE = np.dtype([("x_mask", "<u2"), ("o_mask", "<u2")])
+OUTCOME_DTYPE = np.dtype([("score", "<f8"), ("plies", "<u2"), ("kind", "u1"), ("reserved", "u1"), ("draws", "<u4")])
+LEAFSUM_DTYPE = np.dtype([("lo", "<u8"), ("hi", "<u8"), ("n", "<u8")])
+QINFO_DTYPE = np.dtype([("winner", "i1"), ("sp_white", "i1"), ("sp_black", "i1"), ("force_playwall", "i1")])
+COUNTERS_DTYPE = np.dtype([("kernel_launches", "<u8"), ("rollouts", "<u8"), ("plies", "<u8"),
+                           ("flood_steps", "<u8"), ("flood_queries", "<u8")])
+assert QSTATE_DTYPE.itemsize == 32 and OUTCOME_DTYPE.itemsize == 16 and LEAFSUM_DTYPE.itemsize == 24
+
+EXPORTS = [
+    "mctsb_create", "mctsb_destroy", "mctsb_abi_version", "mctsb_strerror", "mctsb_last_cuda_error",
+    "mctsb_device_count", "mctsb_submit", "mctsb_wait", "mctsb_rollout_batch", "mctsb_rollout_outcomes",
+    "mctsb_rollout_replay", "mctsb_q_movegen", "mctsb_q_play", "mctsb_upload_states", "mctsb_run_resident",
+    "mctsb_int_issue_peak", "mctsb_get_counters", "mctsb_leaf_sum_to_double",
+]
+
+
+class BackendError(RuntimeError):
+    def __init__(self, status, message):
+        super().__init__("mctsb status %d: %s" % (status, message))
+        self.status = status
+
+
+def quoridor_opening():
+    """Quoridor_state() (reference Quoridor.cpp:17-23) as a packed record."""
+    s = np.zeros((), dtype=QSTATE_DTYPE)
+    s["wx"], s["wy"], s["bx"], s["by"] = 0, 4, 8, 4
+    s["wwalls"] = s["bwalls"] = 10
+    return s
+
+
+def build(force=False, verbose=False):
+    from ._build import build_all
+    build_all(force=force, verbose=verbose)
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise FileNotFoundError(
+            "%s not built: run `python -m montecarlotreesearch_b200._build` (needs nvcc). "
+            "The rollout backend has no CPU fallback." % LIB_PATH
+        )
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u32, u64 = C.c_void_p, C.c_int, C.c_uint32, C.c_uint64
+    L.mctsb_create.argtypes = [C.POINTER(vp), i32, u64]
+    L.mctsb_destroy.argtypes = [vp]
+    L.mctsb_strerror.restype = C.c_char_p
+    L.mctsb_strerror.argtypes = [i32]
+    L.mctsb_last_cuda_error.restype = C.c_char_p
+    L.mctsb_last_cuda_error.argtypes = [vp]
+    L.mctsb_device_count.argtypes = [C.POINTER(i32)]
+    L.mctsb_submit.argtypes = [vp, i32, i32, vp, i32, u32, u64]
+    L.mctsb_wait.argtypes = [vp, vp, vp]
+    L.mctsb_rollout_batch.argtypes = [vp, i32, i32, vp, i32, u32, u64, vp, vp]
+    L.mctsb_rollout_outcomes.argtypes = [vp, i32, i32, vp, i32, u32, u64, vp, vp]
+    L.mctsb_rollout_replay.argtypes = [vp, i32, i32, vp, i32, vp, u32, u32, vp, vp]
+    L.mctsb_q_movegen.argtypes = [vp, vp, i32, vp, vp, vp]
+    L.mctsb_q_play.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.mctsb_upload_states.argtypes = [vp, i32, vp, i32]
+    L.mctsb_run_resident.argtypes = [vp, i32, i32, u32, u64, C.POINTER(C.c_float)]
+    L.mctsb_int_issue_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.mctsb_get_counters.argtypes = [vp, vp]
+    L.mctsb_leaf_sum_to_double.restype = C.c_double
+    L.mctsb_leaf_sum_to_double.argtypes = [vp]
+    return L
+
+
+def device_count():
+    L = load_library()
+    n = C.c_int(0)
+    L.mctsb_device_count(C.byref(n))
+    return n.value
+
+
+class RolloutBackend:
+    """Thin object wrapper over the opaque `mctsb_backend*` handle."""
+
+    def __init__(self, device=0, seed=DEFAULT_SEED):
+        self.lib = load_library()
+        self.handle = C.c_void_p()
+        st = self.lib.mctsb_create(C.byref(self.handle), device, seed)
+        if st != 0:
+            self.handle = None
+            raise BackendError(st, self.lib.mctsb_strerror(st).decode())
+        self.device, self.seed = device, seed
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.mctsb_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, st):
+        if st != 0:
+            msg = self.lib.mctsb_strerror(st).decode()
+            if st == 2:
+                msg += " / " + self.lib.mctsb_last_cuda_error(self.handle).decode()
+            raise BackendError(st, msg)
+
+    @staticmethod
+    def _states(game, states):
+        dt = QSTATE_DTYPE if game == GAME_QUORIDOR else TSTATE_DTYPE
+        return np.ascontiguousarray(states, dtype=dt).reshape(-1)
+
+    # -- hot path -----------------------------------------------------------------------------
+    def submit(self, game, policy, states, rollouts_per_leaf, first_rollout_id=0):
+        a = self._states(game, states)
+        self._ck(self.lib.mctsb_submit(self.handle, game, policy, a.ctypes.data, a.size, rollouts_per_leaf, first_rollout_id))
+        self._pending_n = a.size
+
+    def wait(self):
+        n = self._pending_n
+        score = np.zeros(n, dtype=np.float64)
+        sums = np.zeros(n, dtype=LEAFSUM_DTYPE)
+        self._ck(self.lib.mctsb_wait(self.handle, score.ctypes.data, sums.ctypes.data))
+        return score, sums
+
+    def rollout_batch(self, game, policy, states, rollouts_per_leaf, first_rollout_id=0):
+        self.submit(game, policy, states, rollouts_per_leaf, first_rollout_id)
+        return self.wait()
+
+    def rollout_outcomes(self, game, policy, states, rollouts_per_leaf, first_rollout_id=0, finals=True):
+        a = self._states(game, states)
+        n = a.size * rollouts_per_leaf
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        fin = np.zeros(n, dtype=QSTATE_DTYPE) if (finals and game == GAME_QUORIDOR) else None
+        self._ck(self.lib.mctsb_rollout_outcomes(self.handle, game, policy, a.ctypes.data, a.size, rollouts_per_leaf,
+                                                 first_rollout_id, out.ctypes.data, fin.ctypes.data if fin is not None else None))
+        return out, fin
+
+    def rollout_replay(self, game, policy, states, streams, finals=True):
+        a = self._states(game, states)
+        st = np.ascontiguousarray(streams, dtype=np.uint32)
+        assert st.ndim == 2 and st.shape[0] == a.size
+        out = np.zeros(a.size, dtype=OUTCOME_DTYPE)
+        fin = np.zeros(a.size, dtype=QSTATE_DTYPE) if (finals and game == GAME_QUORIDOR) else None
+        self._ck(self.lib.mctsb_rollout_replay(self.handle, game, policy, a.ctypes.data, a.size, st.ctypes.data,
+                                               st.shape[1], st.shape[1], out.ctypes.data,
+                                               fin.ctypes.data if fin is not None else None))
+        return out, fin
+
+    # -- rule primitives ------------------------------------------------------------------------
+    def q_movegen(self, states):
+        a = self._states(GAME_QUORIDOR, states)
+        legal = np.zeros((a.size, 4), dtype=np.uint64)
+        info = np.zeros(a.size, dtype=QINFO_DTYPE)
+        ev = np.zeros(a.size, dtype=np.float64)
+        self._ck(self.lib.mctsb_q_movegen(self.handle, a.ctypes.data, a.size, legal.ctypes.data, info.ctypes.data, ev.ctypes.data))
+        return legal, info, ev
+
+    def q_play(self, states, move_ids):
+        a = self._states(GAME_QUORIDOR, states)
+        ids = np.ascontiguousarray(move_ids, dtype=np.int32)
+        out = np.zeros(a.size, dtype=QSTATE_DTYPE)
+        ok = np.zeros(a.size, dtype=np.uint8)
+        self._ck(self.lib.mctsb_q_play(self.handle, a.ctypes.data, ids.ctypes.data, a.size, out.ctypes.data, ok.ctypes.data))
+        return out, ok
+
+    # -- device-resident throughput path ------------------------------------------------------------
+    def upload_states(self, game, states):
+        a = self._states(game, states)
+        self._ck(self.lib.mctsb_upload_states(self.handle, game, a.ctypes.data, a.size))
+        self._pending_n = a.size
+
+    def run_resident(self, game, policy, rollouts_per_leaf, first_rollout_id=0, timed=True):
+        ms = C.c_float(0)
+        self._ck(self.lib.mctsb_run_resident(self.handle, game, policy, rollouts_per_leaf, first_rollout_id,
+                                             C.byref(ms) if timed else None))
+        return ms.value
+
+    def int_issue_peak(self):
+        ops = C.c_double(0)
+        ms = C.c_float(0)
+        self._ck(self.lib.mctsb_int_issue_peak(self.handle, C.byref(ops), C.byref(ms)))
+        return ops.value, ms.value
+
+    def counters(self):
+        c = np.zeros((), dtype=COUNTERS_DTYPE)
+        self._ck(self.lib.mctsb_get_counters(self.handle, c.ctypes.data))
+        return {k: int(c[k]) for k in COUNTERS_DTYPE.names}
+
+
+def unpack_legal(mask4):
+    """(n,4) uint64 -> (n,209) uint8"""
+    m = np.asarray(mask4, dtype=np.uint64).reshape(-1, 4)
+    bits = np.unpackbits(m.view(np.uint8).reshape(m.shape[0], 32), axis=1, bitorder="little")
+    return bits[:, :NUM_MOVES]

@@ -1,0 +1,393 @@
+// mctsb_api.cu — implementation of the C ABI in include/mctsb.h on top of the sm_100a kernels.
+// Host side of the drop-in boundary: what MCTS_node::rollout() (reference mcts/src/mcts.cpp:57-81)
+// does with JobScheduler + RolloutJob, done with one stream, pinned staging buffers and kernels.
+// There is no CPU fallback anywhere in this file: without a CUDA device creation fails.
+#include "rollout_kernels.cuh"
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+using namespace mctsb;
+
+struct mctsb_backend {
+    int device;
+    uint64_t seed;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    // device buffers (grown on demand, never shrunk)
+    void *d_states; size_t cap_states;               // bytes
+    mctsb_leaf_sum *d_sums; size_t cap_sums;         // elements
+    mctsb_outcome *d_outcomes; size_t cap_outcomes;  // elements
+    void *d_finals; size_t cap_finals;               // bytes
+    uint32_t *d_streams; size_t cap_streams;         // elements
+    void *d_aux; size_t cap_aux;                     // bytes (movegen / play outputs)
+    unsigned long long *d_counters;                  // [4]
+    uint32_t *d_sink;                                // int-peak microbenchmark
+    // pinned host staging
+    void *h_in; size_t cap_h_in;
+    void *h_out; size_t cap_h_out;
+    // pending submit
+    bool pending; int pend_game; uint32_t pend_leaves;
+    // resident state
+    int res_game; uint32_t res_leaves;
+    uint64_t launches;
+    char cuda_err[256];
+};
+
+namespace {
+
+int fail_cuda(mctsb_backend *b, cudaError_t e, const char *what) {
+    if (b) snprintf(b->cuda_err, sizeof b->cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? MCTSB_ERR_OOM : MCTSB_ERR_CUDA;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail_cuda(b, e_, #call); } while (0)
+
+template <class T> int grow_dev(mctsb_backend *b, T **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return MCTSB_OK;
+    if (*ptr) CK(cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    size_t n = need + need / 4 + 256;
+    CK(cudaMalloc((void **)ptr, n * sizeof(T)));
+    *cap = n;
+    return MCTSB_OK;
+}
+int grow_bytes(mctsb_backend *b, void **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return MCTSB_OK;
+    if (*ptr) CK(cudaFree(*ptr));
+    *ptr = nullptr; *cap = 0;
+    size_t n = need + need / 4 + 4096;
+    CK(cudaMalloc(ptr, n));
+    *cap = n;
+    return MCTSB_OK;
+}
+int grow_pinned(mctsb_backend *b, void **ptr, size_t *cap, size_t need) {
+    if (need <= *cap) return MCTSB_OK;
+    if (*ptr) CK(cudaFreeHost(*ptr));
+    *ptr = nullptr; *cap = 0;
+    size_t n = need + need / 4 + 4096;
+    CK(cudaHostAlloc(ptr, n, cudaHostAllocDefault));
+    *cap = n;
+    return MCTSB_OK;
+}
+#define TRY(call) do { int s_ = (call); if (s_ != MCTSB_OK) return s_; } while (0)
+
+size_t state_size(int game) { return game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate); }
+
+bool valid_game_policy(int game, int policy) {
+    if (game == MCTSB_GAME_QUORIDOR) return policy == MCTSB_POLICY_REF || policy == MCTSB_POLICY_UNI;
+    if (game == MCTSB_GAME_TICTACTOE) return policy == MCTSB_POLICY_REF;
+    return false;
+}
+
+// host-side validation of packed Quoridor records (cheap structural checks only)
+bool valid_qstates(const mctsb_qstate *s, int n) {
+    for (int i = 0; i < n; i++) {
+        const mctsb_qstate &p = s[i];
+        if (p.wx > 8 || p.wy > 8 || p.bx > 8 || p.by > 8 || p.wwalls > 10 || p.bwalls > 10 || p.turn > 1 || p.flags != 0) return false;
+        if (p.wx == p.bx && p.wy == p.by) return false;
+        if (p.h_anchor & p.v_anchor) return false;                                   // crossing walls
+        if (p.h_anchor & ((p.h_anchor << 1) & ~0x0101010101010101ull)) return false; // overlapping horizontals
+        if (p.v_anchor & (p.v_anchor << 8)) return false;                            // overlapping verticals
+    }
+    return true;
+}
+
+int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const RolloutParams &p) {
+    cudaError_t e = game == MCTSB_GAME_QUORIDOR ? launch_quoridor_rollouts(p, policy, replay, b->stream)
+                                                : launch_ttt_rollouts(p, replay, b->stream);
+    if (e != cudaSuccess) return fail_cuda(b, e, "rollout kernel launch");
+    b->launches++;
+    return MCTSB_OK;
+}
+
+int upload_states(mctsb_backend *b, int game, const void *states, int n) {
+    size_t bytes = (size_t)n * state_size(game);
+    TRY(grow_bytes(b, &b->d_states, &b->cap_states, bytes));
+    TRY(grow_pinned(b, &b->h_in, &b->cap_h_in, bytes));
+    memcpy(b->h_in, states, bytes);
+    CK(cudaMemcpyAsync(b->d_states, b->h_in, bytes, cudaMemcpyHostToDevice, b->stream));
+    return MCTSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mctsb_abi_version(void) { return MCTSB_ABI_VERSION; }
+
+const char *mctsb_strerror(int status) {
+    switch (status) {
+        case MCTSB_OK: return "ok";
+        case MCTSB_ERR_NO_DEVICE: return "no CUDA device: the rollout backend has no CPU fallback";
+        case MCTSB_ERR_CUDA: return "CUDA runtime error (see mctsb_last_cuda_error)";
+        case MCTSB_ERR_BAD_ARG: return "bad argument";
+        case MCTSB_ERR_BAD_STATE: return "packed state is not a valid position";
+        case MCTSB_ERR_NOT_SUBMITTED: return "wait without a pending submit";
+        case MCTSB_ERR_BUSY: return "a submitted batch has not been waited for";
+        case MCTSB_ERR_OOM: return "out of device or pinned memory";
+        default: return "unknown status";
+    }
+}
+
+const char *mctsb_last_cuda_error(const mctsb_backend *b) { return b ? b->cuda_err : ""; }
+
+int mctsb_device_count(int *count) {
+    if (!count) return MCTSB_ERR_BAD_ARG;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { *count = 0; cudaGetLastError(); return MCTSB_ERR_NO_DEVICE; }
+    *count = n;
+    return n > 0 ? MCTSB_OK : MCTSB_ERR_NO_DEVICE;
+}
+
+int mctsb_create(mctsb_backend **out, int device, uint64_t seed) {
+    if (!out) return MCTSB_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (mctsb_device_count(&n) != MCTSB_OK) return MCTSB_ERR_NO_DEVICE;
+    if (device < 0 || device >= n) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = new (std::nothrow) mctsb_backend();
+    if (!b) return MCTSB_ERR_OOM;
+    memset(b, 0, sizeof *b);
+    b->device = device; b->seed = seed; b->res_game = -1;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_counters, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(b->d_counters, 0, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_sink, 16 * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMemset(b->d_sink, 0, 16 * sizeof(uint32_t));
+    if (e != cudaSuccess) { mctsb_destroy(b); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? MCTSB_ERR_OOM : MCTSB_ERR_CUDA; }
+    *out = b;
+    return MCTSB_OK;
+}
+
+int mctsb_destroy(mctsb_backend *b) {
+    if (!b) return MCTSB_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    cudaFree(b->d_states); cudaFree(b->d_sums); cudaFree(b->d_outcomes); cudaFree(b->d_finals);
+    cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink);
+    if (b->h_in) cudaFreeHost(b->h_in);
+    if (b->h_out) cudaFreeHost(b->h_out);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return MCTSB_OK;
+}
+
+double mctsb_leaf_sum_to_double(const mctsb_leaf_sum *s) {
+    if (!s) return 0.0;
+    unsigned __int128 t = ((unsigned __int128)s->hi << 29) + s->lo;   // exact integer: sum of score * 2^57
+    if (t == 0) return 0.0;
+    int msb = 127;
+    while (!((t >> msb) & 1)) msb--;
+    const double inv = 1.0 / 144115188075855872.0;                    // 2^-57
+    if (msb <= 52) return (double)(uint64_t)t * inv;
+    int shift = msb - 52;                                             // round to nearest even at 53 bits
+    uint64_t mant = (uint64_t)(t >> shift);
+    unsigned __int128 rem = t & (((unsigned __int128)1 << shift) - 1), half = (unsigned __int128)1 << (shift - 1);
+    if (rem > half || (rem == half && (mant & 1))) mant++;
+    double r = (double)mant;
+    for (int i = 0; i < shift; i++) r *= 2.0;
+    return r * inv;
+}
+
+int mctsb_submit(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
+                 uint32_t rollouts_per_leaf, uint64_t first_rollout_id) {
+    if (!b || !leaf_states || n_leaves <= 0 || rollouts_per_leaf == 0 || !valid_game_policy(game, policy)) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (game == MCTSB_GAME_QUORIDOR && !valid_qstates((const mctsb_qstate *)leaf_states, n_leaves)) return MCTSB_ERR_BAD_STATE;
+    CK(cudaSetDevice(b->device));
+    TRY(upload_states(b, game, leaf_states, n_leaves));
+    TRY(grow_dev(b, &b->d_sums, &b->cap_sums, (size_t)n_leaves));
+    TRY(grow_pinned(b, &b->h_out, &b->cap_h_out, (size_t)n_leaves * sizeof(mctsb_leaf_sum)));
+    CK(cudaMemsetAsync(b->d_sums, 0, (size_t)n_leaves * sizeof(mctsb_leaf_sum), b->stream));
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = b->d_states; p.n_leaves = (uint32_t)n_leaves; p.rollouts_per_leaf = rollouts_per_leaf;
+    p.n_rollouts = (uint64_t)n_leaves * rollouts_per_leaf; p.seed = b->seed; p.first_rollout_id = first_rollout_id;
+    p.sums = b->d_sums; p.counters = b->d_counters;
+    TRY(launch_rollouts(b, game, policy, false, p));
+    CK(cudaMemcpyAsync(b->h_out, b->d_sums, (size_t)n_leaves * sizeof(mctsb_leaf_sum), cudaMemcpyDeviceToHost, b->stream));
+    b->pending = true; b->pend_game = game; b->pend_leaves = (uint32_t)n_leaves;
+    return MCTSB_OK;
+}
+
+int mctsb_wait(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums) {
+    if (!b) return MCTSB_ERR_BAD_ARG;
+    if (!b->pending) return MCTSB_ERR_NOT_SUBMITTED;
+    CK(cudaSetDevice(b->device));
+    b->pending = false;
+    CK(cudaStreamSynchronize(b->stream));
+    const mctsb_leaf_sum *h = (const mctsb_leaf_sum *)b->h_out;
+    for (uint32_t i = 0; i < b->pend_leaves; i++) {
+        if (sums) sums[i] = h[i];
+        if (score_sum) score_sum[i] = mctsb_leaf_sum_to_double(&h[i]);
+    }
+    return MCTSB_OK;
+}
+
+int mctsb_rollout_batch(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
+                        uint32_t rollouts_per_leaf, uint64_t first_rollout_id, double *score_sum, mctsb_leaf_sum *sums) {
+    TRY(mctsb_submit(b, game, policy, leaf_states, n_leaves, rollouts_per_leaf, first_rollout_id));
+    return mctsb_wait(b, score_sum, sums);
+}
+
+int mctsb_rollout_outcomes(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
+                           uint32_t rollouts_per_leaf, uint64_t first_rollout_id, mctsb_outcome *outcomes, void *final_states) {
+    if (!b || !leaf_states || !outcomes || n_leaves <= 0 || rollouts_per_leaf == 0 || !valid_game_policy(game, policy)) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (game == MCTSB_GAME_QUORIDOR && !valid_qstates((const mctsb_qstate *)leaf_states, n_leaves)) return MCTSB_ERR_BAD_STATE;
+    if (game != MCTSB_GAME_QUORIDOR) final_states = nullptr;
+    CK(cudaSetDevice(b->device));
+    size_t n = (size_t)n_leaves * rollouts_per_leaf;
+    TRY(upload_states(b, game, leaf_states, n_leaves));
+    TRY(grow_dev(b, &b->d_outcomes, &b->cap_outcomes, n));
+    if (final_states) TRY(grow_bytes(b, &b->d_finals, &b->cap_finals, n * sizeof(mctsb_qstate)));
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = b->d_states; p.n_leaves = (uint32_t)n_leaves; p.rollouts_per_leaf = rollouts_per_leaf;
+    p.n_rollouts = n; p.seed = b->seed; p.first_rollout_id = first_rollout_id;
+    p.outcomes = b->d_outcomes; p.finals = final_states ? b->d_finals : nullptr; p.counters = b->d_counters;
+    TRY(launch_rollouts(b, game, policy, false, p));
+    CK(cudaMemcpyAsync(outcomes, b->d_outcomes, n * sizeof(mctsb_outcome), cudaMemcpyDeviceToHost, b->stream));
+    if (final_states) CK(cudaMemcpyAsync(final_states, b->d_finals, n * sizeof(mctsb_qstate), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return MCTSB_OK;
+}
+
+int mctsb_rollout_replay(mctsb_backend *b, int game, int policy, const void *states, int n, const uint32_t *streams,
+                         uint32_t stream_len, uint32_t stream_stride, mctsb_outcome *outcomes, void *final_states) {
+    if (!b || !states || !streams || !outcomes || n <= 0 || stream_len == 0 || stream_stride < stream_len || !valid_game_policy(game, policy)) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (game == MCTSB_GAME_QUORIDOR && !valid_qstates((const mctsb_qstate *)states, n)) return MCTSB_ERR_BAD_STATE;
+    if (game != MCTSB_GAME_QUORIDOR) final_states = nullptr;
+    CK(cudaSetDevice(b->device));
+    TRY(upload_states(b, game, states, n));
+    size_t words = (size_t)n * stream_stride;
+    TRY(grow_dev(b, &b->d_streams, &b->cap_streams, words));
+    CK(cudaMemcpyAsync(b->d_streams, streams, words * sizeof(uint32_t), cudaMemcpyHostToDevice, b->stream));
+    TRY(grow_dev(b, &b->d_outcomes, &b->cap_outcomes, (size_t)n));
+    if (final_states) TRY(grow_bytes(b, &b->d_finals, &b->cap_finals, (size_t)n * sizeof(mctsb_qstate)));
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = b->d_states; p.n_leaves = (uint32_t)n; p.rollouts_per_leaf = 1; p.n_rollouts = (uint64_t)n;
+    p.streams = b->d_streams; p.stream_len = stream_len; p.stream_stride = stream_stride;
+    p.outcomes = b->d_outcomes; p.finals = final_states ? b->d_finals : nullptr; p.counters = b->d_counters;
+    TRY(launch_rollouts(b, game, policy, true, p));
+    CK(cudaMemcpyAsync(outcomes, b->d_outcomes, (size_t)n * sizeof(mctsb_outcome), cudaMemcpyDeviceToHost, b->stream));
+    if (final_states) CK(cudaMemcpyAsync(final_states, b->d_finals, (size_t)n * sizeof(mctsb_qstate), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return MCTSB_OK;
+}
+
+int mctsb_q_movegen(mctsb_backend *b, const mctsb_qstate *states, int n, uint64_t *legal, mctsb_qinfo *info, double *eval) {
+    if (!b || !states || n <= 0) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (!valid_qstates(states, n)) return MCTSB_ERR_BAD_STATE;
+    CK(cudaSetDevice(b->device));
+    TRY(upload_states(b, MCTSB_GAME_QUORIDOR, states, n));
+    size_t o_legal = 0, o_info = o_legal + (size_t)n * 32, o_eval = (o_info + (size_t)n * sizeof(mctsb_qinfo) + 15) & ~(size_t)15;
+    size_t total = o_eval + (size_t)n * sizeof(double);
+    TRY(grow_bytes(b, &b->d_aux, &b->cap_aux, total));
+    char *base = (char *)b->d_aux;
+    cudaError_t e = launch_quoridor_movegen((const mctsb_qstate *)b->d_states, n, (uint64_t *)(base + o_legal),
+                                            (mctsb_qinfo *)(base + o_info), (double *)(base + o_eval), b->stream);
+    if (e != cudaSuccess) return fail_cuda(b, e, "movegen kernel launch");
+    b->launches++;
+    if (legal) CK(cudaMemcpyAsync(legal, base + o_legal, (size_t)n * 32, cudaMemcpyDeviceToHost, b->stream));
+    if (info) CK(cudaMemcpyAsync(info, base + o_info, (size_t)n * sizeof(mctsb_qinfo), cudaMemcpyDeviceToHost, b->stream));
+    if (eval) CK(cudaMemcpyAsync(eval, base + o_eval, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return MCTSB_OK;
+}
+
+int mctsb_q_play(mctsb_backend *b, const mctsb_qstate *states, const int32_t *move_ids, int n, mctsb_qstate *out, uint8_t *ok) {
+    if (!b || !states || !move_ids || !out || n <= 0) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (!valid_qstates(states, n)) return MCTSB_ERR_BAD_STATE;
+    CK(cudaSetDevice(b->device));
+    TRY(upload_states(b, MCTSB_GAME_QUORIDOR, states, n));
+    size_t o_ids = 0, o_out = ((size_t)n * 4 + 31) & ~(size_t)31, o_ok = o_out + (size_t)n * 32, total = o_ok + (size_t)n;
+    TRY(grow_bytes(b, &b->d_aux, &b->cap_aux, total));
+    char *base = (char *)b->d_aux;
+    CK(cudaMemcpyAsync(base + o_ids, move_ids, (size_t)n * 4, cudaMemcpyHostToDevice, b->stream));
+    cudaError_t e = launch_quoridor_play((const mctsb_qstate *)b->d_states, (const int32_t *)(base + o_ids), n,
+                                         (mctsb_qstate *)(base + o_out), (uint8_t *)(base + o_ok), b->stream);
+    if (e != cudaSuccess) return fail_cuda(b, e, "play kernel launch");
+    b->launches++;
+    CK(cudaMemcpyAsync(out, base + o_out, (size_t)n * 32, cudaMemcpyDeviceToHost, b->stream));
+    if (ok) CK(cudaMemcpyAsync(ok, base + o_ok, (size_t)n, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return MCTSB_OK;
+}
+
+int mctsb_upload_states(mctsb_backend *b, int game, const void *leaf_states, int n_leaves) {
+    if (!b || !leaf_states || n_leaves <= 0 || (game != MCTSB_GAME_QUORIDOR && game != MCTSB_GAME_TICTACTOE)) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (game == MCTSB_GAME_QUORIDOR && !valid_qstates((const mctsb_qstate *)leaf_states, n_leaves)) return MCTSB_ERR_BAD_STATE;
+    CK(cudaSetDevice(b->device));
+    TRY(upload_states(b, game, leaf_states, n_leaves));
+    TRY(grow_dev(b, &b->d_sums, &b->cap_sums, (size_t)n_leaves));
+    TRY(grow_pinned(b, &b->h_out, &b->cap_h_out, (size_t)n_leaves * sizeof(mctsb_leaf_sum)));
+    CK(cudaStreamSynchronize(b->stream));
+    b->res_game = game; b->res_leaves = (uint32_t)n_leaves;
+    return MCTSB_OK;
+}
+
+int mctsb_run_resident(mctsb_backend *b, int game, int policy, uint32_t rollouts_per_leaf, uint64_t first_rollout_id, float *elapsed_ms) {
+    if (!b || rollouts_per_leaf == 0 || !valid_game_policy(game, policy)) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (b->res_game != game || b->res_leaves == 0) return MCTSB_ERR_NOT_SUBMITTED;
+    CK(cudaSetDevice(b->device));
+    CK(cudaMemsetAsync(b->d_sums, 0, (size_t)b->res_leaves * sizeof(mctsb_leaf_sum), b->stream));
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = b->d_states; p.n_leaves = b->res_leaves; p.rollouts_per_leaf = rollouts_per_leaf;
+    p.n_rollouts = (uint64_t)b->res_leaves * rollouts_per_leaf; p.seed = b->seed; p.first_rollout_id = first_rollout_id;
+    p.sums = b->d_sums; p.counters = b->d_counters;
+    CK(cudaEventRecord(b->ev0, b->stream));
+    TRY(launch_rollouts(b, game, policy, false, p));
+    CK(cudaEventRecord(b->ev1, b->stream));
+    CK(cudaMemcpyAsync(b->h_out, b->d_sums, (size_t)b->res_leaves * sizeof(mctsb_leaf_sum), cudaMemcpyDeviceToHost, b->stream));
+    b->pending = true; b->pend_game = game; b->pend_leaves = b->res_leaves;
+    if (elapsed_ms) {
+        CK(cudaEventSynchronize(b->ev1));
+        CK(cudaEventElapsedTime(elapsed_ms, b->ev0, b->ev1));
+    }
+    return MCTSB_OK;
+}
+
+int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms) {
+    if (!b || !thread_ops_per_sec) return MCTSB_ERR_BAD_ARG;
+    CK(cudaSetDevice(b->device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, b->device));
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 14;
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {           // first trip warms up, best of the rest
+        CK(cudaEventRecord(b->ev0, b->stream));
+        cudaError_t e = launch_int_peak(b->d_sink, blocks, threads, iters, b->stream);
+        if (e != cudaSuccess) return fail_cuda(b, e, "int peak launch");
+        b->launches++;
+        CK(cudaEventRecord(b->ev1, b->stream));
+        CK(cudaEventSynchronize(b->ev1));
+        float ms = 0; CK(cudaEventElapsedTime(&ms, b->ev0, b->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    *thread_ops_per_sec = (double)blocks * threads * (double)iters * INT_PEAK_OPS_PER_ITER / (best * 1e-3);
+    if (elapsed_ms) *elapsed_ms = best;
+    return MCTSB_OK;
+}
+
+int mctsb_get_counters(mctsb_backend *b, mctsb_counters *out) {
+    if (!b || !out) return MCTSB_ERR_BAD_ARG;
+    CK(cudaSetDevice(b->device));
+    unsigned long long h[4];
+    CK(cudaStreamSynchronize(b->stream));
+    CK(cudaMemcpy(h, b->d_counters, sizeof h, cudaMemcpyDeviceToHost));
+    out->kernel_launches = b->launches; out->rollouts = h[0]; out->plies = h[1]; out->flood_steps = h[2]; out->flood_queries = h[3];
+    return MCTSB_OK;
+}
+
+}  // extern "C"

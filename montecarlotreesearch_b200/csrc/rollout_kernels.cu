@@ -1,0 +1,265 @@
+// rollout_kernels.cu — hand-written sm_100a kernels for the MCTS Simulation phase.
+//
+// Replaces `*score = state->rollout()` executed by RolloutJob::run on the pthread JobScheduler
+// (reference mcts/include/mcts.h:82-91, mcts/src/JobScheduler.cpp:88-131) and the summing loop of
+// MCTS_node::rollout (reference mcts/src/mcts.cpp:57-81).
+//
+// Mapping: one thread = one rollout; the position lives in registers (qcore.cuh).  Leaf states
+// are staged with 16-byte vector loads (a 32-byte record is two uint4).  Nothing on this path is
+// a contraction, so tensor cores are not used; the bound is SM integer issue.
+#include "rollout_kernels.cuh"
+#include "qcore.cuh"
+#include "ttt_core.cuh"
+
+namespace mctsb {
+
+static constexpr int kThreads = 128;
+
+__device__ __forceinline__ mctsb_qstate load_qstate(const void *base, uint32_t idx) {
+    const uint4 *p = reinterpret_cast<const uint4 *>(base) + 2ull * idx;
+    uint4 lo = __ldg(p), hi = __ldg(p + 1);
+    mctsb_qstate s;
+    s.h_anchor = (uint64_t)lo.x | ((uint64_t)lo.y << 32);
+    s.v_anchor = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+    s.wx = hi.x & 0xff; s.wy = (hi.x >> 8) & 0xff; s.bx = (hi.x >> 16) & 0xff; s.by = hi.x >> 24;
+    s.wwalls = hi.y & 0xff; s.bwalls = (hi.y >> 8) & 0xff; s.turn = (hi.y >> 16) & 0xff; s.flags = hi.y >> 24;
+    s.move_counter = hi.z; s.reserved = hi.w;
+    return s;
+}
+
+__device__ __forceinline__ void store_qstate(void *base, uint64_t idx, const mctsb_qstate &s) {
+    uint4 lo, hi;
+    lo.x = (uint32_t)s.h_anchor; lo.y = (uint32_t)(s.h_anchor >> 32);
+    lo.z = (uint32_t)s.v_anchor; lo.w = (uint32_t)(s.v_anchor >> 32);
+    hi.x = s.wx | (s.wy << 8) | (s.bx << 16) | ((uint32_t)s.by << 24);
+    hi.y = s.wwalls | (s.bwalls << 8) | (s.turn << 16) | ((uint32_t)s.flags << 24);
+    hi.z = s.move_counter; hi.w = 0;
+    uint4 *p = reinterpret_cast<uint4 *>(base) + 2ull * idx;
+    p[0] = lo; p[1] = hi;
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Exact per-leaf accumulation (include/mctsb.h: score*2^57 split in two 29-bit limbs).  When the
+// whole warp works on one leaf — the common case, R >= 32 — the limbs are reduced with shuffles
+// and one lane issues the three atomics.
+__device__ __forceinline__ void accumulate_leaf(mctsb_leaf_sum *sums, uint32_t leaf, bool active, double score) {
+    unsigned long long fx = active ? __double2ull_rz(score * 144115188075855872.0) : 0ull;
+    unsigned long long lo = fx & ((1ull << 29) - 1), hi = fx >> 29, n = active ? 1ull : 0ull;
+    uint32_t leaf0 = __shfl_sync(0xffffffffu, leaf, 0);
+    bool uniform = __all_sync(0xffffffffu, !active || leaf == leaf0);
+    bool lane0_active = __shfl_sync(0xffffffffu, (int)active, 0);
+    if (uniform && lane0_active) {
+        lo = warp_sum_u64(lo); hi = warp_sum_u64(hi); n = warp_sum_u64(n);
+        if ((threadIdx.x & 31) == 0) {
+            atomicAdd((unsigned long long *)&sums[leaf0].lo, lo);
+            atomicAdd((unsigned long long *)&sums[leaf0].hi, hi);
+            atomicAdd((unsigned long long *)&sums[leaf0].n, n);
+        }
+    } else if (active) {
+        atomicAdd((unsigned long long *)&sums[leaf].lo, lo);
+        atomicAdd((unsigned long long *)&sums[leaf].hi, hi);
+        atomicAdd((unsigned long long *)&sums[leaf].n, 1ull);
+    }
+}
+
+__device__ __forceinline__ void accumulate_counters(unsigned long long *counters, bool active, const QWork &wk, int plies) {
+    if (!counters) return;
+    unsigned long long r = warp_sum_u64(active ? 1ull : 0ull);
+    unsigned long long p = warp_sum_u64(active ? (unsigned long long)plies : 0ull);
+    unsigned long long fs = warp_sum_u64(active ? (unsigned long long)wk.flood_steps : 0ull);
+    unsigned long long fq = warp_sum_u64(active ? (unsigned long long)wk.flood_queries : 0ull);
+    if ((threadIdx.x & 31) == 0 && r) {
+        atomicAdd(counters + 0, r); atomicAdd(counters + 1, p); atomicAdd(counters + 2, fs); atomicAdd(counters + 3, fq);
+    }
+}
+
+__device__ __forceinline__ void store_outcome(mctsb_outcome *out, uint64_t r, double score, int plies, int kind, uint32_t draws) {
+    // 16-byte record, one vector store
+    uint4 v;
+    unsigned long long sb = (unsigned long long)__double_as_longlong(score);
+    v.x = (uint32_t)sb; v.y = (uint32_t)(sb >> 32);
+    v.z = (uint32_t)(plies & 0xffff) | ((uint32_t)(kind & 0xff) << 16);
+    v.w = draws;
+    reinterpret_cast<uint4 *>(out)[r] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Quoridor: POLICY 0 = REF (Quoridor_state::rollout, Quoridor.cpp:809-855), 1 = UNI.
+// REPLAY: rollout r plays state r against pre-drawn stream r (parity mode).
+// ---------------------------------------------------------------------------------------------
+template <int POLICY, bool REPLAY>
+__global__ void __launch_bounds__(kThreads) quoridor_rollout_kernel(RolloutParams p) {
+    const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = r < p.n_rollouts;
+    const uint32_t leaf = active ? (REPLAY ? (uint32_t)r : (uint32_t)(r / p.rollouts_per_leaf)) : 0u;
+    uint8_t pool[128];
+    double score = 0.0; int plies = 0, kind = 0; uint32_t draws = 0;
+    QWork wk = {0u, 0u, 0u};
+    QState s;
+    if (active) {
+        mctsb_qstate packed = load_qstate(p.states, leaf);
+        q_unpack(s, packed);
+        if (REPLAY) {
+            StreamDraws d; d.init(p.streams + (size_t)r * p.stream_stride, p.stream_len);
+            score = POLICY == 1 ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+            draws = d.consumed();
+        } else {
+            PhiloxDraws d; d.init(p.seed, p.first_rollout_id + r);
+            score = POLICY == 1 ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+            draws = d.consumed();
+        }
+        if (p.outcomes) store_outcome(p.outcomes, r, score, plies, kind, draws);
+        if (p.finals) { mctsb_qstate f; q_pack(s, f); store_qstate(p.finals, r, f); }
+    }
+    if (p.sums) accumulate_leaf(p.sums, leaf, active, score);
+    accumulate_counters(p.counters, active, wk, plies);
+}
+
+cudaError_t launch_quoridor_rollouts(const RolloutParams &p, int policy, bool replay, cudaStream_t st) {
+    if (p.n_rollouts == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((p.n_rollouts + kThreads - 1) / kThreads);
+    if (policy == MCTSB_POLICY_UNI) {
+        if (replay) quoridor_rollout_kernel<1, true><<<blocks, kThreads, 0, st>>>(p);
+        else        quoridor_rollout_kernel<1, false><<<blocks, kThreads, 0, st>>>(p);
+    } else {
+        if (replay) quoridor_rollout_kernel<0, true><<<blocks, kThreads, 0, st>>>(p);
+        else        quoridor_rollout_kernel<0, false><<<blocks, kThreads, 0, st>>>(p);
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Tic-Tac-Toe (TicTacToe_state::rollout, TicTacToe.cpp:73-107)
+// ---------------------------------------------------------------------------------------------
+template <bool REPLAY>
+__global__ void __launch_bounds__(kThreads) ttt_rollout_kernel(RolloutParams p) {
+    const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = r < p.n_rollouts;
+    const uint32_t leaf = active ? (REPLAY ? (uint32_t)r : (uint32_t)(r / p.rollouts_per_leaf)) : 0u;
+    double score = 0.0; int plies = 0, kind = 0; uint32_t draws = 0;
+    if (active) {
+        uint32_t packed = __ldg(reinterpret_cast<const uint32_t *>(p.states) + leaf);
+        uint32_t x = packed & 0xffffu, o = packed >> 16;
+        if (REPLAY) {
+            StreamDraws d; d.init(p.streams + (size_t)r * p.stream_stride, p.stream_len);
+            score = t_rollout(x, o, d, plies, kind); draws = d.consumed();
+        } else {
+            PhiloxDraws d; d.init(p.seed, p.first_rollout_id + r);
+            score = t_rollout(x, o, d, plies, kind); draws = d.consumed();
+        }
+        if (p.outcomes) store_outcome(p.outcomes, r, score, plies, kind, draws);
+    }
+    if (p.sums) accumulate_leaf(p.sums, leaf, active, score);
+    QWork wk = {0u, 0u, 0u};
+    accumulate_counters(p.counters, active, wk, plies);
+}
+
+cudaError_t launch_ttt_rollouts(const RolloutParams &p, bool replay, cudaStream_t st) {
+    if (p.n_rollouts == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((p.n_rollouts + kThreads - 1) / kThreads);
+    if (replay) ttt_rollout_kernel<true><<<blocks, kThreads, 0, st>>>(p);
+    else        ttt_rollout_kernel<false><<<blocks, kThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Move generation / rule primitives: one warp per position.  Lane l tests the walls anchored at
+// l and l+32 in both orientations with the flood-fill path test; __ballot_sync assembles the four
+// 32-bit halves of the two 64-bit legality masks (generate_all_moves, Quoridor.cpp:594-616;
+// legal_wall, Quoridor.cpp:289-329).
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) quoridor_movegen_kernel(const mctsb_qstate *states, int n, uint64_t *legal4,
+                                                                    mctsb_qinfo *info, double *eval) {
+    const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    QState s;
+    q_unpack(s, load_qstate(states, warp));
+    uint64_t ch, cv;
+    q_cheap_wall_masks(s, ch, cv);
+    uint32_t bal[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        int a = 32 * (j >> 1) + lane, vertical = j & 1;
+        bool ok = ((vertical ? cv : ch) >> a) & 1ull;
+        if (ok) ok = q_wall_keeps_paths(s, 2 * a + vertical, nullptr);
+        bal[j] = __ballot_sync(0xffffffffu, ok);
+    }
+    if (lane == 0) {
+        uint64_t lh = (uint64_t)bal[0] | ((uint64_t)bal[2] << 32), lv = (uint64_t)bal[1] | ((uint64_t)bal[3] << 32);
+        if (legal4) {
+            uint64_t m[4];
+            q_parts_to_mask(s, q_step_mask(s), lh, lv, m);
+            legal4[4ull * warp + 0] = m[0]; legal4[4ull * warp + 1] = m[1];
+            legal4[4ull * warp + 2] = m[2]; legal4[4ull * warp + 3] = m[3];
+        }
+        if (info) {
+            mctsb_qinfo qi;
+            qi.winner = (int8_t)q_winner(s);
+            qi.sp_white = (int8_t)q_sp(s, 0, nullptr);
+            qi.sp_black = (int8_t)q_sp(s, 1, nullptr);
+            qi.force_playwall = (int8_t)q_force_playwall(s, nullptr);
+            info[warp] = qi;
+        }
+        if (eval) eval[warp] = q_eval(s, nullptr);
+    }
+}
+
+cudaError_t launch_quoridor_movegen(const mctsb_qstate *states, int n, uint64_t *legal4, mctsb_qinfo *info,
+                                    double *eval, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    unsigned blocks = (unsigned)(((uint64_t)n * 32 + kThreads - 1) / kThreads);
+    quoridor_movegen_kernel<<<blocks, kThreads, 0, st>>>(states, n, legal4, info, eval);
+    return cudaGetLastError();
+}
+
+// next_state (Quoridor.cpp:506-510 -> play_move, :344-392), one thread per (state, move)
+__global__ void __launch_bounds__(kThreads) quoridor_play_kernel(const mctsb_qstate *states, const int32_t *ids, int n,
+                                                                 mctsb_qstate *out, uint8_t *ok) {
+    const int i = blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    QState s;
+    mctsb_qstate packed = load_qstate(states, i);
+    q_unpack(s, packed);
+    bool legal = q_legal_move(s, ids[i]);
+    if (legal) { q_play_id(s, ids[i]); q_pack(s, packed); }
+    store_qstate(out, i, packed);
+    if (ok) ok[i] = legal ? 1 : 0;
+}
+
+cudaError_t launch_quoridor_play(const mctsb_qstate *states, const int32_t *ids, int n, mctsb_qstate *out,
+                                 uint8_t *ok, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    quoridor_play_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, st>>>(states, ids, n, out, ok);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Integer-issue peak: 8 independent chains per thread, each trip = 8 x (4 LOP3 + 4 IADD3) = 64
+// thread-level integer instructions on the ALU pipe, the mix the flood fill is made of.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, int iters) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a0 = t, a1 = t ^ 0x9e3779b9u, a2 = t + 0x7f4a7c15u, a3 = ~t, a4 = t * 3u, a5 = t * 5u, a6 = t * 7u, a7 = t * 11u;
+    uint32_t k1 = sink[0], k2 = sink[1];   // runtime values so nothing folds
+    for (int i = 0; i < iters; i++) {
+#define MC_CHAIN(a)                                                                      \
+        a = (a ^ k1) & (a | k2); a = a + k1 + k2; a = (a & k2) ^ (a | k1); a = a + k2 + 1u; \
+        a = (a ^ k2) | (a & k1); a = a + k1 + 3u; a = (a | k1) ^ (a & k2); a = a + k2 + k1;
+        MC_CHAIN(a0) MC_CHAIN(a1) MC_CHAIN(a2) MC_CHAIN(a3) MC_CHAIN(a4) MC_CHAIN(a5) MC_CHAIN(a6) MC_CHAIN(a7)
+#undef MC_CHAIN
+    }
+    uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u) sink[2] = r;    // practically never; keeps the chains alive
+}
+
+cudaError_t launch_int_peak(uint32_t *sink, int blocks, int threads, int iters, cudaStream_t st) {
+    int_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+}  // namespace mctsb

@@ -1,0 +1,40 @@
+// rollout_kernels.cuh — sm_100a kernels of the rollout backend (declarations + launch params).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/mctsb.h"
+
+namespace mctsb {
+
+struct RolloutParams {
+    const void *states;            // mctsb_qstate[n_leaves] or mctsb_tstate[n_leaves]
+    uint32_t n_leaves;
+    uint32_t rollouts_per_leaf;    // R; rollout r belongs to leaf r / R
+    uint64_t n_rollouts;           // n_leaves * R
+    uint64_t seed;
+    uint64_t first_rollout_id;
+    // replay mode (one rollout per state): pre-drawn u32 streams
+    const uint32_t *streams;
+    uint32_t stream_len, stream_stride;
+    // outputs (any may be null)
+    mctsb_leaf_sum *sums;          // [n_leaves], accumulated with integer atomics
+    mctsb_outcome *outcomes;       // [n_rollouts]
+    void *finals;                  // mctsb_qstate[n_rollouts]
+    unsigned long long *counters;  // [4]: rollouts, plies, flood_steps, flood_queries
+};
+
+// one thread = one rollout
+cudaError_t launch_quoridor_rollouts(const RolloutParams &p, int policy, bool replay, cudaStream_t st);
+cudaError_t launch_ttt_rollouts(const RolloutParams &p, bool replay, cudaStream_t st);
+
+// one warp = one position; the 128 wall candidates are spread over the lanes
+cudaError_t launch_quoridor_movegen(const mctsb_qstate *states, int n, uint64_t *legal4, mctsb_qinfo *info,
+                                    double *eval, cudaStream_t st);
+cudaError_t launch_quoridor_play(const mctsb_qstate *states, const int32_t *ids, int n, mctsb_qstate *out,
+                                 uint8_t *ok, cudaStream_t st);
+
+// integer-issue roofline denominator: independent LOP3/IADD3 chains on all SMs
+cudaError_t launch_int_peak(uint32_t *sink, int blocks, int threads, int iters, cudaStream_t st);
+static const int INT_PEAK_OPS_PER_ITER = 64;   // thread-level integer ops per loop trip
+
+}  // namespace mctsb

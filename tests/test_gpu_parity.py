@@ -1,0 +1,232 @@
+"""GPU (-m gpu): the sm_100a kernels, called through the C ABI, against the oracle and the
+reference goldens.  Bit-exact for every integer / index / score value."""
+from fractions import Fraction
+
+import numpy as np
+import pytest
+
+import montecarlotreesearch_b200 as m
+from tests.util import golden, philox_stream
+
+pytestmark = pytest.mark.gpu
+G, T = m.GAME_QUORIDOR, m.GAME_TICTACTOE
+
+
+@pytest.fixture(scope="module")
+def be():
+    b = m.RolloutBackend(0, m.DEFAULT_SEED)
+    yield b
+    b.close()
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return golden("corpus_q.npy")
+
+
+def test_library_is_the_cuda_one(be):
+    assert be.counters()["kernel_launches"] == 0
+    be.rollout_batch(T, 0, np.zeros(1, dtype=m.TSTATE_DTYPE), 32)
+    assert be.counters()["kernel_launches"] == 1
+
+
+# ---- rule primitives on the whole corpus -----------------------------------------------------------
+def test_movegen_vs_golden(be, corpus):
+    g = golden("golden_q_primitives.npz")
+    legal, info, ev = be.q_movegen(corpus[g["index"]])
+    bits = m.unpack_legal(legal)
+    assert (np.packbits(bits, axis=1, bitorder="little") == g["legal"]).all()
+    assert (info["winner"] == g["winner"]).all() and (info["sp_white"] == g["sp_white"]).all()
+    assert (info["sp_black"] == g["sp_black"]).all() and (info["force_playwall"] == g["force_playwall"]).all()
+    assert (ev == g["eval"]).all()
+    # the legal set is exactly what generate_all_moves enumerates
+    for j in range(len(g["index"])):
+        n = int(g["n_actions"][j])
+        assert sorted(np.nonzero(bits[j])[0].tolist()) == sorted(g["actions"][j, :n].tolist())
+
+
+def test_movegen_vs_oracle_full_corpus(be, port, corpus):
+    legal, info, ev = be.q_movegen(corpus)
+    bits = m.unpack_legal(legal)
+    for i in range(len(corpus)):
+        p = port.q_primitives(corpus[i])
+        assert (bits[i] == p["legal"]).all(), i
+        assert (info["winner"][i], info["sp_white"][i], info["sp_black"][i], info["force_playwall"][i]) == (
+            p["winner"], p["sp_white"], p["sp_black"], p["force_playwall"])
+        assert ev[i] == p["eval"]
+
+
+def test_play_vs_oracle(be, port, corpus):
+    rng = np.random.default_rng(4)
+    idx = rng.choice(len(corpus), 2000)
+    ids = rng.integers(0, 209, size=2000).astype(np.int32)
+    out, ok = be.q_play(corpus[idx], ids)
+    for j in range(2000):
+        a_ok, a = port.q_play(corpus[idx[j]], int(ids[j]))
+        assert bool(ok[j]) == a_ok and out[j].tobytes() == a.tobytes()
+
+
+# ---- replayed playouts -----------------------------------------------------------------------------
+def test_replay_vs_reference_golden(be, corpus):
+    g = golden("golden_q_replay.npz")
+    streams = np.stack([philox_stream(int(g["seed"]), int(i), 16384) for i in g["id"]])
+    out, fin = be.rollout_replay(G, m.POLICY_REF, corpus[g["index"]], streams)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    assert fin.tobytes() == g["final"].tobytes()
+
+
+def test_replay_vs_oracle_random_streams(be, port, corpus):
+    rng = np.random.default_rng(12)
+    idx = rng.choice(len(corpus), 1024)
+    streams = rng.integers(0, 2**32, size=(1024, 8192), dtype=np.uint32)
+    out, fin = be.rollout_replay(G, m.POLICY_REF, corpus[idx], streams)
+    exp, efin = port.q_rollout_streams(corpus[idx], streams)
+    assert out.tobytes() == exp.tobytes() and fin.tobytes() == efin.tobytes()
+
+
+def test_known_answer_streams(be):
+    g = golden("golden_kat.npz")
+    streams = np.stack([
+        np.zeros(65536, np.uint32),
+        np.full(65536, 0x80000000, np.uint32),
+        ((np.arange(65536, dtype=np.uint64) * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)).astype(np.uint32),
+        (((np.arange(65536, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B9)) ^ (np.arange(65536, dtype=np.uint64) >> np.uint64(3))).astype(np.uint32),
+    ])
+    out, _ = be.rollout_replay(G, m.POLICY_REF, np.repeat(m.quoridor_opening(), 4), streams)
+    tout, _ = be.rollout_replay(T, 0, np.zeros(4, dtype=m.TSTATE_DTYPE), streams)
+    for j, name in enumerate(("S0", "S1", "S2", "S3")):
+        assert [out["score"][j], out["draws"][j], out["kind"][j], out["plies"][j], tout["score"][j], tout["draws"][j]] == list(g[name])
+
+
+# ---- Philox-keyed playouts ---------------------------------------------------------------------------
+def test_opening_rollouts_vs_reference_golden(be):
+    g = golden("golden_q_opening.npz")
+    out, _ = be.rollout_outcomes(G, m.POLICY_REF, m.quoridor_opening(), 512, 0)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+
+
+def test_free_running_scores_vs_reference_golden(be, corpus):
+    g = golden("golden_q_distribution.npz")
+    n = int(g["n"])
+    states = np.array([m.quoridor_opening() if i < 0 else corpus[i] for i in g["index"]], dtype=m.QSTATE_DTYPE)
+    # leaf j, rollout k uses id first + j*n + k; the golden used first_id for every state, so run one leaf at a time
+    for j in range(len(states)):
+        out, _ = be.rollout_outcomes(G, m.POLICY_REF, states[j], n, int(g["first_id"]), finals=False)
+        assert (out["score"] == g["scores"][j]).all(), j
+
+
+def test_three_sigma_agreement_on_disjoint_streams(be, corpus):
+    """Free-running win rates with streams the reference never saw: sample means within 3 sigma
+    (sample variance; scores are not Bernoulli)."""
+    g = golden("golden_q_distribution.npz")
+    states = np.array([m.quoridor_opening() if i < 0 else corpus[i] for i in g["index"]], dtype=m.QSTATE_DTYPE)
+    R = 20000
+    out, _ = be.rollout_outcomes(G, m.POLICY_REF, states, R, 1 << 40, finals=False)
+    sc = out["score"].reshape(len(states), R)
+    for j in range(len(states)):
+        ref = g["scores"][j]
+        se = np.sqrt(ref.var(ddof=1) / len(ref) + sc[j].var(ddof=1) / R)
+        assert abs(ref.mean() - sc[j].mean()) <= 3.0 * se + 1e-12, (j, ref.mean(), sc[j].mean(), se)
+
+
+def test_uniform_policy_vs_golden(be, corpus):
+    g = golden("golden_q_uniform.npz")
+    for j, i in enumerate(g["index"]):
+        out, _ = be.rollout_outcomes(G, m.POLICY_UNI, corpus[i], 1, int(g["id"][j]))
+        assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]
+        assert out["kind"][0] == g["kind"][j] and out["plies"][0] == g["plies"][j]
+
+
+def test_uniform_policy_vs_oracle(be, port, corpus):
+    rng = np.random.default_rng(2)
+    idx = rng.choice(4096, 64)
+    out, fin = be.rollout_outcomes(G, m.POLICY_UNI, corpus[idx], 2, 77)
+    for j, i in enumerate(idx):
+        exp, efin, _ = port.q_rollout_philox(corpus[i], m.DEFAULT_SEED, 77 + 2 * j, 2, policy=1, finals=True)
+        assert out[2 * j: 2 * j + 2].tobytes() == exp.tobytes() and fin[2 * j: 2 * j + 2].tobytes() == efin.tobytes()
+
+
+# ---- Tic-Tac-Toe ---------------------------------------------------------------------------------------
+def test_tictactoe_vs_golden(be):
+    g = golden("golden_t.npz")
+    out, _ = be.rollout_outcomes(T, 0, np.zeros(1, dtype=m.TSTATE_DTYPE), 20000, 0)
+    assert (out["score"] == g["empty_scores"]).all() and (out["draws"] == g["empty_draws"]).all()
+    st = np.zeros(len(g["states"]), dtype=m.TSTATE_DTYPE)
+    st["x_mask"], st["o_mask"] = g["states"][:, 0], g["states"][:, 1]
+    out, _ = be.rollout_outcomes(T, 0, st, 1, 7000)       # leaf j uses id 7000 + j
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+
+
+# ---- aggregation, partition independence, edge cases ------------------------------------------------------
+def test_leaf_sums_are_exact_and_order_free(be, corpus):
+    states = corpus[:37]
+    R = 257                                   # ragged: warps straddle leaves
+    out, _ = be.rollout_outcomes(G, m.POLICY_REF, states, R, 123, finals=False)
+    score, sums = be.rollout_batch(G, m.POLICY_REF, states, R, 123)
+    sc = out["score"].reshape(37, R)
+    for i in range(37):
+        exact = sum(Fraction(float(v)) for v in sc[i])
+        assert Fraction(int(sums["hi"][i]) * (1 << 29) + int(sums["lo"][i]), 1 << 57) == exact
+        assert int(sums["n"][i]) == R and score[i] == float(exact)
+
+
+def test_results_do_not_depend_on_batch_shape(be, corpus):
+    """Rollout id r always yields the same playout, however the ids are cut into leaves/launches."""
+    s = corpus[5]
+    a, _ = be.rollout_outcomes(G, m.POLICY_REF, s, 600, 1000, finals=False)
+    b1, _ = be.rollout_outcomes(G, m.POLICY_REF, s, 173, 1000, finals=False)
+    b2, _ = be.rollout_outcomes(G, m.POLICY_REF, s, 427, 1173, finals=False)
+    assert a.tobytes() == b1.tobytes() + b2.tobytes()
+    c, _ = be.rollout_outcomes(G, m.POLICY_REF, np.repeat(s, 3), 200, 1000, finals=False)
+    assert a.tobytes() == c.tobytes()
+
+
+def test_terminal_and_single_inputs(be):
+    s = m.quoridor_opening().copy()
+    s["wx"] = 8                                # White already on its goal row: no draws, score 1
+    out, fin = be.rollout_outcomes(G, m.POLICY_REF, s, 3, 0)
+    assert (out["score"] == 1.0).all() and (out["draws"] == 0).all() and (out["plies"] == 0).all() and (out["kind"] == 0).all()
+    s["wx"], s["bx"] = 3, 0                    # Black on row 0
+    out, _ = be.rollout_outcomes(G, m.POLICY_REF, s, 1, 0)
+    assert out["score"][0] == 0.0 and out["kind"][0] == 1
+    t = np.zeros(1, dtype=m.TSTATE_DTYPE)
+    t["x_mask"] = 0b000000111                  # x already won
+    out, _ = be.rollout_outcomes(T, 0, t, 2, 0)
+    assert (out["score"] == 1.0).all() and (out["draws"] == 0).all()
+
+
+def test_bad_arguments_are_refused(be):
+    s = m.quoridor_opening().copy()
+    s["bx"], s["by"] = 0, 4                    # both pawns on one square
+    with pytest.raises(m.BackendError) as e:
+        be.rollout_batch(G, m.POLICY_REF, s, 4)
+    assert e.value.status == 4
+    with pytest.raises(m.BackendError) as e:
+        be.rollout_batch(G, 7, m.quoridor_opening(), 4)
+    assert e.value.status == 3
+    be.submit(G, m.POLICY_REF, m.quoridor_opening(), 32)
+    with pytest.raises(m.BackendError) as e:
+        be.submit(G, m.POLICY_REF, m.quoridor_opening(), 32)
+    assert e.value.status == 6
+    be.wait()
+    with pytest.raises(m.BackendError) as e:
+        be.wait()
+    assert e.value.status == 5
+
+
+def test_full_size_properties(be):
+    """Config 2 size (1M rollouts from the opening): properties that need no CPU replay."""
+    n = 1 << 20
+    score, sums = be.rollout_batch(G, m.POLICY_REF, m.quoridor_opening(), n, 0)
+    assert int(sums["n"][0]) == n
+    mean = score[0] / n
+    g = golden("golden_q_distribution.npz")
+    ref = g["scores"][0]
+    assert abs(mean - ref.mean()) <= 3.0 * np.sqrt(ref.var(ddof=1) / len(ref) + ref.var(ddof=1) / n)
+    # same ids in two halves -> the exact integer sums add up
+    _, s1 = be.rollout_batch(G, m.POLICY_REF, m.quoridor_opening(), n // 2, 0)
+    _, s2 = be.rollout_batch(G, m.POLICY_REF, m.quoridor_opening(), n // 2, n // 2)
+    assert int(s1["lo"][0]) + int(s2["lo"][0]) == int(sums["lo"][0])
+    assert int(s1["hi"][0]) + int(s2["hi"][0]) == int(sums["hi"][0])

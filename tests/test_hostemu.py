@@ -1,0 +1,87 @@
+"""CPU: the DEVICE rule/rollout core (csrc/qcore.cuh, ttt_core.cuh) compiled for the host by
+tests/hostemu (test-only, never shipped) against the oracle and the reference goldens.  Lets the
+kernel logic be checked bit-for-bit on a box without a GPU; the -m gpu tests repeat this through
+the C ABI on the real kernels."""
+import numpy as np
+import pytest
+
+from oracle.reflib import opening_state
+from tests.util import golden, philox_stream
+
+
+@pytest.fixture(scope="module")
+def emu():
+    from tests.hostemu.emulib import EmuLib
+    return EmuLib()
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return golden("corpus_q.npy")
+
+
+def test_core_primitives_vs_golden(emu, corpus):
+    g = golden("golden_q_primitives.npz")
+    for j, i in enumerate(g["index"]):
+        p = emu.q_primitives(corpus[i])
+        for k in ("winner", "sp_white", "sp_black", "force_playwall"):
+            assert p[k] == g[k][j], (k, i)
+        assert p["eval"] == g["eval"][j]
+        assert (np.packbits(p["legal"], bitorder="little") == g["legal"][j]).all()
+        assert (np.packbits(p["cheap"], bitorder="little") == g["cheap"][j]).all()
+        s2 = g["steps2"][j]
+        assert (p["steps2"] == s2[s2 >= 0]).all()
+        if g["winner"][j] == 0:
+            assert emu.q_best_step(corpus[i]) == g["best_step"][j]
+
+
+def test_core_primitives_vs_oracle_on_corpus(emu, port, corpus):
+    for i in range(300, 4608, 9):
+        a, b = port.q_primitives(corpus[i]), emu.q_primitives(corpus[i])
+        for k in ("winner", "sp_white", "sp_black", "force_playwall", "eval"):
+            assert a[k] == b[k]
+        assert (a["legal"] == b["legal"]).all() and (a["cheap"] == b["cheap"]).all()
+
+
+def test_core_replay_vs_golden(emu, corpus):
+    g = golden("golden_q_replay.npz")
+    seed = int(g["seed"])
+    streams = np.stack([philox_stream(seed, int(i), 16384) for i in g["id"]])
+    out, fin, _ = emu.q_rollout_streams(corpus[g["index"]], streams)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    assert fin.tobytes() == g["final"].tobytes()
+
+
+def test_core_philox_vs_golden(emu):
+    g = golden("golden_q_opening.npz")
+    out, _, _ = emu.q_rollout_philox(opening_state(), int(g["seed"]), 0, 512)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+
+
+def test_core_uniform_vs_golden(emu, corpus):
+    g = golden("golden_q_uniform.npz")
+    for j, i in enumerate(g["index"]):
+        out, _, _ = emu.q_rollout_philox(corpus[i], int(g["seed"]), int(g["id"][j]), 1, policy=1)
+        assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]
+        assert out["kind"][0] == g["kind"][j] and out["plies"][0] == g["plies"][j]
+
+
+def test_core_play_vs_oracle(emu, port, corpus):
+    rng = np.random.default_rng(3)
+    for i in rng.choice(4608, 200, replace=False):
+        for mid in rng.integers(0, 209, size=12):
+            a_ok, a = port.q_play(corpus[i], int(mid))
+            b_ok, b = emu.q_play(corpus[i], int(mid))
+            assert a_ok == b_ok and a.tobytes() == b.tobytes()
+
+
+def test_core_tictactoe_vs_golden(emu):
+    g = golden("golden_t.npz")
+    out = emu.t_rollout_philox(0, 0, int(g["seed"]), 0, 20000)
+    assert (out["score"] == g["empty_scores"]).all() and (out["draws"] == g["empty_draws"]).all()
+    for j in range(0, len(g["states"]), 3):
+        x, o = int(g["states"][j][0]), int(g["states"][j][1])
+        out = emu.t_rollout_philox(x, o, int(g["seed"]), 7000 + j, 1)
+        assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]

@@ -1,0 +1,126 @@
+"""CPU: the plain-C oracle (oracle/*.c) against the golden vectors generated from the compiled,
+unmodified reference (tests/golden/make_golden.py).  This is what pins the oracle."""
+import numpy as np
+import pytest
+
+from oracle.reflib import QSTATE_DTYPE, opening_state
+from tests.util import golden, philox_stream
+
+
+@pytest.fixture(scope="module")
+def corpus():
+    return golden("corpus_q.npy")
+
+
+def test_philox_known_answers():
+    from tests.util import philox4x32_10
+    # Random123 kat_vectors for philox4x32-10
+    v = philox4x32_10([0], [0], [0], [0], 0, 0)
+    assert [int(x[0]) for x in v] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    v = philox4x32_10([0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], [0xFFFFFFFF], 0xFFFFFFFF, 0xFFFFFFFF)
+    assert [int(x[0]) for x in v] == [0x408F276D, 0x41C83B0E, 0xA20BC7C6, 0x6D5451FD]
+    v = philox4x32_10([0x243F6A88], [0x85A308D3], [0x13198A2E], [0x03707344], 0xA4093822, 0x299F31D0)
+    assert [int(x[0]) for x in v] == [0xD16CFE09, 0x94FDCCEB, 0x5001E420, 0x24126EA1]
+
+
+def test_corpus_shape(corpus):
+    assert corpus.dtype == QSTATE_DTYPE and corpus.shape == (4608,)
+    walls = np.array([bin(int(s["h_anchor"])).count("1") + bin(int(s["v_anchor"])).count("1") for s in corpus[:4096]])
+    assert walls.min() >= 10 and walls.max() <= 20
+
+
+def test_primitives_match_reference(port, corpus):
+    g = golden("golden_q_primitives.npz")
+    for j, i in enumerate(g["index"]):
+        p = port.q_primitives(corpus[i])
+        for k in ("winner", "sp_white", "sp_black", "force_playwall"):
+            assert p[k] == g[k][j], (k, i)
+        assert p["eval"] == g["eval"][j]
+        assert (np.packbits(p["legal"], bitorder="little") == g["legal"][j]).all()
+        assert (np.packbits(p["cheap"], bitorder="little") == g["cheap"][j]).all()
+        n = int(g["n_actions"][j])
+        assert len(p["actions"]) == n and (p["actions"] == g["actions"][j, :n]).all()
+        s2 = g["steps2"][j]
+        assert (p["steps2"] == s2[s2 >= 0]).all()
+        if not p["terminal"]:
+            assert port.q_best_step(corpus[i]) == g["best_step"][j]
+
+
+def test_replay_matches_reference(port, corpus):
+    g = golden("golden_q_replay.npz")
+    seed = int(g["seed"])
+    for j, i in enumerate(g["index"]):
+        st = philox_stream(seed, int(g["id"][j]), 16384)
+        r = port.q_rollout_stream(corpus[i], st)
+        assert r["score"] == g["score"][j] and r["draws"] == g["draws"][j]
+        assert r["kind"] == g["kind"][j] and r["plies"] == g["plies"][j]
+        assert r["final"].tobytes() == g["final"][j].tobytes()
+        m = g["moves"][j]
+        assert (r["moves"] == m[m >= 0]).all()
+        # the same playout through the oracle's own Philox path
+        out, fin, _ = port.q_rollout_philox(corpus[i], seed, int(g["id"][j]), 1, finals=True)
+        assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]
+        assert fin[0].tobytes() == g["final"][j].tobytes()
+
+
+def test_opening_rollouts_match_reference(port):
+    g = golden("golden_q_opening.npz")
+    out, _, _ = port.q_rollout_philox(opening_state(), int(g["seed"]), 0, 512)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+
+
+def test_known_answer_streams(port):
+    g = golden("golden_kat.npz")
+    streams = {
+        "S0": np.zeros(65536, np.uint32),
+        "S1": np.full(65536, 0x80000000, np.uint32),
+        "S2": ((np.arange(65536, dtype=np.uint64) * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)).astype(np.uint32),
+        "S3": (((np.arange(65536, dtype=np.uint64) + np.uint64(1)) * np.uint64(0x9E3779B9)) ^ (np.arange(65536, dtype=np.uint64) >> np.uint64(3))).astype(np.uint32),
+    }
+    for name, st in streams.items():
+        r = port.q_rollout_stream(opening_state(), st)
+        t = port.t_rollout_stream(0, 0, st)
+        assert [r["score"], r["draws"], r["kind"], r["plies"], t[0], t[1]] == list(g[name]), name
+    # S0 is also the value recorded independently during the survey
+    assert g["S0"][0] == 0.89999999999999991 and g["S0"][1] == 2336
+
+
+def test_uniform_policy_matches_reference_api_driver(port, corpus):
+    g = golden("golden_q_uniform.npz")
+    for j, i in enumerate(g["index"]):
+        out, _, _ = port.q_rollout_philox(corpus[i], int(g["seed"]), int(g["id"][j]), 1, policy=1)
+        assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]
+        assert out["kind"][0] == g["kind"][j] and out["plies"][0] == g["plies"][j]
+
+
+def test_free_running_scores_match_reference(port, corpus):
+    g = golden("golden_q_distribution.npz")
+    n = int(g["n"])
+    for j, i in enumerate(g["index"][:4]):
+        s = opening_state() if i < 0 else corpus[i]
+        out, _, _ = port.q_rollout_philox(s, int(g["seed"]), int(g["first_id"]), n)
+        assert (out["score"] == g["scores"][j]).all()
+
+
+def test_tictactoe_matches_reference(port):
+    g = golden("golden_t.npz")
+    for j, (x, o, winner, terminal, p1, amask) in enumerate(g["states"]):
+        p = port.t_primitives(int(x), int(o))
+        assert (p["winner"], p["terminal"], p["player1_turn"]) == (winner, terminal, p1)
+        assert sum(1 << int(c) for c in p["actions"]) == amask
+        out = port.t_rollout_philox(int(x), int(o), int(g["seed"]), 7000 + j, 1)
+        assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]
+    out = port.t_rollout_philox(0, 0, int(g["seed"]), 0, 20000)
+    assert (out["score"] == g["empty_scores"]).all() and (out["draws"] == g["empty_draws"]).all()
+
+
+def test_exact_leaf_sum(port):
+    g = golden("golden_q_opening.npz")
+    from fractions import Fraction
+    acc, as_double = port.leaf_sum(g["score"])
+    exact = sum(Fraction(float(s)) for s in g["score"])
+    assert Fraction(int(acc["hi"]) * (1 << 29) + int(acc["lo"]), 1 << 57) == exact
+    assert int(acc["n"]) == len(g["score"])
+    # correctly rounded conversion
+    assert as_double == float(exact)
