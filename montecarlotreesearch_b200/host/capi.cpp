@@ -1,0 +1,179 @@
+// capi.cpp — flat C entry points over the C++ host side, for ctypes-driven tests and bench scripts.
+// (The C++ classes are the interface a reference user programs against; this file only lets Python
+// drive them.)  A caller may install its own RolloutBackend through a callback — the tests use that
+// to exercise the tree logic on a machine without a GPU; nothing in the product installs one.
+#include "mcts.h"
+#include "Quoridor.h"
+#include "TicTacToe.h"
+#include "mctsb.h"
+#include <cstring>
+#include <memory>
+
+extern "C" {
+typedef void (*mcts_rollout_cb)(int game, int policy, const void *states, int n_leaves, uint32_t rollouts_per_leaf,
+                                uint64_t first_rollout_id, double *score_sum, void *user);
+}
+
+namespace {
+class CallbackBackend : public RolloutBackend {
+    mcts_rollout_cb cb; void *user;
+    int g = 0, p = 0, n = 0; uint32_t R = 0; uint64_t first = 0; std::vector<unsigned char> held;
+public:
+    CallbackBackend(mcts_rollout_cb cb, void *user) : cb(cb), user(user) {}
+    void rollout_batch(int game, int policy, const void *states, int n_leaves, uint32_t rpl, uint64_t first_id, double *out) override {
+        cb(game, policy, states, n_leaves, rpl, first_id, out, user);
+    }
+    void submit(int game, int policy, const void *states, int n_leaves, uint32_t rpl, uint64_t first_id) override {
+        size_t rec = game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate);
+        held.assign((const unsigned char *)states, (const unsigned char *)states + rec * n_leaves);
+        g = game; p = policy; n = n_leaves; R = rpl; first = first_id;
+    }
+    void wait(double *out) override { cb(g, p, held.data(), n, R, first, out, user); }
+};
+
+struct HostSession {
+    std::unique_ptr<RolloutBackend> backend;
+    std::unique_ptr<MCTS_tree> tree;
+    int game = 0;
+};
+
+MCTS_state *make_state(int game, const void *packed, int policy) {
+    if (game == MCTSB_GAME_QUORIDOR) return new Quoridor_state(*(const mctsb_qstate *)packed, policy);
+    const mctsb_tstate *t = (const mctsb_tstate *)packed;
+    return new TicTacToe_state(t->x_mask & 0x1ff, t->o_mask & 0x1ff, (t->o_mask & 0x8000) ? 'o' : 'x');
+}
+
+int move_index(int game, const MCTS_move *m) {
+    if (game == MCTSB_GAME_QUORIDOR) return ((const Quoridor_move *)m)->canonical_id();
+    const TicTacToe_move *t = (const TicTacToe_move *)m;
+    return t->x * 3 + t->y;
+}
+
+MCTS_move *make_move(int game, int id, const MCTS_state *s) {
+    if (game == MCTSB_GAME_QUORIDOR) return Quoridor_move::from_canonical_id(id, ((const Quoridor_state *)s)->whose_turn());
+    return new TicTacToe_move(id / 3, id % 3, ((const TicTacToe_state *)s)->get_turn());
+}
+}  // namespace
+
+extern "C" {
+
+// ---- rule-level entry points of the host game class (CPU only, no rollouts) ----------------------
+int mcts_host_q_actions(const mctsb_qstate *s, int32_t *ids, int max_ids) {
+    Quoridor_state q(*s);
+    queue<MCTS_move *> *Q = q.actions_to_try();
+    int n = 0;
+    while (!Q->empty()) { if (n < max_ids) ids[n] = ((Quoridor_move *)Q->front())->canonical_id(); n++; delete Q->front(); Q->pop(); }
+    delete Q;
+    return n;
+}
+
+int mcts_host_q_next(const mctsb_qstate *s, int id, mctsb_qstate *out) {
+    Quoridor_state q(*s);
+    Quoridor_move *m = Quoridor_move::from_canonical_id(id, q.whose_turn());
+    bool ok = q.legal_move(m);
+    if (ok) { MCTS_state *n = q.next_state(m); ((Quoridor_state *)n)->pack(*out); delete n; } else *out = *s;
+    delete m;
+    return ok ? 1 : 0;
+}
+
+int mcts_host_q_info(const mctsb_qstate *s, int32_t *info6, double *eval) {
+    Quoridor_state q(*s);
+    char w = q.check_winner();
+    info6[0] = w == 'W' ? 1 : w == 'B' ? 2 : 0;
+    info6[1] = q.get_shortest_path('W'); info6[2] = q.get_shortest_path('B');
+    info6[3] = q.force_playwall() ? 1 : 0; info6[4] = q.is_terminal() ? 1 : 0; info6[5] = q.player1_turn() ? 1 : 0;
+    if (eval) *eval = q.evaluate();
+    Quoridor_move *b = q.is_terminal() ? NULL : q.get_best_step_move(q.whose_turn());
+    int r = b ? b->canonical_id() : -1;
+    delete b;
+    return r;
+}
+
+int mcts_host_q_sprint(const mctsb_qstate *s, int id, char *buf, int cap) {
+    Quoridor_state q(*s);
+    Quoridor_move *m = Quoridor_move::from_canonical_id(id, q.whose_turn());
+    string t = m->sprint();
+    delete m;
+    strncpy(buf, t.c_str(), cap - 1); buf[cap - 1] = 0;
+    return (int)t.size();
+}
+
+// ---- tree sessions ---------------------------------------------------------------------------------
+// backend: cb == NULL -> CudaRolloutBackend(device, seed) (fails without a GPU); else the caller's callback.
+void *mcts_host_session_create(int game, const void *packed_root, int policy, int device, uint64_t seed,
+                               uint32_t rollouts_per_leaf, uint32_t leaves_per_flush, mcts_rollout_cb cb, void *user,
+                               char *err, int err_cap) {
+    try {
+        mcts_set_verbose(false);
+        std::unique_ptr<HostSession> h(new HostSession());
+        if (cb) h->backend.reset(new CallbackBackend(cb, user));
+        else h->backend.reset(new CudaRolloutBackend(device, seed));
+        MCTS_batching b; b.rollouts_per_leaf = rollouts_per_leaf; b.leaves_per_flush = leaves_per_flush;
+        h->game = game;
+        h->tree.reset(new MCTS_tree(make_state(game, packed_root, policy), h->backend.get(), b));
+        return h.release();
+    } catch (const std::exception &e) {
+        if (err && err_cap > 0) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+        return NULL;
+    }
+}
+
+void mcts_host_session_destroy(void *hs) { delete (HostSession *)hs; }
+
+int mcts_host_grow(void *hs, int max_iter, double max_seconds, char *err, int err_cap) {
+    try { ((HostSession *)hs)->tree->grow_tree(max_iter, max_seconds); return 0; }
+    catch (const std::exception &e) { if (err && err_cap > 0) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; } return -1; }
+}
+
+// out4 = {root simulations, root score, tree size, #children}; children: {move id, simulations, score} each
+int mcts_host_root_stats(void *hs, double *out4, double *children, int max_children) {
+    HostSession *h = (HostSession *)hs;
+    const MCTS_node *root = h->tree->get_root();
+    out4[0] = root->get_number_of_simulations(); out4[1] = root->get_score(); out4[2] = root->get_size();
+    out4[3] = (double)root->get_children().size();
+    int n = 0;
+    for (const MCTS_node *c : root->get_children()) {
+        if (n >= max_children) break;
+        children[3 * n] = move_index(h->game, c->get_move()); children[3 * n + 1] = c->get_number_of_simulations();
+        children[3 * n + 2] = c->get_score(); n++;
+    }
+    return n;
+}
+
+int mcts_host_best_move(void *hs) {
+    HostSession *h = (HostSession *)hs;
+    MCTS_node *b = h->tree->select_best_child();
+    return b ? move_index(h->game, b->get_move()) : -1;
+}
+
+int mcts_host_advance(void *hs, int move_id) {
+    HostSession *h = (HostSession *)hs;
+    MCTS_move *m = make_move(h->game, move_id, h->tree->get_current_state());
+    h->tree->advance_tree(m);
+    delete m;    // the tree keeps its own copy (the child's move) or built a fresh root
+    return h->tree->get_current_state()->is_terminal() ? 1 : 0;
+}
+
+int mcts_host_current_state(void *hs, void *packed_out) {
+    HostSession *h = (HostSession *)hs;
+    return h->tree->get_current_state()->gpu_pack(packed_out) ? 0 : -1;
+}
+
+void mcts_host_counters(void *hs, uint64_t *flushes, uint64_t *rollouts) {
+    HostSession *h = (HostSession *)hs;
+    *flushes = h->tree->get_flushes(); *rollouts = h->tree->get_rollouts_played();
+}
+
+int mcts_host_export_root(void *hs, double *buf, int cap) {
+    std::vector<double> v; ((HostSession *)hs)->tree->export_root_stats(v);
+    if ((int)v.size() > cap) return -(int)v.size();
+    memcpy(buf, v.data(), v.size() * sizeof(double));
+    return (int)v.size();
+}
+
+int mcts_host_import_root(void *hs, const double *buf, int n) {
+    try { std::vector<double> v(buf, buf + n); ((HostSession *)hs)->tree->import_root_stats(v); return 0; }
+    catch (const std::exception &) { return -1; }
+}
+
+}  // extern "C"

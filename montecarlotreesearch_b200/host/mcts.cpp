@@ -1,0 +1,343 @@
+// mcts.cpp — host search tree (Selection, Expansion, Backpropagation) with the Simulation phase
+// flushed to the GPU rollout backend.  Behavioural contract: the reference's mcts/src/mcts.cpp
+// (cited per function); the code is written from scratch.
+#include "mcts.h"
+#include "mctsb.h"
+#include <algorithm>
+#include <cassert>
+#include <cmath>
+#include <ctime>
+
+static bool g_verbose = true;
+void mcts_set_verbose(bool on) { g_verbose = on; }
+
+/*** MCTS_node ***/
+
+// reference mcts.cpp:15-21 — actions and terminal flag are computed eagerly; the node owns state, move,
+// children and whatever stays in untried_actions (mcts.cpp:23-35)
+MCTS_node::MCTS_node(MCTS_node *parent, MCTS_state *state, const MCTS_move *move, MCTS_tree *tree)
+    : terminal(false), size(0), number_of_simulations(0), score(0.0), state(state), move(move),
+      children(new vector<MCTS_node *>()), parent(parent), untried_actions(NULL), tree(tree), virtual_visits(0) {
+    children->reserve(STARTING_NUMBER_OF_CHILDREN);
+    untried_actions = state->actions_to_try();
+    terminal = state->is_terminal();
+}
+
+MCTS_node::~MCTS_node() {
+    delete state;
+    delete move;
+    for (MCTS_node *c : *children) delete c;
+    delete children;
+    while (!untried_actions->empty()) { delete untried_actions->front(); untried_actions->pop(); }
+    delete untried_actions;
+}
+
+bool MCTS_node::is_fully_expanded() const { return terminal || untried_actions->empty(); }   // mcts.cpp:92-94
+bool MCTS_node::is_terminal() const { return terminal; }
+unsigned int MCTS_node::get_size() const { return size; }
+const MCTS_move *MCTS_node::get_move() const { return move; }
+const MCTS_state *MCTS_node::get_current_state() const { return state; }
+
+// Expansion only: pop the FRONT of the FIFO (children appear in actions_to_try order, mcts.cpp:46-54)
+MCTS_node *MCTS_node::expand_no_rollout() {
+    if (terminal || untried_actions->empty()) return NULL;
+    MCTS_move *next_move = untried_actions->front();
+    untried_actions->pop();
+    MCTS_state *next = state->next_state(next_move);
+    MCTS_node *child = new MCTS_node(this, next, next_move, tree);
+    children->push_back(child);
+    return child;
+}
+
+// reference mcts.cpp:37-55
+void MCTS_node::expand() {
+    if (is_terminal()) { rollout(); return; }          // terminal nodes are re-scored (mcts.cpp:38-40)
+    if (is_fully_expanded()) { cerr << "Warning: Cannot expanded this node any more!" << endl; return; }
+    MCTS_node *child = expand_no_rollout();
+    child->rollout();
+}
+
+// Simulation phase of ONE leaf.  Replaces mcts.cpp:57-81: instead of NUMBER_OF_THREADS RolloutJobs on
+// the pthread pool, `rollouts_per_leaf` playouts of this node's state run on the GPU and their sum
+// is back-propagated with the matching count.
+void MCTS_node::rollout() {
+    uint32_t R = tree ? tree->batching.rollouts_per_leaf : 4;
+    int game = state->gpu_game_id();
+    if (game >= 0) {
+        unsigned char packed[32];
+        if (!state->gpu_pack(packed)) throw std::runtime_error("gpu_pack failed for a state that advertises a gpu_game_id");
+        RolloutBackend *be = tree ? tree->get_backend() : default_rollout_backend();
+        double sum = 0.0;
+        be->rollout_batch(game, state->gpu_policy_id(), packed, 1, R, next_rollout_ids(R), &sum);
+        if (tree) { tree->flushes++; tree->rollouts_played += R; }
+        backpropagate(sum, (int)R);
+        return;
+    }
+    // a game the backend does not know: its own virtual rollout(), validated like mcts.cpp:68-75
+    double sum = 0.0;
+    for (uint32_t i = 0; i < R; i++) {
+        double r = state->rollout();
+        if (r >= 0.0 && r <= 1.0) sum += r;
+        else cerr << "Warning: Invalid result when aggregating parallel rollouts" << endl;
+    }
+    backpropagate(sum, (int)R);
+}
+
+// reference mcts.cpp:83-90: score += w; n += n; every ancestor's `size` counts the event
+void MCTS_node::backpropagate(double w, int n) {
+    for (MCTS_node *node = this; node != NULL; node = node->parent) {
+        node->score += w;
+        node->number_of_simulations += (unsigned)n;
+        if (node->parent != NULL) node->parent->size++;
+    }
+}
+
+void MCTS_node::add_virtual(int n) {
+    for (MCTS_node *node = this; node != NULL; node = node->parent) node->virtual_visits = (unsigned)((int)node->virtual_visits + n);
+}
+
+// reference mcts.cpp:104-130.  UCT on the win rate of the side to move AT THIS NODE; first strict
+// maximum wins; c <= 0 means pure win rate.  Simulations still in flight (virtual_visits) count as
+// losses for the side choosing here — zero unless leaves_per_flush > 1.
+MCTS_node *MCTS_node::select_best_child(double c) const {
+    if (children->empty()) return NULL;
+    if (children->size() == 1) return children->at(0);
+    double best = -1;
+    MCTS_node *argmax = NULL;
+    const bool p1 = state->player1_turn();
+    const double n_parent = (double)(number_of_simulations + virtual_visits);
+    for (MCTS_node *child : *children) {
+        double n = (double)(child->number_of_simulations + child->virtual_visits);
+        double s = child->score + (p1 ? 0.0 : (double)child->virtual_visits);
+        double winrate = s / n;
+        if (!p1) winrate = 1.0 - winrate;
+        double uct = c > 0 ? winrate + c * sqrt(log(n_parent) / n) : winrate;
+        if (uct > best) { best = uct; argmax = child; }
+    }
+    return argmax;
+}
+
+// reference mcts.cpp:132-157
+MCTS_node *MCTS_node::advance_tree(const MCTS_move *m) {
+    MCTS_node *next = NULL;
+    for (MCTS_node *child : *children) {
+        if (*(child->move) == *m) next = child;
+        else delete child;
+    }
+    children->clear();
+    if (next == NULL) {
+        if (g_verbose) cout << "INFO: Didn't find child node. Had to start over." << endl;
+        next = new MCTS_node(NULL, state->next_state(m), NULL, tree);
+    } else {
+        next->parent = NULL;
+    }
+    return next;
+}
+
+double MCTS_node::calculate_winrate(bool player1turn) const {   // mcts.cpp:252-258
+    return player1turn ? score / number_of_simulations : 1.0 - score / number_of_simulations;
+}
+
+// reference mcts.cpp:222-250 (note: sorts the children in place)
+void MCTS_node::print_stats() const {
+    const unsigned TOPK = 10;
+    if (number_of_simulations == 0) { cout << "Tree not expanded yet" << endl; return; }
+    cout << "___ INFO _______________________" << endl
+         << "Tree size: " << size << endl
+         << "Number of simulations: " << number_of_simulations << endl
+         << "Branching factor at root: " << children->size() << endl
+         << "Chances of P1 winning: " << setprecision(4) << 100.0 * (score / number_of_simulations) << "%" << endl;
+    const bool p1 = state->player1_turn();
+    std::sort(children->begin(), children->end(), [p1](const MCTS_node *a, const MCTS_node *b) {
+        return a->calculate_winrate(p1) > b->calculate_winrate(p1);
+    });
+    cout << "Best moves:" << endl;
+    for (unsigned i = 0; i < children->size() && i < TOPK; i++)
+        cout << "  " << i + 1 << ". " << children->at(i)->move->sprint() << "  -->  "
+             << setprecision(4) << 100.0 * children->at(i)->calculate_winrate(p1) << "%" << endl;
+    cout << "________________________________" << endl;
+}
+
+
+/*** MCTS_tree ***/
+
+MCTS_tree::MCTS_tree(MCTS_state *starting_state) : root(NULL), backend(NULL), flushes(0), rollouts_played(0) {
+    assert(starting_state != NULL);
+    root = new MCTS_node(NULL, starting_state, NULL, this);
+}
+
+MCTS_tree::MCTS_tree(MCTS_state *starting_state, RolloutBackend *backend, MCTS_batching batching)
+    : root(NULL), backend(backend), batching(batching), flushes(0), rollouts_played(0) {
+    assert(starting_state != NULL);
+    root = new MCTS_node(NULL, starting_state, NULL, this);
+}
+
+MCTS_tree::~MCTS_tree() { delete root; }
+
+RolloutBackend *MCTS_tree::get_backend() { return backend ? backend : default_rollout_backend(); }
+
+// reference mcts.cpp:161-171
+MCTS_node *MCTS_tree::select(double c) {
+    MCTS_node *node = root;
+    while (!node->is_terminal()) {
+        if (!node->is_fully_expanded()) return node;
+        node = node->select_best_child(c);
+    }
+    return node;
+}
+
+// One kernel launch for all the leaves collected by grow_tree: every leaf gets rollouts_per_leaf
+// playouts; results come back as one exact sum per leaf and are back-propagated in selection order.
+void MCTS_tree::flush_leaves(vector<MCTS_node *> &leaves) {
+    if (leaves.empty()) return;
+    const uint32_t R = batching.rollouts_per_leaf;
+    size_t i = 0;
+    while (i < leaves.size()) {
+        // group consecutive leaves that the backend can take in one call (same game/policy); others fall back
+        int game = leaves[i]->state->gpu_game_id();
+        if (game < 0) { leaves[i]->add_virtual(-(int)R); leaves[i]->rollout(); i++; continue; }
+        int policy = leaves[i]->state->gpu_policy_id();
+        size_t rec = game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate), j = i;
+        vector<unsigned char> packed;
+        while (j < leaves.size() && leaves[j]->state->gpu_game_id() == game && leaves[j]->state->gpu_policy_id() == policy) {
+            packed.resize((j - i + 1) * rec);
+            if (!leaves[j]->state->gpu_pack(&packed[(j - i) * rec])) throw std::runtime_error("gpu_pack failed");
+            j++;
+        }
+        vector<double> sums(j - i, 0.0);
+        get_backend()->rollout_batch(game, policy, packed.data(), (int)(j - i), R, next_rollout_ids((uint64_t)R * (j - i)), sums.data());
+        flushes++; rollouts_played += (uint64_t)R * (j - i);
+        for (size_t k = i; k < j; k++) {
+            leaves[k]->add_virtual(-(int)R);
+            leaves[k]->backpropagate(sums[k - i], (int)R);
+        }
+        i = j;
+    }
+    leaves.clear();
+}
+
+// reference mcts.cpp:182-210: up to max_iter Selection+Expansion+Simulation+Backpropagation rounds,
+// stopped early when difftime(now, start) > max_time (whole seconds, strict).
+void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
+    if (g_verbose) cout << "Growing tree..." << endl;
+    time_t start_t, now_t;
+    time(&start_t);
+    double dt = 0;
+    const uint32_t K = batching.leaves_per_flush == 0 ? 1 : batching.leaves_per_flush;
+    int i = 0;
+    if (K == 1) {
+        for (; i < max_iter; i++) {
+            MCTS_node *node = select();
+            node->expand();
+            time(&now_t);
+            dt = difftime(now_t, start_t);
+            if (dt > max_time_in_seconds) {
+                if (g_verbose) cout << "Early stopping: Made " << (i + 1) << " iterations in " << dt << " seconds." << endl;
+                break;
+            }
+        }
+    } else {
+        vector<MCTS_node *> leaves;
+        while (i < max_iter) {
+            for (uint32_t k = 0; k < K && i < max_iter; k++, i++) {
+                MCTS_node *node = select();
+                MCTS_node *leaf = node->is_terminal() ? node : node->expand_no_rollout();
+                if (leaf == NULL) leaf = node;                        // cannot happen: select() returns expandable or terminal nodes
+                leaf->add_virtual((int)batching.rollouts_per_leaf);   // keep the next selection away from this path
+                leaves.push_back(leaf);
+            }
+            flush_leaves(leaves);
+            time(&now_t);
+            dt = difftime(now_t, start_t);
+            if (dt > max_time_in_seconds) {
+                if (g_verbose) cout << "Early stopping: Made " << i << " iterations in " << dt << " seconds." << endl;
+                break;
+            }
+        }
+    }
+    if (g_verbose) {
+        time(&now_t);
+        cout << "Finished in " << difftime(now_t, start_t) << " seconds." << endl;
+    }
+}
+
+unsigned int MCTS_tree::get_size() const { return root->get_size(); }
+const MCTS_state *MCTS_tree::get_current_state() const { return root->get_current_state(); }
+MCTS_node *MCTS_tree::select_best_child() { return root->select_best_child(0.0); }   // mcts.cpp:268-270
+void MCTS_tree::print_stats() const { root->print_stats(); }
+
+void MCTS_tree::advance_tree(const MCTS_move *move) {   // mcts.cpp:260-264
+    MCTS_node *old_root = root;
+    root = root->advance_tree(move);
+    delete old_root;
+}
+
+// ---- root-parallel merge ---------------------------------------------------------------------------
+// Slot k belongs to the k-th move of root->state->actions_to_try() (the same list on every rank), NOT to
+// the k-th child: children exist only as far as expanded and print_stats() re-sorts them (mcts.cpp:234-242).
+static vector<MCTS_move *> root_action_list(const MCTS_state *s) {
+    vector<MCTS_move *> v;
+    queue<MCTS_move *> *q = s->actions_to_try();
+    while (!q->empty()) { v.push_back(q->front()); q->pop(); }
+    delete q;
+    return v;
+}
+
+void MCTS_tree::export_root_stats(vector<double> &out) const {
+    vector<MCTS_move *> acts = root_action_list(root->state);
+    out.assign(2 * acts.size(), 0.0);
+    for (MCTS_node *c : *root->children)
+        for (size_t k = 0; k < acts.size(); k++)
+            if (*acts[k] == *c->move) { out[2 * k] = c->number_of_simulations; out[2 * k + 1] = c->score; break; }
+    for (MCTS_move *m : acts) delete m;
+}
+
+void MCTS_tree::import_root_stats(const vector<double> &in) {
+    vector<MCTS_move *> acts = root_action_list(root->state);
+    if (in.size() != 2 * acts.size()) { for (MCTS_move *m : acts) delete m; throw std::invalid_argument("root stats size mismatch"); }
+    // children are created in action order; make sure every slot that carries statistics has its child
+    size_t last = 0;
+    for (size_t k = 0; k < acts.size(); k++) if (in[2 * k] > 0) last = k + 1;
+    while (root->children->size() < last && root->expand_no_rollout() != NULL) {}
+    double sims = 0, score = 0;
+    for (MCTS_node *c : *root->children)
+        for (size_t k = 0; k < acts.size(); k++)
+            if (*acts[k] == *c->move) {
+                c->number_of_simulations = (unsigned)in[2 * k]; c->score = in[2 * k + 1];
+                sims += in[2 * k]; score += in[2 * k + 1];
+                break;
+            }
+    root->number_of_simulations = (unsigned)sims;
+    root->score = score;
+    for (MCTS_move *m : acts) delete m;
+}
+
+
+/*** MCTS_agent ***/
+
+MCTS_agent::MCTS_agent(MCTS_state *starting_state, int max_iter, int max_seconds)
+    : tree(new MCTS_tree(starting_state)), max_iter(max_iter), max_seconds(max_seconds) {}
+
+MCTS_agent::MCTS_agent(MCTS_state *starting_state, int max_iter, int max_seconds, RolloutBackend *backend, MCTS_batching batching)
+    : tree(new MCTS_tree(starting_state, backend, batching)), max_iter(max_iter), max_seconds(max_seconds) {}
+
+MCTS_agent::~MCTS_agent() { delete tree; }
+
+// reference mcts.cpp:281-306
+const MCTS_move *MCTS_agent::genmove(const MCTS_move *enemy_move) {
+    if (enemy_move != NULL) tree->advance_tree(enemy_move);
+    if (tree->get_current_state()->is_terminal()) return NULL;
+    if (g_verbose) cout << "___ DEBUG ______________________" << endl << "Growing tree..." << endl;
+    tree->grow_tree(max_iter, max_seconds);
+    if (g_verbose) cout << "Tree size: " << tree->get_size() << endl << "________________________________" << endl;
+    MCTS_node *best_child = tree->select_best_child();
+    if (best_child == NULL) {
+        cerr << "Warning: Tree root has no children! Possibly terminal node!" << endl;
+        return NULL;
+    }
+    const MCTS_move *best_move = best_child->get_move();
+    tree->advance_tree(best_move);
+    return best_move;
+}
+
+const MCTS_state *MCTS_agent::get_current_state() const { return tree->get_current_state(); }

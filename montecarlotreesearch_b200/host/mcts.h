@@ -1,0 +1,117 @@
+// mcts.h — host search tree.  Same public interface as the reference's mcts/include/mcts.h:26-79
+// (MCTS_node / MCTS_tree / MCTS_agent: select, select_best_child, grow_tree, advance_tree, get_size,
+// get_current_state, print_stats, genmove, feedback); written from scratch.  The tree (UCT
+// selection, expansion, backpropagation) stays on the host; the Simulation phase — the reference's
+// RolloutJob fan-out onto a pthread JobScheduler (mcts.h:82-91, mcts.cpp:57-81) — is replaced by
+// batched flushes to the GPU rollout backend (rollout_backend.h -> include/mctsb.h).
+#ifndef MCTS_H
+#define MCTS_H
+
+#include "state.h"
+#include "rollout_backend.h"
+#include <cstdint>
+#include <iomanip>
+#include <queue>
+#include <vector>
+
+#define STARTING_NUMBER_OF_CHILDREN 32   // same preallocation hint as the reference (mcts.h:11)
+
+using namespace std;
+
+// How the Simulation phase is batched.  The reference plays NUMBER_OF_THREADS = 4 rollouts of one
+// leaf per iteration (JobScheduler.h:10, mcts.cpp:62-64); here one iteration plays
+// `rollouts_per_leaf` of them on the GPU, and `leaves_per_flush` > 1 selects that many distinct
+// leaves (virtual loss keeps the selections apart) and flushes them in one kernel launch.
+struct MCTS_batching {
+    uint32_t rollouts_per_leaf = 4;
+    uint32_t leaves_per_flush = 1;
+};
+
+class MCTS_tree;
+
+class MCTS_node {
+    friend class MCTS_tree;
+    bool terminal;
+    unsigned int size;
+    unsigned int number_of_simulations;
+    double score;
+    MCTS_state *state;
+    const MCTS_move *move;
+    vector<MCTS_node *> *children;
+    MCTS_node *parent;
+    queue<MCTS_move *> *untried_actions;
+    MCTS_tree *tree;                       // owner (batching parameters, backend, rollout ids); may be NULL
+    unsigned int virtual_visits;           // pending simulations counted as losses while a flush is in flight
+    void backpropagate(double w, int n);
+    void add_virtual(int n);
+    MCTS_node *expand_no_rollout();        // Expansion without Simulation; NULL when nothing to expand
+public:
+    MCTS_node(MCTS_node *parent, MCTS_state *state, const MCTS_move *move, MCTS_tree *tree = NULL);
+    ~MCTS_node();
+    bool is_fully_expanded() const;
+    bool is_terminal() const;
+    const MCTS_move *get_move() const;
+    unsigned int get_size() const;
+    void expand();
+    void rollout();
+    MCTS_node *select_best_child(double c) const;
+    MCTS_node *advance_tree(const MCTS_move *m);
+    const MCTS_state *get_current_state() const;
+    void print_stats() const;
+    double calculate_winrate(bool player1turn) const;
+    // read-only accessors (not in the reference; used by tests and the multi-GPU root merge)
+    unsigned int get_number_of_simulations() const { return number_of_simulations; }
+    double get_score() const { return score; }
+    const vector<MCTS_node *> &get_children() const { return *children; }
+};
+
+
+class MCTS_tree {
+    friend class MCTS_node;
+    MCTS_node *root;
+    RolloutBackend *backend;               // not owned; NULL = process default (created on first use)
+    MCTS_batching batching;
+    uint64_t flushes, rollouts_played;
+    RolloutBackend *get_backend();
+    void flush_leaves(vector<MCTS_node *> &leaves);
+public:
+    MCTS_tree(MCTS_state *starting_state);
+    MCTS_tree(MCTS_state *starting_state, RolloutBackend *backend, MCTS_batching batching);
+    ~MCTS_tree();
+    MCTS_node *select(double c=1.41);
+    MCTS_node *select_best_child();
+    void grow_tree(int max_iter, double max_time_in_seconds);
+    void advance_tree(const MCTS_move *move);
+    unsigned int get_size() const;
+    const MCTS_state *get_current_state() const;
+    void print_stats() const;
+    // extensions
+    void set_batching(MCTS_batching b) { batching = b; }
+    MCTS_batching get_batching() const { return batching; }
+    const MCTS_node *get_root() const { return root; }
+    uint64_t get_flushes() const { return flushes; }
+    uint64_t get_rollouts_played() const { return rollouts_played; }
+    // Root-parallel merge: add other trees' root-child statistics, keyed by the
+    // position of the child's move in the root's actions_to_try() order.
+    void export_root_stats(vector<double> &visits_and_scores) const;     // 2 doubles per root action
+    void import_root_stats(const vector<double> &visits_and_scores);     // REPLACES the children's statistics
+};
+
+
+class MCTS_agent {
+    MCTS_tree *tree;
+    int max_iter, max_seconds;
+public:
+    MCTS_agent(MCTS_state *starting_state, int max_iter = 100000, int max_seconds = 30);
+    MCTS_agent(MCTS_state *starting_state, int max_iter, int max_seconds, RolloutBackend *backend, MCTS_batching batching);
+    ~MCTS_agent();
+    const MCTS_move *genmove(const MCTS_move *enemy_move);
+    const MCTS_state *get_current_state() const;
+    void feedback() const { tree->print_stats(); }
+    MCTS_tree *get_tree() { return tree; }
+};
+
+// quiet mode: the reference prints progress lines from grow_tree/genmove (mcts.cpp:185-209,289-297)
+void mcts_set_verbose(bool on);
+
+#endif

@@ -185,7 +185,7 @@ def test_results_do_not_depend_on_batch_shape(be, corpus):
 
 def test_terminal_and_single_inputs(be):
     s = m.quoridor_opening().copy()
-    s["wx"] = 8                                # White already on its goal row: no draws, score 1
+    s["wx"], s["by"] = 8, 3                    # White already on its goal row: no draws, score 1
     out, fin = be.rollout_outcomes(G, m.POLICY_REF, s, 3, 0)
     assert (out["score"] == 1.0).all() and (out["draws"] == 0).all() and (out["plies"] == 0).all() and (out["kind"] == 0).all()
     s["wx"], s["bx"] = 3, 0                    # Black on row 0
