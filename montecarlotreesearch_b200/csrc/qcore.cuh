@@ -46,6 +46,7 @@ MC_HD int popc32(uint32_t v) {
     return __builtin_popcount(v);
 #endif
 }
+MC_HD int popc64(uint64_t v) { return popc32((uint32_t)v) + popc32((uint32_t)(v >> 32)); }
 MC_HD int ctz32(uint32_t v) {   // v != 0
 #if defined(__CUDA_ARCH__)
     return __ffs((int)v) - 1;
@@ -343,17 +344,138 @@ MC_HD bool q_force_playwall(QState &s, QWork *wk) {
 #define MCTSB_THR_0_75 3221225472u
 #define MCTSB_THR_0_80 3435973837u
 
-// "Does this wall hurt the enemy more than the mover", shared by the best-wall and the guided
-// branch (Quoridor.cpp:728-733, 756-761).  Returns enemy_enc - our_enc (> 0) or 0 if rejected.
-MC_HD int q_wall_gain(QState &s, int k, QWork *wk) {
+// ------------------------------------------------------------------------------------------------
+// Exact pruning of shortest-path queries.
+//
+// The reference answers "how long is q's shortest path if wall m is added" with a fresh BFS for
+// every candidate m (get_shortest_path(q, m), Quoridor.cpp:138-156; ~1 270 BFS per playout).  A
+// wall only changes the distance if it removes an edge that lies on SOME shortest path of q, so one
+// pass per player replaces most of those BFS by a bit test:
+//   1. goal-rooted layers  L_0 = goal row, L_j = cells at distance j from the goal row, until the
+//      pawn is reached (d = sp(q));
+//   2. trace from the pawn down the layers: A_d = {pawn}, A_k = neighbours(A_{k+1}) in L_k; the edges
+//      used are exactly the edges on shortest paths (stored at the upper / left cell of the edge);
+//   3. fold the edge boards into anchor masks: cut_h / cut_v bit a <=> the horizontal / vertical wall
+//      anchored at a removes at least one such edge.
+// m not in cut  =>  sp(q, m) == sp(q) exactly; m in cut => run the flood fill as before.
+// ------------------------------------------------------------------------------------------------
+#define MCTSB_MAX_LAYERS 28          // deeper searches fall back to "every wall may cut" (still exact)
+
+// Scratch for the layers: plain array on the host, strided shared memory in the kernels.
+struct LocalLayers {
+    B81 l[MCTSB_MAX_LAYERS];
+    MC_HD void put(int j, B81 v) { l[j] = v; }
+    MC_HD B81 get(int j) const { return l[j]; }
+};
+
+// 9-bit row x of a cell board
+MC_HD uint32_t b81_row(B81 v, int x) {
+    int pos = 9 * x, w = pos >> 5, sh = pos & 31;
+    uint32_t lo = w == 0 ? v.a : w == 1 ? v.b : v.c, hi = w == 0 ? v.b : w == 1 ? v.c : 0u;
+    uint32_t r = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+    return r & 0x1ffu;
+}
+
+struct QCut { uint64_t h, v; int sp; };    // anchors whose wall cuts a shortest-path edge, and sp(q)
+
+template <class Layers>
+MC_HD QCut q_cut_masks(const QState &s, int player, Layers &ls, QWork *wk) {
+    QCut out;
+    const B81 goal = player ? b81(MCTSB_GOAL_B_A, 0u, 0u) : b81(0u, 0u, MCTSB_GOAL_W_C);
+    const B81 pawn = b81_bit(s.cell[player]);
+    const B81 oS = s.openS, oE = s.openE;
+    if (wk) wk->flood_queries++;
+    // 1. layers from the goal row
+    B81 reached = goal;
+    int d = 0;
+    bool found = b81_any(pawn & goal), dead = false;
+    while (!found && !dead) {
+        B81 grown = q_flood_step(reached, oS, oE);
+        B81 layer = andn(grown, reached);
+        if (wk) wk->flood_steps++;
+        d++;
+        if (!b81_any(layer) || d >= MCTSB_MAX_LAYERS) { dead = true; break; }
+        ls.put(d, layer);
+        reached = grown;
+        found = b81_any(layer & pawn);
+    }
+    if (dead) {                                   // walled off (never in a legal position) or too deep to store
+        out.h = out.v = ~0ull;
+        out.sp = d >= MCTSB_MAX_LAYERS ? q_flood_dist(oS, oE, s.cell[player], player, wk) : -1;
+        return out;
+    }
+    out.sp = d;
+    // 2. trace the shortest paths back to the goal row
+    B81 A = pawn, ES = b81(0, 0, 0), EE = b81(0, 0, 0);
+    for (int k = d - 1; k >= 0; k--) {
+        B81 L = k == 0 ? goal : ls.get(k);
+        B81 sS = A & oS & shr<9>(L);              // u in A steps south into L_k: edge stored at u
+        B81 tN = shr<9>(A) & oS & L;              // u in A steps north to v = u-9 in L_k: edge stored at v
+        B81 sE = A & oE & shr<1>(L);
+        B81 tW = shr<1>(A) & oE & L;
+        ES = ES | sS | tN; EE = EE | sE | tW;
+        A = shl<9>(sS) | tN | shl<1>(sE) | tW;
+        if (wk) wk->flood_steps++;
+    }
+    // 3. edges -> wall anchors.  Horizontal anchor (x,y) removes the south edges of cells (x,y),(x,y+1);
+    //    vertical anchor (x,y) removes the east edges of cells (x,y),(x+1,y).
+    uint64_t ch = 0, cv = 0;
+    uint32_t e_prev = b81_row(EE, 0);
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        uint32_t r = b81_row(ES, x);
+        ch |= (uint64_t)((r | (r >> 1)) & 0xffu) << (8 * x);
+        uint32_t e_next = b81_row(EE, x + 1);
+        cv |= (uint64_t)((e_prev | e_next) & 0xffu) << (8 * x);
+        e_prev = e_next;
+    }
+    out.h = ch; out.v = cv;
+    return out;
+}
+
+// position of candidate k = 2*anchor + orientation in the un-shuffled pool (Quoridor.cpp:709-718:
+// anchors row-major, horizontal before vertical) = number of cheap-legal candidates before it
+MC_HD int q_pool_rank(uint64_t cheap_h, uint64_t cheap_v, int k) {
+    int a = k >> 1;
+    uint64_t below = a ? (~0ull >> (64 - a)) : 0ull;
+    uint64_t below_h = (k & 1) ? (below | (1ull << a)) : below;
+    return popc64(cheap_h & below_h) + popc64(cheap_v & below);
+}
+
+// candidate with pool rank r (inverse of q_pool_rank)
+MC_HD int q_pool_select(uint64_t cheap_h, uint64_t cheap_v, int r) {
+    for (int a = 0; a < 64; a++) {
+        if ((cheap_h >> a) & 1ull) { if (r == 0) return 2 * a; r--; }
+        if ((cheap_v >> a) & 1ull) { if (r == 0) return 2 * a + 1; r--; }
+    }
+    return -1;
+}
+
+// Gain of wall k for the mover (enemy_enc - our_enc if > 0, else 0): the acceptance test shared by
+// the best-wall and guided branches (Quoridor.cpp:728-733, 756-761).  `k` must be in cut(enemy) —
+// every other wall has enemy_enc == 0 and is rejected without a query.  The mover's own path is
+// re-measured only if the wall may touch it (own_cut_known && !in_own_cut => our_enc == 0).
+MC_HD int q_wall_gain(const QState &s, int k, int sp_e, int sp_p, bool own_may_change, QWork *wk) {
     int p = s.turn, e = 1 - p;
     int ep = q_sp_with_wall(s, e, k, wk);
-    int ee = ep - q_sp(s, e, wk);
+    int ee = ep - sp_e;
     if (!(ep >= 0 && ee > 0)) return 0;
-    int op = q_sp_with_wall(s, p, k, wk);
-    int oe = op - q_sp(s, p, wk);
-    if (!(op >= 0 && ee > oe)) return 0;
-    return ee - oe;
+    int oe = 0;
+    if (own_may_change) {
+        int op = q_sp_with_wall(s, p, k, wk);
+        if (op < 0) return 0;
+        oe = op - sp_p;
+    }
+    return ee > oe ? ee - oe : 0;
+}
+
+MC_HD bool q_mask_has(uint64_t h, uint64_t v, int k) { return (((k & 1) ? v : h) >> (k >> 1)) & 1ull; }
+MC_HD void q_mask_clear(uint64_t &h, uint64_t &v, int k) { if (k & 1) v &= ~(1ull << (k >> 1)); else h &= ~(1ull << (k >> 1)); }
+MC_HD int q_mask_first(uint64_t h, uint64_t v) {       // lowest candidate in pool order, -1 if empty
+    int ah = h ? (((uint32_t)h) ? ctz32((uint32_t)h) : 32 + ctz32((uint32_t)(h >> 32))) : 64;
+    int av = v ? (((uint32_t)v) ? ctz32((uint32_t)v) : 32 + ctz32((uint32_t)(v >> 32))) : 64;
+    if (ah == 64 && av == 64) return -1;
+    return ah <= av ? 2 * ah : 2 * av + 1;
 }
 
 // Encoded move: 0..80 pawn target cell; 128 + k wall (k = 2*anchor + orientation); -1 none.
@@ -364,40 +486,86 @@ MC_HD int q_move_to_id(int mv) {
     return ((k & 1) ? 145 : 81) + (k >> 1);
 }
 
-// pick_semirandom_move, Quoridor.cpp:680-803, bug-faithful (SURVEY.md 8a): the wall branch is
-// entered iff Black still has walls, one draw is consumed iff force_playwall() is false.
+// Place of pool element `r` (rank in the un-shuffled pool, Quoridor.cpp:709-718) in OUR shuffle
+// (include/mctsb.h "Random draws"): element j0 = mulhi(draw(base), n) comes first, every other
+// element is ordered by (its own draw, r).  Returned as one ascending 64-bit sort key.
 template <class Draws>
-MC_HD int q_pick_semirandom(QState &s, Draws &d, uint8_t *pool, QWork *wk) {
-    int e = 1 - s.turn;
+MC_HD uint64_t q_shuffle_key(Draws &d, uint32_t base, int n, int j0, int r) {
+    if (n < 2 || r == j0) return 0ull;
+    uint32_t key = d.at(base + 1u + (uint32_t)(r < j0 ? r : r - 1));
+    return (((uint64_t)key + 1ull) << 7) | (uint64_t)r;
+}
+
+// pick_semirandom_move, Quoridor.cpp:680-803, bug-faithful (SURVEY.md 8a): the wall branch is
+// entered iff Black still has walls, one draw is consumed iff force_playwall() is false.  The
+// shuffled pool (Quoridor.cpp:707-720) is never built: only candidates that can pass the branch's
+// test are ranked, each from its own draw.
+template <class Draws, class Layers>
+MC_HD int q_pick_semirandom(QState &s, Draws &d, Layers &ls, QWork *wk) {
+    const int p = s.turn, e = 1 - p;
+    uint64_t cheap_h = 0, cheap_v = 0;
+    if (s.nwalls[1] != 0) q_cheap_wall_masks(s, cheap_h, cheap_v);
+    const int n = popc64(cheap_h) + popc64(cheap_v);
+    // enemy cut masks are needed by the best-wall and guided branches (77.5 % of the wall plies)
+    QCut cut_e; cut_e.h = cut_e.v = 0; cut_e.sp = 0;
+    if (n > 0) {
+        cut_e = q_cut_masks(s, e, ls, wk);
+        s.sp[e] = (int8_t)cut_e.sp;
+    }
+    const int sp_p = q_sp(s, p, wk), sp_e = q_sp(s, e, wk);
     if (!q_force_playwall(s, wk)) (void)d.next();
     if (s.nwalls[1] != 0) {
-        uint64_t lh, lv;
-        q_cheap_wall_masks(s, lh, lv);
-        int n = 0;
-        for (int a = 0; a < 64; a++) {                       // pool order: i, j, (h, v)  (:709-718)
-            if ((lh >> a) & 1ull) pool[n++] = (uint8_t)(2 * a);
-            if ((lv >> a) & 1ull) pool[n++] = (uint8_t)(2 * a + 1);
-        }
-        for (int i = 0; i + 1 < n; i++) {                    // our shuffle (:720)
-            int j = i + (int)mulhi_u32(d.next(), (uint32_t)(n - i));
-            uint8_t t = pool[i]; pool[i] = pool[j]; pool[j] = t;
-        }
-        if (d.next() < MCTSB_THR_0_10) {                     // best wall (:721-746)
-            int best = -1, maxdiff = 0;
-            for (int i = 0; i < n; i++) { int g = q_wall_gain(s, pool[i], wk); if (g > maxdiff) { maxdiff = g; best = pool[i]; } }
+        const uint32_t base = d.consumed();
+        int j0 = 0;
+        if (n >= 2) { j0 = (int)mulhi_u32(d.at(base), (uint32_t)n); d.skip((uint32_t)n); }
+        if (d.next() < MCTSB_THR_0_10) {                       // best wall (:721-746): max gain, first in shuffled order
+            uint64_t ch = cheap_h & cut_e.h, cv = cheap_v & cut_e.v;
+            int best = -1, best_gain = 0; uint64_t best_key = 0;
+            if (ch | cv) {
+                QCut cut_p = q_cut_masks(s, p, ls, wk);
+                for (int k = q_mask_first(ch, cv); k >= 0; q_mask_clear(ch, cv, k), k = q_mask_first(ch, cv)) {
+                    int g = q_wall_gain(s, k, sp_e, sp_p, q_mask_has(cut_p.h, cut_p.v, k), wk);
+                    if (g <= 0 || g < best_gain) continue;
+                    uint64_t key = q_shuffle_key(d, base, n, j0, q_pool_rank(cheap_h, cheap_v, k));
+                    if (g > best_gain || key < best_key) { best = k; best_gain = g; best_key = key; }
+                }
+            }
             if (best >= 0) return 128 + best;
-        } else if (d.next() < MCTSB_THR_0_75) {              // guided (:748-772)
-            for (int i = 0; i < n; i++) if (q_wall_gain(s, pool[i], wk) > 0) return 128 + pool[i];
-        } else {                                             // first fully legal (:773-788)
-            for (int i = 0; i < n; i++) if (q_wall_keeps_paths(s, pool[i], wk)) return 128 + pool[i];
+        } else if (d.next() < MCTSB_THR_0_75) {                // guided (:748-772): first in shuffled order with gain > 0
+            uint64_t ch = cheap_h & cut_e.h, cv = cheap_v & cut_e.v;
+            while (ch | cv) {
+                int best = -1; uint64_t best_key = 0;                      // next candidate in shuffled order
+                uint64_t th = ch, tv = cv;
+                for (int k = q_mask_first(th, tv); k >= 0; q_mask_clear(th, tv, k), k = q_mask_first(th, tv)) {
+                    uint64_t key = q_shuffle_key(d, base, n, j0, q_pool_rank(cheap_h, cheap_v, k));
+                    if (best < 0 || key < best_key) { best = k; best_key = key; }
+                }
+                if (q_wall_gain(s, best, sp_e, sp_p, true, wk) > 0) return 128 + best;
+                q_mask_clear(ch, cv, best);
+            }
+        } else if (n > 0) {                                    // first fully legal in shuffled order (:773-788)
+            int k = q_pool_select(cheap_h, cheap_v, j0);       // the head of the shuffle: one draw
+            if (q_wall_keeps_paths(s, k, wk)) return 128 + k;
+            uint64_t th = cheap_h, tv = cheap_v;
+            q_mask_clear(th, tv, k);
+            while (th | tv) {                                  // rare: walk on in key order
+                int best = -1; uint64_t best_key = 0;
+                uint64_t uh = th, uv = tv;
+                for (int c = q_mask_first(uh, uv); c >= 0; q_mask_clear(uh, uv, c), c = q_mask_first(uh, uv)) {
+                    uint64_t key = q_shuffle_key(d, base, n, j0, q_pool_rank(cheap_h, cheap_v, c));
+                    if (best < 0 || key < best_key) { best = c; best_key = key; }
+                }
+                if (q_wall_keeps_paths(s, best, wk)) return 128 + best;
+                q_mask_clear(th, tv, best);
+            }
         }
     }
     uint32_t steps = q_step_mask(s);
     if (s.nwalls[e] == 0 || d.next() < MCTSB_THR_0_80) return q_best_step(s, steps, wk);   // :792-793
     uint32_t r = d.next() & 0x7fffffffu;                     // rand() (:796)
-    int n = popc32(steps);
-    if (n == 0) return -1;                                   // the reference divides by zero here
-    int idx = (int)(r % (uint32_t)n);
+    int ns = popc32(steps);
+    if (ns == 0) return -1;                                  // the reference divides by zero here
+    int idx = (int)(r % (uint32_t)ns);
     for (int i = 0; i < 12; i++) if ((steps >> i) & 1u) { if (idx == 0) return s.cell[s.turn] + q_step_delta(i); idx--; }
     return -1;
 }
@@ -410,13 +578,13 @@ MC_HD void q_play_encoded(QState &s, int mv) {
 // test at the top of each ply only, heuristic evaluation afterwards.  The evaluation inside the
 // loop (:826-829) can never stop the playout and has no side effect besides filling the path
 // cache, so it is not computed here.
-template <class Draws>
-MC_HD double q_rollout_ref(QState &s, Draws &d, uint8_t *pool, int &plies, int &kind, QWork *wk) {
+template <class Draws, class Layers>
+MC_HD double q_rollout_ref(QState &s, Draws &d, Layers &ls, int &plies, int &kind, QWork *wk) {
     plies = 0; kind = 2;
     for (int i = 0; i < 50; i++) {
         int w = q_winner(s);
         if (w) { kind = w == 1 ? 0 : 1; return w == 1 ? 1.0 : 0.0; }
-        int mv = q_pick_semirandom(s, d, pool, wk);
+        int mv = q_pick_semirandom(s, d, ls, wk);
         if (mv < 0) { kind = 3; break; }
         q_play_encoded(s, mv);
         plies++;
@@ -466,8 +634,6 @@ MC_HD int q_nth_move(const QState &s, uint32_t steps, uint64_t legal_h, uint64_t
     }
     return -1;
 }
-
-MC_HD int popc64(uint64_t v) { return popc32((uint32_t)v) + popc32((uint32_t)(v >> 32)); }
 
 // UNI policy (no reference function; oracle = loop over the reference's public API): uniformly
 // random legal move per ply, idx = mulhi(draw, |L|), ply cap MCTSB_UNI_MAX_PLIES scoring 0.5.

@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kThreads) quoridor_rollout_kernel(RolloutParam
     const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool active = r < p.n_rollouts;
     const uint32_t leaf = active ? (REPLAY ? (uint32_t)r : (uint32_t)(r / p.rollouts_per_leaf)) : 0u;
-    uint8_t pool[128];
+    LocalLayers pool;
     double score = 0.0; int plies = 0, kind = 0; uint32_t draws = 0;
     QWork wk = {0u, 0u, 0u};
     QState s;

@@ -10,8 +10,13 @@
  *                                                     key = {lo32(s), hi32(s)})[k & 3]
  *   U()      = u32 * 2^-32                       (replaces dist(gen), Quoridor.cpp:696,721,748,792)
  *   rand()   = u32 & 0x7fffffff                  (replaces rand(),    Quoridor.cpp:796, TicTacToe.cpp:93)
- *   shuffle  = forward Fisher-Yates: for i in 0..n-2: j = i + mulhi32(u32, n-i); swap(a[i],a[j])
- *              (n-1 draws, none when n <= 1)     (replaces std::shuffle, Quoridor.cpp:720)
+ *   shuffle  (replaces std::shuffle, Quoridor.cpp:720), for n >= 2 elements, n draws, none if n <= 1:
+ *              j0 = mulhi32(u32, n)                 -> input element j0 goes first;
+ *              every other input element i (ascending i) then gets key_i = next u32 and the rest
+ *              of the output is those elements ordered by (key_i, i) ascending.
+ *              A uniform shuffle whose first element costs one draw and in which the relative order
+ *              of any subset depends only on that subset's own draws, so a GPU can rank a handful
+ *              of candidates without materialising the permutation.
  */
 #ifndef ORACLE_PHILOX_REF_H
 #define ORACLE_PHILOX_REF_H

@@ -309,9 +309,17 @@ static int qs_pick(qs_t *q, oq_draws *d) {
             if (qs_cheap_wall(q, i, j, 1)) pool[n++] = MCTSB_Q_MOVE_HWALL(i, j);
             if (qs_cheap_wall(q, i, j, 0)) pool[n++] = MCTSB_Q_MOVE_VWALL(i, j);
         }
-        for (int i = 0; i + 1 < n; i++) {                                  /* :720, our shuffle */
-            int j = i + (int)mulhi32(draw_u32(d), (uint32_t)(n - i));
-            int t = pool[i]; pool[i] = pool[j]; pool[j] = t;
+        if (n >= 2) {                                                      /* :720, our shuffle (philox_ref.h) */
+            uint32_t key[128]; int rest[128], m = 0;
+            int j0 = (int)mulhi32(draw_u32(d), (uint32_t)n), head = pool[j0];
+            for (int i = 0; i < n; i++) if (i != j0) { key[m] = draw_u32(d); rest[m] = pool[i]; m++; }
+            for (int i = 1; i < m; i++) {                                  /* stable insertion sort on the key */
+                uint32_t k = key[i]; int v = rest[i], j = i - 1;
+                while (j >= 0 && key[j] > k) { key[j + 1] = key[j]; rest[j + 1] = rest[j]; j--; }
+                key[j + 1] = k; rest[j + 1] = v;
+            }
+            pool[0] = head;
+            for (int i = 0; i < m; i++) pool[i + 1] = rest[i];
         }
         if (draw_unit(d) < 0.1) {                                          /* :721-746 best wall */
             int best = -1, maxdiff = 0;

@@ -35,6 +35,7 @@
 #include <chrono>
 #include <atomic>
 #include <utility>
+#include <iterator>
 #include <pthread.h>
 #include <stdlib.h>
 
@@ -70,11 +71,15 @@ template <typename T> struct stream_real_dist {
     T operator()(stream_engine &) { return (T)refshim::next_u32() * (T)(1.0 / 4294967296.0); }
 };
 template <typename It, typename G> void stream_shuffle(It first, It last, G &) {
-    uint32_t n = (uint32_t)(last - first);
-    for (uint32_t i = 0; i + 1 < n; i++) {
-        uint32_t j = i + mulhi32(refshim::next_u32(), n - i);
-        std::swap(first[i], first[j]);
-    }
+    size_t n = (size_t)(last - first);
+    if (n < 2) return;
+    size_t j0 = mulhi32(refshim::next_u32(), (uint32_t)n);
+    std::vector<std::pair<uint32_t, uint32_t> > keys;            /* (key, input index) of the others */
+    for (size_t i = 0; i < n; i++) if (i != j0) keys.push_back(std::make_pair(refshim::next_u32(), (uint32_t)i));
+    std::sort(keys.begin(), keys.end());
+    std::vector<typename std::iterator_traits<It>::value_type> tmp(first, last);
+    first[0] = tmp[j0];
+    for (size_t i = 0; i + 1 < n; i++) first[i + 1] = tmp[keys[i].second];
 }
 }  // namespace std
 inline int stream_rand() { return (int)(refshim::next_u32() & 0x7fffffffu); }

@@ -37,7 +37,7 @@ int emu_q_play(const mctsb_qstate *p, int id, mctsb_qstate *out) {
 
 int emu_q_rollout_streams(const mctsb_qstate *states, int policy, int n, const uint32_t *streams, uint32_t len,
                           uint32_t stride, mctsb_outcome *out, mctsb_qstate *finals, uint64_t *work3) {
-    uint8_t pool[128];
+    LocalLayers pool;
     for (int i = 0; i < n; i++) {
         QState s; q_unpack(s, states[i]);
         StreamDraws d; d.init(streams + (size_t)i * stride, len);
@@ -53,7 +53,7 @@ int emu_q_rollout_streams(const mctsb_qstate *states, int policy, int n, const u
 
 int emu_q_rollout_philox(const mctsb_qstate *state, int policy, uint64_t seed, uint64_t first_id, int n,
                          mctsb_outcome *out, mctsb_qstate *finals, uint64_t *work3) {
-    uint8_t pool[128];
+    LocalLayers pool;
     for (int i = 0; i < n; i++) {
         QState s; q_unpack(s, *state);
         PhiloxDraws d; d.init(seed, first_id + i);
