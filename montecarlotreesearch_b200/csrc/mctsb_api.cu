@@ -32,6 +32,7 @@ struct mctsb_backend {
     // resident state
     int res_game; uint32_t res_leaves;
     uint64_t launches;
+    bool use_simple_kernel;                          // MCTSB_SIMPLE_KERNEL=1: REF policy on the v1 kernel (A/B cross-check)
     char cuda_err[256];
 };
 
@@ -94,8 +95,11 @@ bool valid_qstates(const mctsb_qstate *s, int n) {
 }
 
 int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const RolloutParams &p) {
-    cudaError_t e = game == MCTSB_GAME_QUORIDOR ? launch_quoridor_rollouts(p, policy, replay, b->stream)
-                                                : launch_ttt_rollouts(p, replay, b->stream);
+    cudaError_t e;
+    if (game == MCTSB_GAME_QUORIDOR && policy == MCTSB_POLICY_REF && !b->use_simple_kernel)
+        e = launch_quoridor_lockstep(p, replay, b->d_counters + 7, b->stream);
+    else if (game == MCTSB_GAME_QUORIDOR) e = launch_quoridor_rollouts(p, policy, replay, b->stream);
+    else e = launch_ttt_rollouts(p, replay, b->stream);
     if (e != cudaSuccess) return fail_cuda(b, e, "rollout kernel launch");
     b->launches++;
     return MCTSB_OK;
@@ -151,12 +155,13 @@ int mctsb_create(mctsb_backend **out, int device, uint64_t seed) {
     if (!b) return MCTSB_ERR_OOM;
     memset(b, 0, sizeof *b);
     b->device = device; b->seed = seed; b->res_game = -1;
+    { const char *ev = getenv("MCTSB_SIMPLE_KERNEL"); b->use_simple_kernel = ev && ev[0] == '1'; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&b->ev1);
-    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_counters, 4 * sizeof(unsigned long long));
-    if (e == cudaSuccess) e = cudaMemset(b->d_counters, 0, 4 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_counters, 8 * sizeof(unsigned long long));
+    if (e == cudaSuccess) e = cudaMemset(b->d_counters, 0, 8 * sizeof(unsigned long long));
     if (e == cudaSuccess) e = cudaMalloc((void **)&b->d_sink, 16 * sizeof(uint32_t));
     if (e == cudaSuccess) e = cudaMemset(b->d_sink, 0, 16 * sizeof(uint32_t));
     if (e != cudaSuccess) { mctsb_destroy(b); cudaGetLastError(); return e == cudaErrorMemoryAllocation ? MCTSB_ERR_OOM : MCTSB_ERR_CUDA; }

@@ -356,7 +356,7 @@ MC_HD bool q_force_playwall(QState &s, QWork *wk) {
 //   2. trace from the pawn down the layers: A_d = {pawn}, A_k = neighbours(A_{k+1}) in L_k; the edges
 //      used are exactly the edges on shortest paths (stored at the upper / left cell of the edge);
 //   3. fold the edge boards into anchor masks: cut_h / cut_v bit a <=> the horizontal / vertical wall
-//      anchored at a removes at least one such edge.
+//      anchored at a may change the distance (see q_trace_to_anchors for the exact rule).
 // m not in cut  =>  sp(q, m) == sp(q) exactly; m in cut => run the flood fill as before.
 // ------------------------------------------------------------------------------------------------
 #define MCTSB_MAX_LAYERS 28          // deeper searches fall back to "every wall may cut" (still exact)
@@ -376,7 +376,48 @@ MC_HD uint32_t b81_row(B81 v, int x) {
     return r & 0x1ffu;
 }
 
-struct QCut { uint64_t h, v; int sp; };    // anchors whose wall cuts a shortest-path edge, and sp(q)
+// Trace state.  Every step walks the shortest-path cells one layer down and files the edges it uses:
+// a layer transition crossed by exactly ONE edge is a bottleneck (every shortest path uses it: removing
+// it lengthens the path for sure); edges of transitions with several edges are "multi" edges.
+struct QTrace { B81 A, S1, E1, Sm, Em; };   // frontier; south / east edges: single (bottleneck) and multi
+
+MC_HD void q_trace_init(QTrace &t, B81 pawn) {
+    t.A = pawn; t.S1 = t.E1 = t.Sm = t.Em = b81(0u, 0u, 0u);
+}
+
+MC_HD void q_trace_step(QTrace &t, B81 L, B81 oS, B81 oE) {
+    B81 sS = t.A & oS & shr<9>(L);            // u in A steps south into L: edge stored at u
+    B81 tN = shr<9>(t.A) & oS & L;            // u in A steps north to v = u-9 in L: edge stored at v
+    B81 sE = t.A & oE & shr<1>(L);
+    B81 tW = shr<1>(t.A) & oE & L;
+    B81 es = sS | tN, ee = sE | tW;
+    int cnt = popc32(es.a) + popc32(es.b) + popc32(es.c) + popc32(ee.a) + popc32(ee.b) + popc32(ee.c);
+    if (cnt == 1) { t.S1 = t.S1 | es; t.E1 = t.E1 | ee; }
+    else          { t.Sm = t.Sm | es; t.Em = t.Em | ee; }
+    t.A = shl<9>(sS) | tN | shl<1>(sE) | tW;
+}
+
+// Anchors whose wall MAY change the distance.  Horizontal anchor (x,y) removes the south edges of cells
+// (x,y),(x,y+1); vertical anchor (x,y) the east edges of cells (x,y),(x+1,y).  A wall changes nothing if
+// it removes no shortest-path edge, and also nothing if it removes exactly one "multi" edge and no
+// bottleneck: the other edges of that transition keep a shortest path alive.  Everything else —
+// a bottleneck edge, or two multi edges — must be measured with a flood fill.
+MC_HD void q_trace_to_anchors(const QTrace &t, uint64_t &may_h, uint64_t &may_v) {
+    uint64_t ch = 0, cv = 0;
+    uint32_t e1_prev = b81_row(t.E1, 0), em_prev = b81_row(t.Em, 0);
+#pragma unroll
+    for (int x = 0; x < 8; x++) {
+        uint32_t r1 = b81_row(t.S1, x), rm = b81_row(t.Sm, x);
+        ch |= (uint64_t)((r1 | (r1 >> 1) | (rm & (rm >> 1))) & 0xffu) << (8 * x);
+        uint32_t e1_next = b81_row(t.E1, x + 1), em_next = b81_row(t.Em, x + 1);
+        cv |= (uint64_t)((e1_prev | e1_next | (em_prev & em_next)) & 0xffu) << (8 * x);
+        e1_prev = e1_next; em_prev = em_next;
+    }
+    may_h = ch; may_v = cv;
+}
+
+struct QCut { uint64_t h, v; int sp; };    // anchors whose wall may change sp(q) (must be measured), and sp(q)
+    // anchors whose wall cuts a shortest-path edge, and sp(q)
 
 template <class Layers>
 MC_HD QCut q_cut_masks(const QState &s, int player, Layers &ls, QWork *wk) {
@@ -406,30 +447,13 @@ MC_HD QCut q_cut_masks(const QState &s, int player, Layers &ls, QWork *wk) {
     }
     out.sp = d;
     // 2. trace the shortest paths back to the goal row
-    B81 A = pawn, ES = b81(0, 0, 0), EE = b81(0, 0, 0);
+    QTrace t; q_trace_init(t, pawn);
     for (int k = d - 1; k >= 0; k--) {
-        B81 L = k == 0 ? goal : ls.get(k);
-        B81 sS = A & oS & shr<9>(L);              // u in A steps south into L_k: edge stored at u
-        B81 tN = shr<9>(A) & oS & L;              // u in A steps north to v = u-9 in L_k: edge stored at v
-        B81 sE = A & oE & shr<1>(L);
-        B81 tW = shr<1>(A) & oE & L;
-        ES = ES | sS | tN; EE = EE | sE | tW;
-        A = shl<9>(sS) | tN | shl<1>(sE) | tW;
+        q_trace_step(t, k == 0 ? goal : ls.get(k), oS, oE);
         if (wk) wk->flood_steps++;
     }
-    // 3. edges -> wall anchors.  Horizontal anchor (x,y) removes the south edges of cells (x,y),(x,y+1);
-    //    vertical anchor (x,y) removes the east edges of cells (x,y),(x+1,y).
-    uint64_t ch = 0, cv = 0;
-    uint32_t e_prev = b81_row(EE, 0);
-#pragma unroll
-    for (int x = 0; x < 8; x++) {
-        uint32_t r = b81_row(ES, x);
-        ch |= (uint64_t)((r | (r >> 1)) & 0xffu) << (8 * x);
-        uint32_t e_next = b81_row(EE, x + 1);
-        cv |= (uint64_t)((e_prev | e_next) & 0xffu) << (8 * x);
-        e_prev = e_next;
-    }
-    out.h = ch; out.v = cv;
+    // 3. edges -> wall anchors
+    q_trace_to_anchors(t, out.h, out.v);
     return out;
 }
 

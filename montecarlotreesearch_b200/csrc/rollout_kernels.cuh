@@ -23,7 +23,11 @@ struct RolloutParams {
     unsigned long long *counters;  // [4]: rollouts, plies, flood_steps, flood_queries
 };
 
-// one thread = one rollout
+// REF policy, production kernel (quoridor_lockstep.cu): one thread = one rollout, the 32 rollouts of a
+// warp advance ply-synchronously; `work_counter` is a device u64 the launch resets
+cudaError_t launch_quoridor_lockstep(const RolloutParams &p, bool replay, unsigned long long *work_counter, cudaStream_t st);
+
+// one thread = one rollout, natural control flow (UNI policy; REF kept as a cross-check)
 cudaError_t launch_quoridor_rollouts(const RolloutParams &p, int policy, bool replay, cudaStream_t st);
 cudaError_t launch_ttt_rollouts(const RolloutParams &p, bool replay, cudaStream_t st);
 

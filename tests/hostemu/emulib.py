@@ -22,6 +22,7 @@ class EmuLib:
         L.emu_t_rollout_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, vp]
         L.emu_t_rollout_streams.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]
         L.emu_t_winner.argtypes = [C.c_uint32, C.c_uint32]
+        L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
 
     def q_primitives(self, s):
         a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
@@ -90,3 +91,22 @@ class EmuLib:
         out = np.zeros(a.size, dtype=OUTCOME_DTYPE)
         self.lib.emu_t_rollout_streams(a.ctypes.data, a.size, st.ctypes.data, st.shape[1], st.shape[1], out.ctypes.data)
         return out
+
+    def lockstep(self, states, R, seed, first_id, streams=None):
+        """The production kernel body with a one-lane warp: Philox mode (streams=None) or replay."""
+        from oracle.reflib import LEAFSUM_DTYPE
+        a = np.ascontiguousarray(states, dtype=QSTATE_DTYPE).reshape(-1)
+        if streams is not None:
+            st = np.ascontiguousarray(streams, dtype=np.uint32)
+            assert R == 1 and st.shape[0] == a.size
+            sp, sl, ss = st.ctypes.data, st.shape[1], st.shape[1]
+        else:
+            sp, sl, ss = None, 0, 0
+        n = a.size * R
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        fin = np.zeros(n, dtype=QSTATE_DTYPE)
+        sums = np.zeros(a.size, dtype=LEAFSUM_DTYPE)
+        ctr = np.zeros(4, dtype=np.uint64)
+        self.lib.emu_lockstep(a.ctypes.data, a.size, R, seed, first_id, sp, sl, ss, out.ctypes.data, fin.ctypes.data,
+                              sums.ctypes.data, ctr.ctypes.data)
+        return out, fin, sums, ctr

@@ -4,6 +4,8 @@
 // into the product library and is not reachable through the C ABI.
 #include "../../montecarlotreesearch_b200/csrc/qcore.cuh"
 #include "../../montecarlotreesearch_b200/csrc/ttt_core.cuh"
+#include "../../montecarlotreesearch_b200/csrc/quoridor_lockstep_body.cuh"
+#include <vector>
 #include <string.h>
 using namespace mctsb;
 
@@ -90,5 +92,31 @@ int emu_t_rollout_streams(const mctsb_tstate *st, int n, const uint32_t *streams
 }
 
 int emu_t_winner(uint32_t x, uint32_t o) { return t_winner(x & 0x1ff, o & 0x1ff); }
+
+
+// The production lockstep kernel body run with a one-lane warp (see quoridor_lockstep_body.cuh).
+int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t seed, uint64_t first_id,
+                 const uint32_t *streams, uint32_t stream_len, uint32_t stream_stride,
+                 mctsb_outcome *out, mctsb_qstate *finals, mctsb_leaf_sum *sums, uint64_t *counters4) {
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = states; p.n_leaves = (uint32_t)n_leaves; p.rollouts_per_leaf = R; p.n_rollouts = (uint64_t)n_leaves * R;
+    p.seed = seed; p.first_rollout_id = first_id; p.streams = streams; p.stream_len = stream_len; p.stream_stride = stream_stride;
+    p.sums = sums; p.outcomes = out; p.finals = finals;
+    unsigned long long ctr[4] = {0, 0, 0, 0};
+    p.counters = ctr;
+    if (sums) memset(sums, 0, sizeof(mctsb_leaf_sum) * (size_t)n_leaves);
+    std::vector<uint32_t> smem((size_t)MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS + (LS_THREADS / 32) * LS_QCAP / 2 + 64);
+    unsigned long long work = 0;
+    if (streams) lockstep_body<true>(p, &work, smem.data());
+    else lockstep_body<false>(p, &work, smem.data());
+    if (counters4) for (int i = 0; i < 4; i++) counters4[i] = ctr[i];
+    return 0;
+}
+
+
+void emu_dbg_hist(unsigned long long *iters, unsigned long long *pend, int reset) {
+    memcpy(iters, g_dbg_iters, sizeof g_dbg_iters); memcpy(pend, g_dbg_pend, sizeof g_dbg_pend);
+    if (reset) { memset(g_dbg_iters, 0, sizeof g_dbg_iters); memset(g_dbg_pend, 0, sizeof g_dbg_pend); }
+}
 
 }

@@ -85,3 +85,29 @@ def test_core_tictactoe_vs_golden(emu):
         x, o = int(g["states"][j][0]), int(g["states"][j][1])
         out = emu.t_rollout_philox(x, o, int(g["seed"]), 7000 + j, 1)
         assert out["score"][0] == g["score"][j] and out["draws"][0] == g["draws"][j]
+
+
+# ---- the production lockstep kernel body, emulated with a one-lane warp --------------------------------
+def test_lockstep_body_vs_reference_golden(emu, corpus):
+    g = golden("golden_q_opening.npz")
+    out, _, sums, _ = emu.lockstep(opening_state(), 512, int(g["seed"]), 0)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    assert int(sums["n"][0]) == 512
+    g = golden("golden_q_replay.npz")
+    streams = np.stack([philox_stream(int(g["seed"]), int(i), 16384) for i in g["id"]])
+    out, fin, _, _ = emu.lockstep(corpus[g["index"]], 1, 0, 0, streams=streams)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    assert fin.tobytes() == g["final"].tobytes()
+
+
+def test_lockstep_body_vs_oracle_many_leaves(emu, port, corpus):
+    rng = np.random.default_rng(17)
+    idx = rng.choice(len(corpus), 120, replace=False)
+    out, fin, sums, _ = emu.lockstep(corpus[idx], 5, 4242, 900)
+    for j, i in enumerate(idx):
+        exp, efin, _ = port.q_rollout_philox(corpus[i], 4242, 900 + 5 * j, 5, finals=True)
+        assert exp.tobytes() == out[5 * j: 5 * j + 5].tobytes() and efin.tobytes() == fin[5 * j: 5 * j + 5].tobytes()
+        acc, _ = port.leaf_sum(exp["score"])
+        assert (int(acc["lo"]), int(acc["hi"]), int(acc["n"])) == (int(sums["lo"][j]), int(sums["hi"][j]), int(sums["n"][j]))
