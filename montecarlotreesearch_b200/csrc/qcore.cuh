@@ -111,6 +111,9 @@ MC_HD void q_add_wall_edges(QState &s, int anchor, bool horizontal) {
 MC_HD bool q_unpack(QState &s, const mctsb_qstate &p) {
     s.hanc = p.h_anchor; s.vanc = p.v_anchor;
     s.openS = MCTSB_ROWS07; s.openE = MCTSB_COLS07;
+#if defined(__CUDA_ARCH__)
+#pragma unroll 1
+#endif
     for (int x = 0; x < 8; x++) {
         uint32_t hrow = (uint32_t)(p.h_anchor >> (8 * x)) & 0xffu;
         uint32_t vrow = (uint32_t)(p.v_anchor >> (8 * x)) & 0xffu;
@@ -145,6 +148,38 @@ MC_HD int q_winner(const QState &s) {
 // Flood fill.  One call = one frontier expansion of all 81 cells in the four directions; replaces
 // one BFS level of calculate_dists_from (Quoridor.cpp:80-104).
 // ------------------------------------------------------------------------------------------------
+#if defined(__CUDACC__)
+// 2^9, 2^1, 2^23, 2^31: kept in the constant bank so that ptxas cannot turn the multiplies below back into shifts
+static __constant__ uint32_t mc_shift_mul[4] = {1u << 9, 1u << 1, 1u << 23, 1u << 31};
+#endif
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ void mc_mulwide(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
+    asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
+}
+// Device form of the step.  The straightforward version is 12 funnel shifts + 18 LOP3, all on the ALU
+// pipe, which issues at half the scheduler's rate.  Here every 81-bit shift is a 32x32->64 multiply by a
+// power of two (IMAD.WIDE on the FMA pipe: x * 2^N = {x << N, x >> (32-N)}), and the carries between
+// words are folded into the final 3-input ORs: 12 IMAD + 19 LOP3, the two pipes share the work.
+__device__ __forceinline__ B81 q_flood_step(B81 r, B81 oS, B81 oE) {
+    const uint32_t L9 = mc_shift_mul[0], L1 = mc_shift_mul[1], R9 = mc_shift_mul[2], R1 = mc_shift_mul[3];
+    uint32_t sa = r.a & oS.a, sb = r.b & oS.b, sc = r.c & oS.c;        // cells that may step south
+    uint32_t ea = r.a & oE.a, eb = r.b & oE.b, ec = r.c & oE.c;        // cells that may step east
+    uint32_t Sa_lo, Sa_hi, Sb_lo, Sb_hi, Ea_lo, Ea_hi, Eb_lo, Eb_hi;
+    mc_mulwide(sa, L9, Sa_lo, Sa_hi); mc_mulwide(sb, L9, Sb_lo, Sb_hi);
+    mc_mulwide(ea, L1, Ea_lo, Ea_hi); mc_mulwide(eb, L1, Eb_lo, Eb_hi);
+    uint32_t Sc = sc * L9, Ec = ec * L1;
+    uint32_t Na_lo, Na_hi, Nb_lo, Nb_hi, Nc_lo, Nc_hi, Wa_lo, Wa_hi, Wb_lo, Wb_hi, Wc_lo, Wc_hi;
+    mc_mulwide(r.a, R9, Na_lo, Na_hi); mc_mulwide(r.b, R9, Nb_lo, Nb_hi); mc_mulwide(r.c, R9, Nc_lo, Nc_hi);   // hi = x >> 9, lo = x << 23
+    mc_mulwide(r.a, R1, Wa_lo, Wa_hi); mc_mulwide(r.b, R1, Wb_lo, Wb_hi); mc_mulwide(r.c, R1, Wc_lo, Wc_hi);   // hi = x >> 1, lo = x << 31
+    (void)Na_lo; (void)Wa_lo;
+    B81 n;
+    n.a = r.a | Sa_lo | Ea_lo | ((Na_hi | Nb_lo) & oS.a) | ((Wa_hi | Wb_lo) & oE.a);
+    n.b = r.b | Sb_lo | Sa_hi | Eb_lo | Ea_hi | ((Nb_hi | Nc_lo) & oS.b) | ((Wb_hi | Wc_lo) & oE.b);
+    n.c = r.c | Sc | Sb_hi | Ec | Eb_hi | (Nc_hi & oS.c) | (Wc_hi & oE.c);
+    return n;
+}
+#else
 MC_HD B81 q_flood_step(B81 r, B81 oS, B81 oE) {
     B81 south = shl<9>(r & oS);           // x -> x+1
     B81 north = shr<9>(r) & oS;           // x -> x-1 : the cell above must have an open south edge
@@ -154,6 +189,7 @@ MC_HD B81 q_flood_step(B81 r, B81 oS, B81 oE) {
                r.b | south.b | north.b | east.b | west.b,
                r.c | south.c | north.c | east.c | west.c);
 }
+#endif
 
 // Shortest path length from `start` to `player`'s goal row ignoring pawns, -1 if walled off:
 // get_shortest_path / calculate_dists_from(stop_at_goal=true), Quoridor.cpp:46-106,161-169.
@@ -206,9 +242,11 @@ MC_HD void q_cheap_wall_masks(const QState &s, uint64_t &legal_h, uint64_t &lega
 // cell of candidate i = mover cell + q_step_delta(i).  Returns the 12-bit mask of legal ones
 // (legal_step, Quoridor.cpp:200-287) for the side to move.
 MC_HD int q_step_delta(int i) {
-    // 9*dx+dy for the 12 candidates
-    const int d[12] = {-9, -18, 9, 18, -1, -2, 1, 2, -10, -8, 8, 10};
-    return d[i];
+    // 9*dx+dy for the 12 candidates: {-9,-18,9,18,-1,-2,1,2,-10,-8,8,10}, biased by 18 and packed 6 bits each
+    const uint64_t packed = (9ull) | (0ull << 6) | (27ull << 12) | (36ull << 18) | (17ull << 24) | (16ull << 30) |
+                            (19ull << 36) | (20ull << 42) | (8ull << 48) | (10ull << 54);
+    if (i >= 10) return i == 10 ? 8 : 10;
+    return (int)((packed >> (6 * i)) & 63ull) - 18;
 }
 
 // 4-bit mask N,S,W,E of the directions a pawn on cell c can move in (board edge or wall blocks)
@@ -466,12 +504,20 @@ MC_HD int q_pool_rank(uint64_t cheap_h, uint64_t cheap_v, int k) {
     return popc64(cheap_h & below_h) + popc64(cheap_v & below);
 }
 
-// candidate with pool rank r (inverse of q_pool_rank)
+// candidate with pool rank r (inverse of q_pool_rank): binary search on the anchor index
 MC_HD int q_pool_select(uint64_t cheap_h, uint64_t cheap_v, int r) {
-    for (int a = 0; a < 64; a++) {
-        if ((cheap_h >> a) & 1ull) { if (r == 0) return 2 * a; r--; }
-        if ((cheap_v >> a) & 1ull) { if (r == 0) return 2 * a + 1; r--; }
+    int a = 0;                                             // largest anchor with (#candidates before it) <= r
+#pragma unroll
+    for (int step = 32; step > 0; step >>= 1) {
+        int t = a + step;                                  // 1..63
+        uint64_t below = ~0ull >> (64 - t);
+        if (popc64(cheap_h & below) + popc64(cheap_v & below) <= r) a = t;
     }
+    uint64_t below = a ? (~0ull >> (64 - a)) : 0ull;
+    int rem = r - (popc64(cheap_h & below) + popc64(cheap_v & below));
+    bool has_h = (cheap_h >> a) & 1ull, has_v = (cheap_v >> a) & 1ull;
+    if (rem == 0 && has_h) return 2 * a;
+    if ((rem == 0 && has_v) || (rem == 1 && has_h && has_v)) return 2 * a + 1;
     return -1;
 }
 
