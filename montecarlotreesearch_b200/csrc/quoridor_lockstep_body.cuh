@@ -297,17 +297,13 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
         {
             const B81 goal_b = qb ? b81(MCTSB_GOAL_B_A, 0u, 0u) : b81(0u, 0u, MCTSB_GOAL_W_C);
             const B81 pawn_a = b81_bit(cell_a), pawn_b = b81_bit(cell_b);
-            B81 tmask = b81(0u, 0u, 0u);                       // step targets still to be reached by search B
-            LS_UNROLL1
-            for (uint32_t m = steps; m; m &= m - 1u) tmask = tmask | b81_bit(cell_b + q_step_delta(ctz32(m)));
             B81 ra = goal_a, rb = goal_b;
+            B81 rb1 = b81(0u, 0u, 0u), rb2 = b81(0u, 0u, 0u);  // search B one and two expansions ago
             bool busy_a = playing || capped, busy_b = busy_a;
             if (busy_a) {
                 wk.flood_queries += 2;
                 if (b81_any(pawn_a & goal_a)) { sp_a = 0; busy_a = false; }
-                tmask = andn(tmask, goal_b);                   // targets on the goal row have distance 0 (fields start at 0)
-                if (b81_any(pawn_b & goal_b)) sp_b = 0;
-                busy_b = sp_b < 0 || b81_any(tmask);
+                if (b81_any(pawn_b & goal_b)) { sp_b = 0; busy_b = false; }
             }
             int j = 0;
             LS_UNROLL1
@@ -324,29 +320,27 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 }
                 if (busy_b) {
                     B81 grown = q_flood_step(rb, s.openS, s.openE);
-                    B81 layer = andn(grown, rb);
                     wk.flood_steps++;
-                    rb = grown;
-                    if (b81_any(layer & pawn_b)) sp_b = j;
-                    B81 hit = layer & tmask;
-                    if (b81_any(hit)) {
-                        tmask = andn(tmask, hit);
-                        LS_UNROLL1
-                        for (uint32_t m = steps; m; m &= m - 1u) {
-                            int i = ctz32(m);
-                            if (b81_test(hit, cell_b + q_step_delta(i))) td_or(td0, td1, td2, i, (uint32_t)j);
-                        }
-                    }
-                    if (!b81_any(layer)) busy_b = false;       // exhausted
-                    else busy_b = sp_b < 0 || b81_any(tmask);
+                    if (b81_any(grown & pawn_b)) { sp_b = j; busy_b = false; }
+                    else if (b81_eq(grown, rb)) busy_b = false;    // exhausted
+                    rb2 = rb1; rb1 = rb; rb = grown;
                 }
             }
-            // unreached step targets (cannot happen while the pawn has a path) keep distance "unreachable"
-            if (b81_any(tmask)) {
+            // Distances of the legal step targets (get_best_step_move measures each with its own BFS,
+            // Quoridor.cpp:476-497).  A target is one or two moves from the pawn, so its distance is within
+            // two of the pawn's: rb2, rb1, rb and one more expansion are the cells within sp-2 .. sp+1.
+            if (LS_ANY(steps != 0u)) {
+                const B81 rb_next = q_flood_step(rb, s.openS, s.openE);
                 LS_UNROLL1
-                for (uint32_t m = steps; m; m &= m - 1u) {
-                    int i = ctz32(m);
-                    if (b81_test(tmask, cell_b + q_step_delta(i))) td_or(td0, td1, td2, i, 0xffu);
+                for (uint32_t m = steps; LS_ANY(m != 0u); m &= m - 1u) {
+                    if (m) {
+                        const int i = ctz32(m), t = cell_b + q_step_delta(i);
+                        uint32_t dist = 0xffu;
+                        if (sp_b >= 0)
+                            dist = b81_test(rb2, t) ? (uint32_t)(sp_b - 2) : b81_test(rb1, t) ? (uint32_t)(sp_b - 1)
+                                 : b81_test(rb, t) ? (uint32_t)sp_b : b81_test(rb_next, t) ? (uint32_t)(sp_b + 1) : (uint32_t)(sp_b + 2);
+                        td_or(td0, td1, td2, i, dist);
+                    }
                 }
             }
         }
@@ -431,12 +425,26 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 for (int o = 1; o < LS_WARP; o <<= 1) { int t = LS_SHFL_UP(off, o); if (lane >= o) off += t; }
                 const int total = LS_SHFL(off, LS_WARP - 1);
                 off -= mine;
-                LS_UNROLL1
-                for (int i = 0; LS_ANY(i < mine); i++) {
-                    if (i < mine) {
-                        int k = head_k;
-                        if (k < 0) { k = q_mask_first(pend_h, pend_v); q_mask_clear(pend_h, pend_v, k); }
-                        wb.queue[off + i] = (uint16_t)((lane << 8) | k);
+                {   // enumerate word by word (h low, h high, v low, v high): one FLO + one LOP per candidate
+                    int wi = 0;
+                    uint32_t cur = (uint32_t)pend_h;
+                    LS_UNROLL1
+                    for (int i = 0; LS_ANY(i < mine); i++) {
+                        if (i < mine) {
+                            int k = head_k;
+                            if (k < 0) {
+                                while (cur == 0u) { wi++; cur = wi == 1 ? (uint32_t)(pend_h >> 32) : wi == 2 ? (uint32_t)pend_v : (uint32_t)(pend_v >> 32); }
+                                const int b = ctz32(cur);
+                                cur &= cur - 1u;
+                                k = 2 * (32 * (wi & 1) + b) + (wi >> 1);
+                            }
+                            wb.queue[off + i] = (uint16_t)((lane << 8) | k);
+                        }
+                    }
+                    if (head_k < 0) {                          // write the unsent remainder back
+                        uint64_t m0 = wi == 0 ? (uint64_t)cur | (pend_h & 0xffffffff00000000ull) : wi == 1 ? (uint64_t)cur << 32 : 0ull;
+                        uint64_t m1 = wi <= 1 ? pend_v : wi == 2 ? (uint64_t)cur | (pend_v & 0xffffffff00000000ull) : (uint64_t)cur << 32;
+                        pend_h = m0; pend_v = m1;
                     }
                 }
                 const bool head_sent = head_k >= 0;
