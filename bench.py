@@ -23,7 +23,6 @@ import json
 import os
 import subprocess
 import sys
-import threading
 import time
 
 import numpy as np
@@ -33,47 +32,64 @@ sys.path.insert(0, ROOT)
 
 METRIC = "quoridor_9x9_ref_policy_rollouts_per_sec"
 UNIT = "rollouts/s"
-# Algorithmic integer work of one REF-policy rollout from the opening position, counted by the
-# oracle (oracle/quoridor_oracle.c work counters, 1500 rollouts): 13 367 flood-fill steps x 24 ops
-# + 4 582 cheap wall tests x 12 ops + 49.1 plies x 200 ops (DESIGN.md "Roofline").
-ALG_OPS_PER_ROLLOUT = 13367 * 24 + 4582 * 12 + 49.1 * 200
-ALG_HBM_BYTES_PER_ROLLOUT = 24.0 / 1.0  # per LEAF: 32 B state in + 24 B sums out; per rollout ~0 at R = 2^20
+# Algorithmic integer work of one REF-policy rollout from the opening position — the REFERENCE algorithm's
+# work, counted by the oracle (oracle/quoridor_oracle.c work counters, 4 000 rollouts under the bench seed):
+# 13 133 BFS levels ("flood-fill steps") x 24 ops + 4 533 cheap wall tests x 12 ops + 49.1 plies x 200 ops
+# (DESIGN.md "Roofline").  The kernel executes fewer steps than this: exact pruning.
+ALG_OPS_PER_ROLLOUT = 13133.3 * 24 + 4532.6 * 12 + 49.1 * 200
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
+# algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
+NCU_DRAM_BYTES_PER_LAUNCH = None
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md): one
+    `nvidia-smi -lms 50` process streaming CSV rows, started before and killed after the region."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        super().__init__(daemon=True)
-        self.gpu, self.rows, self.stop_flag = gpu_index, [], False
+        self.gpu, self.proc, self.rows = gpu_index, None, []
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits"],
-                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([c.strip() for c in out.split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            time.sleep(0.15)          # let the first sample land before the region starts
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return
+        try:
+            self.proc.terminate()
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            out = ""
+        self.rows = [[c.strip() for c in line.split(",")] for line in out.splitlines() if line.count(",") >= 8]
 
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit())
+
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        sm = sorted(v for v in (num(r[1]) for r in self.rows) if v is not None)
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             for name, v in zip(names, r[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][2]) if self.rows[0][2].replace(".", "").isdigit() else None,
-                "reasons": sorted(reasons), "samples": len(self.rows),
-                "power_w_max": max((float(r[3]) for r in self.rows if r[3].replace(".", "").isdigit()), default=None)}
+        power = [v for v in (num(r[3]) for r in self.rows) if v is not None]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": num(self.rows[0][2]), "reasons": sorted(reasons),
+                "samples": len(self.rows), "power_w_max": max(power) if power else None}
 
 
 def host_threads():
@@ -102,7 +118,7 @@ def run_reference_arm(args, rank, world):
     per_step = []
     sample_jobs = 0
     for i in range(args.warmup + args.steps):
-        rate, jobs, secs, mean = reference_rollouts_per_sec(4.0 if i >= args.warmup else 1.0, threads)
+        rate, jobs, secs, mean = reference_rollouts_per_sec(2.0 if i >= args.warmup else 0.5, threads)
         if i >= args.warmup:
             per_step.append((jobs, secs))
             sample_jobs = jobs
@@ -126,7 +142,7 @@ def run_reference_arm(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rollouts", type=int, default=1 << 20, help="rollouts per step per GPU")
@@ -144,6 +160,7 @@ def main():
         return
 
     import montecarlotreesearch_b200 as m
+    from montecarlotreesearch_b200 import multi
 
     dist = None
     if world > 1:
@@ -169,10 +186,6 @@ def main():
 
     # ---- device-resident throughput ("value") -------------------------------------------------------------
     be.upload_states(G, state)
-    stats_dev = None
-    if dist is not None:
-        import torch
-        stats_dev = torch.zeros(3, dtype=torch.int64, device="cuda")
     launches0 = be.counters()["kernel_launches"]
     for w in range(args.warmup):
         be.run_resident(G, P, n, first_id(w), timed=True)
@@ -180,6 +193,7 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
+    barrier()
     kernel_ms = []
     t0 = time.perf_counter()
     total_score = 0.0
@@ -187,16 +201,13 @@ def main():
         ms = be.run_resident(G, P, n, first_id(args.warmup + k), timed=True)
         score, sums = be.wait()
         if dist is not None:
-            import torch
-            stats_dev.copy_(torch.tensor([int(sums["lo"][0]), int(sums["hi"][0]), int(sums["n"][0])], dtype=torch.int64))
-            dist.all_reduce(stats_dev)          # exact integer merge of the root statistics
-            torch.cuda.synchronize()
+            sums = multi.allreduce_leaf_sums(sums, dist, device="cuda")   # exact integer merge over NVLink (NCCL)
+            score = np.array([multi.leaf_sum_to_double(sums["lo"][0], sums["hi"][0])])
         kernel_ms.append(ms)
         total_score += score[0]
     barrier()
     wall_s = time.perf_counter() - t0
-    sampler.stop_flag = True
-    sampler.join(timeout=2)
+    sampler.stop()
     launches = be.counters()["kernel_launches"] - launches0 - args.warmup
 
     dev_ms = float(sum(kernel_ms))
@@ -210,6 +221,7 @@ def main():
         step_ms = dev_ms
     total_rollouts = n * args.steps * world
     value = total_rollouts / (step_ms * 1e-3)
+    mean_score = total_score / (n * args.steps * world) if dist is not None else total_score / (n * args.steps)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     states_host = np.array([state], dtype=m.QSTATE_DTYPE)
@@ -254,14 +266,14 @@ def main():
                    "rollouts_per_step_per_gpu": n, "leaves": 1, "seed": hex(m.DEFAULT_SEED),
                    "l2": "inputs are one 32-byte state; the path is ALU-bound, nothing to flush; rollout ids differ every step"},
         "roofline": {"bound": "sm_int_issue", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
-                     "frac": achieved / int_peak, "traffic": None,
+                     "frac": achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "alg_ops_per_rollout": ALG_OPS_PER_ROLLOUT, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
                      "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3/IADD3 chains, all SMs)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * world, "d2h_bytes_per_step": 24 * world},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
-        "mean_score": total_score / (n * args.steps),
+        "mean_score": mean_score,
         "kernel_ms_per_step": dev_ms / args.steps,
     }
     print(json.dumps(line), flush=True)
