@@ -240,6 +240,9 @@ def main():
     e2e_value = total_rollouts / e2e_s
 
     counters = be.counters()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
     if rank != 0:
         return
 
