@@ -397,7 +397,7 @@ MC_HD bool q_force_playwall(QState &s, QWork *wk) {
 //      anchored at a may change the distance (see q_trace_to_anchors for the exact rule).
 // m not in cut  =>  sp(q, m) == sp(q) exactly; m in cut => run the flood fill as before.
 // ------------------------------------------------------------------------------------------------
-#define MCTSB_MAX_LAYERS 28          // deeper searches fall back to "every wall may cut" (still exact)
+#define MCTSB_MAX_LAYERS 24          // deeper searches fall back to "every wall may cut" (still exact)
 
 // Scratch for the layers: plain array on the host, strided shared memory in the kernels.
 struct LocalLayers {

@@ -87,7 +87,7 @@ static constexpr int LS_SHARE = 32;                     // candidates one lane m
 static constexpr int LS_QCAP = 32 * LS_SHARE;           // queue entries per warp
 
 // per-warp shared scratch of the candidate phase
-struct WarpBuf { uint16_t *queue; unsigned long long *best; };
+struct WarpBuf { uint32_t *queue; unsigned long long *best; };
 
 // layers of one lane live in shared memory, word-interleaved across the block: no bank conflicts
 struct SmemLayers {
@@ -227,10 +227,10 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
     const int lane = LS_TID & 31, warp = LS_TID >> 5;
     SmemLayers ls; ls.base = smem + LS_TID;
     WarpBuf wb;
-    {   // layout: [layers][best slots: 32 x u64 per warp][queues: LS_QCAP x u16 per warp]
+    {   // layout: [layers][best slots: 32 x u64 per warp][queues: LS_QCAP x u32 per warp]
         uint32_t *after = smem + MCTSB_MAX_LAYERS * 3 * LS_THREADS;
         wb.best = reinterpret_cast<unsigned long long *>(after) + 32 * warp;
-        wb.queue = reinterpret_cast<uint16_t *>(after + 2 * LS_THREADS) + LS_QCAP * warp;
+        wb.queue = after + 2 * LS_THREADS + LS_QCAP * warp;
     }
 
     QState s; LaneDraws<REPLAY> d;
@@ -438,7 +438,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                                 cur &= cur - 1u;
                                 k = 2 * (32 * (wi & 1) + b) + (wi >> 1);
                             }
-                            wb.queue[off + i] = (uint16_t)((lane << 8) | k);
+                            wb.queue[off + i] = (uint32_t)lane | ((uint32_t)k << 5);
                         }
                     }
                     if (head_k < 0) {                          // write the unsent remainder back
@@ -450,13 +450,43 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 const bool head_sent = head_k >= 0;
                 head_k = -1;
                 LS_SYNCWARP();
-                // -- work: 32 tasks per trip
+                // -- stage 1, 32 tasks per trip: the first query (the enemy's path with the wall; first legal:
+                //    White's).  Only candidates that pass it need the second query; they are compacted to the
+                //    front of the same queue (ballot + popc), so stage 2 runs with full warps again.
+                int passed = 0;
                 LS_UNROLL1
                 for (int t0 = 0; t0 < total; t0 += LS_WARP) {
                     const int t = t0 + lane;
                     const bool valid = t < total;
-                    const uint32_t ent = valid ? (uint32_t)wb.queue[t] : 0u;
-                    const int owner = (int)(ent >> 8), k = (int)(ent & 0xffu);
+                    const uint32_t ent = valid ? wb.queue[t] : 0u;
+                    const int owner = (int)(ent & 31u), k = (int)((ent >> 5) & 127u);
+                    B81 oS = b81(LS_SHFL(s.openS.a, owner), LS_SHFL(s.openS.b, owner), LS_SHFL(s.openS.c, owner));
+                    B81 oE = b81(LS_SHFL(s.openE.a, owner), LS_SHFL(s.openE.b, owner), LS_SHFL(s.openE.c, owner));
+                    const uint32_t oc = LS_SHFL(pk_cells, owner), osp = LS_SHFL(pk_sp, owner);
+                    const int o_turn = (int)((oc >> 16) & 0xffu), o_mode = (int)(oc >> 24);
+                    const int o_sp_e = (int)(int8_t)(osp & 0xffu);
+                    {   // the candidate wall on the owner's boards
+                        int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
+                        if (k & 1) oE = andn(oE, b81_shifted(0x201u, pos)); else oS = andn(oS, b81_shifted(0x3u, pos));
+                    }
+                    const int p1 = o_mode == 3 ? 0 : 1 - o_turn;
+                    const int c1 = (int)((p1 ? (oc >> 8) : oc) & 0xffu);
+                    const int d1 = warp_flood(valid, oS, oE, c1, p1, wk);
+                    const bool pass = valid && d1 >= 0 && (o_mode == 3 || d1 - o_sp_e > 0);
+                    const unsigned bal = LS_BALLOT(pass);
+                    LS_SYNCWARP();
+                    if (pass) wb.queue[passed + LS_POPC(bal & ((1u << lane) - 1u))] = (ent & 0xfffu) | ((uint32_t)d1 << 12);
+                    passed += LS_POPC(bal);
+                }
+                LS_SYNCWARP();
+                // -- stage 2: the mover's own path with the wall (first legal: Black's), the verdict, and the
+                //    candidate's place in the shuffled pool for the ones that are acceptable
+                LS_UNROLL1
+                for (int t0 = 0; t0 < passed; t0 += LS_WARP) {
+                    const int t = t0 + lane;
+                    const bool valid = t < passed;
+                    const uint32_t ent = valid ? wb.queue[t] : 0u;
+                    const int owner = (int)(ent & 31u), k = (int)((ent >> 5) & 127u), d1 = (int)(ent >> 12);
                     B81 oS = b81(LS_SHFL(s.openS.a, owner), LS_SHFL(s.openS.b, owner), LS_SHFL(s.openS.c, owner));
                     B81 oE = b81(LS_SHFL(s.openE.a, owner), LS_SHFL(s.openE.b, owner), LS_SHFL(s.openE.c, owner));
                     const uint32_t oc = LS_SHFL(pk_cells, owner), osp = LS_SHFL(pk_sp, owner);
@@ -466,26 +496,17 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                     const int o_turn = (int)((oc >> 16) & 0xffu), o_mode = (int)(oc >> 24);
                     const int o_sp_e = (int)(int8_t)(osp & 0xffu), o_sp_p = (int)(int8_t)((osp >> 8) & 0xffu);
                     const int o_n = (int)((osp >> 16) & 0xffu), o_j0 = (int)(osp >> 24);
-                    {   // the candidate wall on the owner's boards
+                    {
                         int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
                         if (k & 1) oE = andn(oE, b81_shifted(0x201u, pos)); else oS = andn(oS, b81_shifted(0x3u, pos));
                     }
-                    // first query: the enemy's path with the wall (first legal: White's); second: the mover's (Black's)
-                    const int p1 = o_mode == 3 ? 0 : 1 - o_turn;
-                    int dq[2] = {-1, -1};
-                    bool go = valid;
-                    LS_UNROLL1
-                    for (int stage = 0; stage < 2; stage++) {
-                        const int pq = stage == 0 ? p1 : 1 - p1;
-                        const int cq = (int)((pq ? (oc >> 8) : oc) & 0xffu);
-                        const int dist = warp_flood(go, oS, oE, cq, pq, wk);
-                        if (stage == 0) { dq[0] = dist; go = valid && dist >= 0 && (o_mode == 3 || dist - o_sp_e > 0); }
-                        else dq[1] = dist;
-                    }
+                    const int p2 = o_mode == 3 ? 1 : o_turn;
+                    const int c2 = (int)((p2 ? (oc >> 8) : oc) & 0xffu);
+                    const int d2 = warp_flood(valid, oS, oE, c2, p2, wk);
                     int gain = 0;                              // > 0: acceptable
-                    if (go && dq[1] >= 0) {
+                    if (valid && d2 >= 0) {
                         if (o_mode == 3) gain = 1;
-                        else { int ee = dq[0] - o_sp_e, oe = dq[1] - o_sp_p; if (ee > oe) gain = o_mode == 1 ? ee - oe : 1; }
+                        else { int ee = d1 - o_sp_e, oe = d2 - o_sp_p; if (ee > oe) gain = o_mode == 1 ? ee - oe : 1; }
                     }
                     const bool accepted = gain > 0;
                     int rk = 0;
