@@ -39,7 +39,7 @@ UNIT = "rollouts/s"
 ALG_OPS_PER_ROLLOUT = 13133.3 * 24 + 4532.6 * 12 + 49.1 * 200
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
 # algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
-NCU_DRAM_BYTES_PER_LAUNCH = None
+NCU_DRAM_BYTES_PER_LAUNCH = 374016 + 746240   # profiles/r01_v2f_lockstep.md
 
 
 class ClockSampler:
@@ -146,6 +146,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rollouts", type=int, default=1 << 20, help="rollouts per step per GPU")
+    ap.add_argument("--workload", default="opening", choices=["opening", "corpus"],
+                    help="opening = configs[1] (headline); corpus = configs[2]: 4096 mid-game states x rollouts/4096 each")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU sample for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -170,8 +172,14 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     be = m.RolloutBackend(local_rank, m.DEFAULT_SEED)
-    state = m.quoridor_opening()
-    n = args.rollouts
+    if args.workload == "corpus":
+        state = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))[:4096]
+        per_leaf = max(1, args.rollouts // 4096)
+    else:
+        state = np.array([m.quoridor_opening()], dtype=m.QSTATE_DTYPE)
+        per_leaf = args.rollouts
+    n_leaves = len(state)
+    n = per_leaf * n_leaves
     G, P = m.GAME_QUORIDOR, m.POLICY_REF
 
     def barrier():
@@ -188,7 +196,7 @@ def main():
     be.upload_states(G, state)
     launches0 = be.counters()["kernel_launches"]
     for w in range(args.warmup):
-        be.run_resident(G, P, n, first_id(w), timed=True)
+        be.run_resident(G, P, per_leaf, first_id(w), timed=True)
         be.wait()
     barrier()
     sampler = ClockSampler(local_rank)
@@ -198,13 +206,13 @@ def main():
     t0 = time.perf_counter()
     total_score = 0.0
     for k in range(args.steps):
-        ms = be.run_resident(G, P, n, first_id(args.warmup + k), timed=True)
+        ms = be.run_resident(G, P, per_leaf, first_id(args.warmup + k), timed=True)
         score, sums = be.wait()
         if dist is not None:
             sums = multi.allreduce_leaf_sums(sums, dist, device="cuda")   # exact integer merge over NVLink (NCCL)
-            score = np.array([multi.leaf_sum_to_double(sums["lo"][0], sums["hi"][0])])
+            score = np.array([multi.leaf_sum_to_double(lo, hi) for lo, hi in zip(sums["lo"], sums["hi"])])
         kernel_ms.append(ms)
-        total_score += score[0]
+        total_score += float(np.sum(score))
     barrier()
     wall_s = time.perf_counter() - t0
     sampler.stop()
@@ -224,12 +232,12 @@ def main():
     mean_score = total_score / (n * args.steps * world) if dist is not None else total_score / (n * args.steps)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
-    states_host = np.array([state], dtype=m.QSTATE_DTYPE)
-    be.rollout_batch(G, P, states_host, n, first_id(1000))
+    states_host = np.ascontiguousarray(state, dtype=m.QSTATE_DTYPE)
+    be.rollout_batch(G, P, states_host, per_leaf, first_id(1000))
     barrier()
     t0 = time.perf_counter()
     for k in range(args.steps):
-        be.rollout_batch(G, P, states_host, n, first_id(2000 + k))
+        be.rollout_batch(G, P, states_host, per_leaf, first_id(2000 + k))
     barrier()
     e2e_s = time.perf_counter() - t0
     if dist is not None:
@@ -264,16 +272,17 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: Quoridor 9x9 opening position, %d independent REF-policy rollouts per GPU per step" % n,
+        "config": {"workload": ("configs[1]: Quoridor 9x9 opening position, %d independent REF-policy rollouts per GPU per step" % n) if args.workload == "opening"
+                   else ("configs[2]: mid-game corpus, 4096 states x %d REF-policy rollouts per GPU per step" % per_leaf),
                    "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)",
-                   "rollouts_per_step_per_gpu": n, "leaves": 1, "seed": hex(m.DEFAULT_SEED),
+                   "rollouts_per_step_per_gpu": n, "leaves": n_leaves, "seed": hex(m.DEFAULT_SEED),
                    "l2": "inputs are one 32-byte state; the path is ALU-bound, nothing to flush; rollout ids differ every step"},
         "roofline": {"bound": "sm_int_issue", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
                      "frac": achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "alg_ops_per_rollout": ALG_OPS_PER_ROLLOUT, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
                      "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3/IADD3 chains, all SMs)"},
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * world, "d2h_bytes_per_step": 24 * world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "mean_score": mean_score,
