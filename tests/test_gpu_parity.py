@@ -230,3 +230,22 @@ def test_full_size_properties(be):
     _, s2 = be.rollout_batch(G, m.POLICY_REF, m.quoridor_opening(), n // 2, n // 2)
     assert int(s1["lo"][0]) + int(s2["lo"][0]) == int(sums["lo"][0])
     assert int(s1["hi"][0]) + int(s2["hi"][0]) == int(sums["hi"][0])
+
+
+def test_two_independent_kernels_agree(be, corpus):
+    """The production lockstep kernel against the one-thread-per-rollout kernel (MCTSB_SIMPLE_KERNEL=1):
+    two device implementations of the REF policy, same outcomes and final positions."""
+    import os
+    os.environ["MCTSB_SIMPLE_KERNEL"] = "1"
+    try:
+        simple = m.RolloutBackend(0, m.DEFAULT_SEED)
+    finally:
+        del os.environ["MCTSB_SIMPLE_KERNEL"]
+    rng = np.random.default_rng(33)
+    states = corpus[rng.choice(len(corpus), 256, replace=False)]
+    a, fa = be.rollout_outcomes(G, m.POLICY_REF, states, 8, 31337)
+    b, fb = simple.rollout_outcomes(G, m.POLICY_REF, states, 8, 31337)
+    simple.close()
+    assert a.tobytes() == b.tobytes() and fa.tobytes() == fb.tobytes()
+    a, fa = be.rollout_outcomes(G, m.POLICY_REF, m.quoridor_opening(), 4096, 99, finals=False)
+    assert abs(a["score"].mean() - 0.65) < 0.03
