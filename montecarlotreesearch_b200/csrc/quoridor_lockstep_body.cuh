@@ -50,6 +50,7 @@ static inline unsigned long long ls_emu_add(unsigned long long *p, unsigned long
 static inline unsigned long long ls_emu_bits(double x) { unsigned long long b; memcpy(&b, &x, 8); return b; }
 #define LS_DBITS(x) ls_emu_bits(x)
 #define LS_UNROLL1
+#define LS_UNROLL2
 #else
 #define LS_DEV __device__ __forceinline__
 #define LS_NOINLINE __device__ __noinline__
@@ -71,6 +72,7 @@ static inline unsigned long long ls_emu_bits(double x) { unsigned long long b; m
 #define LS_D2ULL(x) __double2ull_rz(x)
 #define LS_DBITS(x) ((unsigned long long)__double_as_longlong(x))
 #define LS_UNROLL1 _Pragma("unroll 1")
+#define LS_UNROLL2 _Pragma("unroll 2")
 #endif
 
 namespace mctsb {
@@ -197,7 +199,7 @@ LS_DEV int warp_flood(bool go, B81 oS, B81 oE, int start, int player, QWork &wk)
     bool busy = go;
     if (busy && ((r.a & ga) | (r.c & gc))) { dist = 0; busy = false; }
     if (go) wk.flood_queries++;
-    LS_UNROLL1
+    LS_UNROLL2
     while (LS_ANY(busy)) {
         const B81 n = q_flood_step(r, oS, oE);
         d++;
