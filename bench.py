@@ -148,6 +148,8 @@ def main():
     ap.add_argument("--rollouts", type=int, default=1 << 20, help="rollouts per step per GPU")
     ap.add_argument("--workload", default="opening", choices=["opening", "corpus"],
                     help="opening = configs[1] (headline); corpus = configs[2]: 4096 mid-game states x rollouts/4096 each")
+    ap.add_argument("--policy", default="ref", choices=["ref", "uni"], help="ref = headline (reference rollout()); uni = uniformly random legal moves (secondary)")
+    ap.add_argument("--game", default="quoridor", choices=["quoridor", "tictactoe"], help="tictactoe = configs[0] rollouts from the empty board (secondary)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU sample for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -178,9 +180,14 @@ def main():
     else:
         state = np.array([m.quoridor_opening()], dtype=m.QSTATE_DTYPE)
         per_leaf = args.rollouts
+    if args.game == "tictactoe":
+        state = np.zeros(1, dtype=m.TSTATE_DTYPE)
+        per_leaf = args.rollouts
     n_leaves = len(state)
     n = per_leaf * n_leaves
-    G, P = m.GAME_QUORIDOR, m.POLICY_REF
+    G = m.GAME_QUORIDOR if args.game == "quoridor" else m.GAME_TICTACTOE
+    P = m.POLICY_UNI if (args.policy == "uni" and args.game == "quoridor") else m.POLICY_REF
+    secondary = args.game != "quoridor" or args.policy != "ref"
 
     def barrier():
         if dist is not None:
@@ -232,7 +239,7 @@ def main():
     mean_score = total_score / (n * args.steps * world) if dist is not None else total_score / (n * args.steps)
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
-    states_host = np.ascontiguousarray(state, dtype=m.QSTATE_DTYPE)
+    states_host = np.ascontiguousarray(state)
     be.rollout_batch(G, P, states_host, per_leaf, first_id(1000))
     barrier()
     t0 = time.perf_counter()
@@ -256,7 +263,7 @@ def main():
 
     # ---- CPU baseline on this box's host cores (bounded sample) ------------------------------------------
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and not secondary:
         try:
             threads = host_threads()
             rate, jobs, secs, mean = reference_rollouts_per_sec(args.cpu_seconds, threads)
@@ -271,7 +278,7 @@ def main():
     achieved = per_gpu_rate * alg_ops
     exec_steps_per_rollout = counters["flood_steps"] / max(1, counters["rollouts"])
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "metric": METRIC if not secondary else "%s_%s_rollouts_per_sec" % (args.game, args.policy), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic",
         "config": {"workload": ("configs[1]: Quoridor 9x9 opening position, %d independent REF-policy rollouts per GPU per step" % n) if args.workload == "opening"
