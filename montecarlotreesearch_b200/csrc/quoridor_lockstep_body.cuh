@@ -419,34 +419,39 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             LS_DBG(if (playing) g_dbg_pend[mode][popc64(pend_h) + popc64(pend_v)]++;)
             LS_UNROLL1
             while (LS_ANY((pend_h | pend_v) != 0ull || head_k >= 0)) {
-                // -- publish: every lane queues up to LS_SHARE candidates, offsets by an exclusive warp scan
-                int cnt = head_k >= 0 ? 1 : popc64(pend_h) + popc64(pend_v);
-                int mine = cnt < LS_SHARE ? cnt : LS_SHARE;
+                // -- publish: every lane queues up to LS_SHARE candidates (half horizontal, half vertical), offsets
+                //    by an exclusive warp scan.  Order inside the queue is free: every queued candidate is measured.
+                const int nh = popc64(pend_h), nv = popc64(pend_v);
+                const int mh = head_k >= 0 ? 0 : (nh < LS_SHARE / 2 ? nh : LS_SHARE / 2);
+                const int mv = head_k >= 0 ? 0 : (nv < LS_SHARE / 2 ? nv : LS_SHARE / 2);
+                const int mine = head_k >= 0 ? 1 : mh + mv;
                 int off = mine;
                 LS_UNROLL1
                 for (int o = 1; o < LS_WARP; o <<= 1) { int t = LS_SHFL_UP(off, o); if (lane >= o) off += t; }
                 const int total = LS_SHFL(off, LS_WARP - 1);
                 off -= mine;
-                {   // enumerate word by word (h low, h high, v low, v high): one FLO + one LOP per candidate
-                    int wi = 0;
-                    uint32_t cur = (uint32_t)pend_h;
+                if (head_k >= 0) wb.queue[off] = (uint32_t)lane | ((uint32_t)head_k << 5);
+                {   // two independent bit iterators per trip: one FLO + one LOP per candidate
+                    uint32_t ch = (uint32_t)pend_h, cv = (uint32_t)pend_v;
+                    int wh = 0, wv = 0;
                     LS_UNROLL1
-                    for (int i = 0; LS_ANY(i < mine); i++) {
-                        if (i < mine) {
-                            int k = head_k;
-                            if (k < 0) {
-                                while (cur == 0u) { wi++; cur = wi == 1 ? (uint32_t)(pend_h >> 32) : wi == 2 ? (uint32_t)pend_v : (uint32_t)(pend_v >> 32); }
-                                const int b = ctz32(cur);
-                                cur &= cur - 1u;
-                                k = 2 * (32 * (wi & 1) + b) + (wi >> 1);
-                            }
-                            wb.queue[off + i] = (uint32_t)lane | ((uint32_t)k << 5);
+                    for (int i = 0; LS_ANY(i < mh || i < mv); i++) {
+                        if (i < mh) {
+                            if (ch == 0u) { wh = 1; ch = (uint32_t)(pend_h >> 32); }
+                            const int bpos = ctz32(ch);
+                            ch &= ch - 1u;
+                            wb.queue[off + i] = (uint32_t)lane | ((uint32_t)(2 * (32 * wh + bpos)) << 5);
+                        }
+                        if (i < mv) {
+                            if (cv == 0u) { wv = 1; cv = (uint32_t)(pend_v >> 32); }
+                            const int bpos = ctz32(cv);
+                            cv &= cv - 1u;
+                            wb.queue[off + mh + i] = (uint32_t)lane | ((uint32_t)(2 * (32 * wv + bpos) + 1) << 5);
                         }
                     }
-                    if (head_k < 0) {                          // write the unsent remainder back
-                        uint64_t m0 = wi == 0 ? (uint64_t)cur | (pend_h & 0xffffffff00000000ull) : wi == 1 ? (uint64_t)cur << 32 : 0ull;
-                        uint64_t m1 = wi <= 1 ? pend_v : wi == 2 ? (uint64_t)cur | (pend_v & 0xffffffff00000000ull) : (uint64_t)cur << 32;
-                        pend_h = m0; pend_v = m1;
+                    if (head_k < 0) {                          // the unsent remainder stays pending
+                        pend_h = wh == 0 ? ((uint64_t)ch | (pend_h & 0xffffffff00000000ull)) : ((uint64_t)ch << 32);
+                        pend_v = wv == 0 ? ((uint64_t)cv | (pend_v & 0xffffffff00000000ull)) : ((uint64_t)cv << 32);
                     }
                 }
                 const bool head_sent = head_k >= 0;
