@@ -168,6 +168,7 @@ def main():
 
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)

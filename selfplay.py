@@ -42,6 +42,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
