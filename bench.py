@@ -287,10 +287,12 @@ def main():
                    "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)",
                    "rollouts_per_step_per_gpu": n, "leaves": n_leaves, "seed": hex(m.DEFAULT_SEED),
                    "l2": "inputs are one 32-byte state; the path is ALU-bound, nothing to flush; rollout ids differ every step"},
-        "roofline": {"bound": "sm_int_issue", "achieved": achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
-                     "frac": achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+        "roofline": {"bound": "sm_int_issue", "achieved": None if secondary else achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
+                     "frac": None if secondary else achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
-                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3/IADD3 chains, all SMs)"},
+                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3/IADD3 chains, all SMs); "
+                             "achieved = rollouts/s x the REFERENCE algorithm's integer work per rollout (DESIGN.md 5); executed "
+                             "thread instructions per second from ncu are in profiles/ (0.60 of this peak)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world},
         "gpu_launches": int(launches),
