@@ -39,7 +39,7 @@ UNIT = "rollouts/s"
 ALG_OPS_PER_ROLLOUT = 13133.3 * 24 + 4532.6 * 12 + 49.1 * 200
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
 # algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
-NCU_DRAM_BYTES_PER_LAUNCH = 374016 + 746240   # profiles/r01_v2f_lockstep.md
+NCU_DRAM_BYTES_PER_LAUNCH = 366848 + 776192   # profiles/r01_final_lockstep.md
 
 
 class ClockSampler:
