@@ -199,6 +199,7 @@ def main():
 
     # ---- measured integer-issue peak (roofline denominator) -----------------------------------------
     int_peak, _ = be.int_issue_peak()
+    lop3_peak, _ = be.lop3_peak()
 
     # ---- device-resident throughput ("value") -------------------------------------------------------------
     be.upload_states(G, state)
@@ -289,10 +290,10 @@ def main():
                    "l2": "inputs are one 32-byte state; the path is ALU-bound, nothing to flush; rollout ids differ every step"},
         "roofline": {"bound": "sm_int_issue", "achieved": None if secondary else achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
                      "frac": None if secondary else achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
-                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3/IADD3 chains, all SMs); "
+                     "alu_pipe_lop3_peak": lop3_peak / 1e12, "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
+                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3 + integer-add chains on all SMs, both pipes; alu_pipe_lop3_peak = LOP3 only); "
                              "achieved = rollouts/s x the REFERENCE algorithm's integer work per rollout (DESIGN.md 5); executed "
-                             "thread instructions per second from ncu are in profiles/ (0.60 of this peak)"},
+                             "thread instructions per second from ncu are in profiles/ (17.7 T/s = 0.51 of this peak)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world},
         "gpu_launches": int(launches),

@@ -363,7 +363,7 @@ int mctsb_run_resident(mctsb_backend *b, int game, int policy, uint32_t rollouts
     return MCTSB_OK;
 }
 
-int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms) {
+static int run_peak_probe(mctsb_backend *b, bool lop3_only, double *thread_ops_per_sec, float *elapsed_ms) {
     if (!b || !thread_ops_per_sec) return MCTSB_ERR_BAD_ARG;
     CK(cudaSetDevice(b->device));
     cudaDeviceProp prop;
@@ -372,7 +372,8 @@ int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *el
     float best = 1e30f;
     for (int rep = 0; rep < 4; rep++) {           // first trip warms up, best of the rest
         CK(cudaEventRecord(b->ev0, b->stream));
-        cudaError_t e = launch_int_peak(b->d_sink, blocks, threads, iters, b->stream);
+        cudaError_t e = lop3_only ? launch_lop3_peak(b->d_sink, blocks, threads, iters, b->stream)
+                                  : launch_int_peak(b->d_sink, blocks, threads, iters, b->stream);
         if (e != cudaSuccess) return fail_cuda(b, e, "int peak launch");
         b->launches++;
         CK(cudaEventRecord(b->ev1, b->stream));
@@ -383,6 +384,14 @@ int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *el
     *thread_ops_per_sec = (double)blocks * threads * (double)iters * INT_PEAK_OPS_PER_ITER / (best * 1e-3);
     if (elapsed_ms) *elapsed_ms = best;
     return MCTSB_OK;
+}
+
+int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms) {
+    return run_peak_probe(b, false, thread_ops_per_sec, elapsed_ms);
+}
+
+int mctsb_lop3_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms) {
+    return run_peak_probe(b, true, thread_ops_per_sec, elapsed_ms);
 }
 
 int mctsb_get_counters(mctsb_backend *b, mctsb_counters *out) {

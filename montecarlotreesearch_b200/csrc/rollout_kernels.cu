@@ -239,17 +239,21 @@ cudaError_t launch_quoridor_play(const mctsb_qstate *states, const int32_t *ids,
 }
 
 // ---------------------------------------------------------------------------------------------
-// Integer-issue peak: 8 independent chains per thread, each trip = 8 x (4 LOP3 + 4 IADD3) = 64
-// thread-level integer instructions on the ALU pipe, the mix the flood fill is made of.
-// ---------------------------------------------------------------------------------------------
+// Integer-issue peak probes.  8 independent dependency chains per thread, 8 steps per chain per trip = 64
+// thread-level integer instructions per trip, each one spelled as a volatile PTX statement so that the
+// count executed is exactly the count claimed (the compiler may neither fold nor split them).
+//   int_peak_kernel : LOP3 and integer ADD alternating — the instruction mix of the flood fill; ptxas is
+//                     free to place the adds on either pipe (IADD3 on the ALU pipe, IMAD.IADD on the FMA pipe)
+//   lop3_peak_kernel: LOP3 only — the ALU pipe's own ceiling; LOP3 has no second pipe to go to
+#define MC_LOP3(a) asm volatile("lop3.b32 %0, %0, %1, %2, 0x96;" : "+r"(a) : "r"(k1), "r"(k2));
+#define MC_ADD(a)  asm volatile("add.u32 %0, %0, %1;" : "+r"(a) : "r"(k2));
 __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, int iters) {
     uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t a0 = t, a1 = t ^ 0x9e3779b9u, a2 = t + 0x7f4a7c15u, a3 = ~t, a4 = t * 3u, a5 = t * 5u, a6 = t * 7u, a7 = t * 11u;
     uint32_t k1 = sink[0], k2 = sink[1];   // runtime values so nothing folds
+#pragma unroll 1
     for (int i = 0; i < iters; i++) {
-#define MC_CHAIN(a)                                                                      \
-        a = (a ^ k1) & (a | k2); a = a + k1 + k2; a = (a & k2) ^ (a | k1); a = a + k2 + 1u; \
-        a = (a ^ k2) | (a & k1); a = a + k1 + 3u; a = (a | k1) ^ (a & k2); a = a + k2 + k1;
+#define MC_CHAIN(a) MC_LOP3(a) MC_ADD(a) MC_LOP3(a) MC_ADD(a) MC_LOP3(a) MC_ADD(a) MC_LOP3(a) MC_ADD(a)
         MC_CHAIN(a0) MC_CHAIN(a1) MC_CHAIN(a2) MC_CHAIN(a3) MC_CHAIN(a4) MC_CHAIN(a5) MC_CHAIN(a6) MC_CHAIN(a7)
 #undef MC_CHAIN
     }
@@ -257,8 +261,29 @@ __global__ void __launch_bounds__(256) int_peak_kernel(uint32_t *sink, int iters
     if (r == 0x12345678u) sink[2] = r;    // practically never; keeps the chains alive
 }
 
+__global__ void __launch_bounds__(256) lop3_peak_kernel(uint32_t *sink, int iters) {
+    uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    uint32_t a0 = t, a1 = t ^ 0x9e3779b9u, a2 = t + 0x7f4a7c15u, a3 = ~t, a4 = t * 3u, a5 = t * 5u, a6 = t * 7u, a7 = t * 11u;
+    uint32_t k1 = sink[0], k2 = sink[1];
+#pragma unroll 1
+    for (int i = 0; i < iters; i++) {
+#define MC_CHAIN(a) MC_LOP3(a) MC_LOP3(a) MC_LOP3(a) MC_LOP3(a) MC_LOP3(a) MC_LOP3(a) MC_LOP3(a) MC_LOP3(a)
+        MC_CHAIN(a0) MC_CHAIN(a1) MC_CHAIN(a2) MC_CHAIN(a3) MC_CHAIN(a4) MC_CHAIN(a5) MC_CHAIN(a6) MC_CHAIN(a7)
+#undef MC_CHAIN
+    }
+    uint32_t r = a0 ^ a1 ^ a2 ^ a3 ^ a4 ^ a5 ^ a6 ^ a7;
+    if (r == 0x12345678u) sink[2] = r;
+}
+#undef MC_LOP3
+#undef MC_ADD
+
 cudaError_t launch_int_peak(uint32_t *sink, int blocks, int threads, int iters, cudaStream_t st) {
     int_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_lop3_peak(uint32_t *sink, int blocks, int threads, int iters, cudaStream_t st) {
+    lop3_peak_kernel<<<blocks, threads, 0, st>>>(sink, iters);
     return cudaGetLastError();
 }
 

@@ -39,6 +39,7 @@ cudaError_t launch_quoridor_play(const mctsb_qstate *states, const int32_t *ids,
 
 // integer-issue roofline denominator: independent LOP3/IADD3 chains on all SMs
 cudaError_t launch_int_peak(uint32_t *sink, int blocks, int threads, int iters, cudaStream_t st);
+cudaError_t launch_lop3_peak(uint32_t *sink, int blocks, int threads, int iters, cudaStream_t st);   // LOP3 only (ALU pipe)
 static const int INT_PEAK_OPS_PER_ITER = 64;   // thread-level integer ops per loop trip
 
 }  // namespace mctsb
