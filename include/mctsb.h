@@ -188,6 +188,8 @@ int mctsb_run_resident(mctsb_backend *b, int game, int policy, uint32_t rollouts
 int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms);
 /* The same with LOP3 only: the ALU pipe's own ceiling (the flood fill is LOP3-bound). */
 int mctsb_lop3_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms);
+/* Bench hygiene: overwrite a 256 MiB scratch buffer (twice the L2) on the backend stream and wait. */
+int mctsb_flush_l2(mctsb_backend *b);
 
 /* Counters of the last kernel launch(es): launches issued by this backend since creation, and
  * the executed-work counters the rollout kernel accumulates (flood-fill steps, plies). */

@@ -35,7 +35,7 @@ EXPORTS = [
     "mctsb_create", "mctsb_destroy", "mctsb_abi_version", "mctsb_strerror", "mctsb_last_cuda_error",
     "mctsb_device_count", "mctsb_submit", "mctsb_wait", "mctsb_rollout_batch", "mctsb_rollout_outcomes",
     "mctsb_rollout_replay", "mctsb_q_movegen", "mctsb_q_play", "mctsb_upload_states", "mctsb_run_resident",
-    "mctsb_int_issue_peak", "mctsb_lop3_peak", "mctsb_get_counters", "mctsb_leaf_sum_to_double",
+    "mctsb_int_issue_peak", "mctsb_lop3_peak", "mctsb_flush_l2", "mctsb_get_counters", "mctsb_leaf_sum_to_double",
 ]
 
 
@@ -84,6 +84,7 @@ def load_library():
     L.mctsb_run_resident.argtypes = [vp, i32, i32, u32, u64, C.POINTER(C.c_float)]
     L.mctsb_int_issue_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.mctsb_lop3_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
+    L.mctsb_flush_l2.argtypes = [vp]
     L.mctsb_get_counters.argtypes = [vp, vp]
     L.mctsb_leaf_sum_to_double.restype = C.c_double
     L.mctsb_leaf_sum_to_double.argtypes = [vp]
@@ -209,6 +210,9 @@ class RolloutBackend:
         ms = C.c_float(0)
         self._ck(self.lib.mctsb_lop3_peak(self.handle, C.byref(ops), C.byref(ms)))
         return ops.value, ms.value
+
+    def flush_l2(self):
+        self._ck(self.lib.mctsb_flush_l2(self.handle))
 
     def counters(self):
         c = np.zeros((), dtype=COUNTERS_DTYPE)

@@ -24,6 +24,7 @@ struct mctsb_backend {
     void *d_aux; size_t cap_aux;                     // bytes (movegen / play outputs)
     unsigned long long *d_counters;                  // [4]
     uint32_t *d_sink;                                // int-peak microbenchmark
+    void *d_flush; size_t flush_bytes;                // L2 flush scratch (bench hygiene)
     // pinned host staging
     void *h_in; size_t cap_h_in;
     void *h_out; size_t cap_h_out;
@@ -174,7 +175,7 @@ int mctsb_destroy(mctsb_backend *b) {
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_states); cudaFree(b->d_sums); cudaFree(b->d_outcomes); cudaFree(b->d_finals);
-    cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink);
+    cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink); cudaFree(b->d_flush);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->ev0) cudaEventDestroy(b->ev0);
@@ -392,6 +393,18 @@ int mctsb_int_issue_peak(mctsb_backend *b, double *thread_ops_per_sec, float *el
 
 int mctsb_lop3_peak(mctsb_backend *b, double *thread_ops_per_sec, float *elapsed_ms) {
     return run_peak_probe(b, true, thread_ops_per_sec, elapsed_ms);
+}
+
+int mctsb_flush_l2(mctsb_backend *b) {
+    if (!b) return MCTSB_ERR_BAD_ARG;
+    CK(cudaSetDevice(b->device));
+    if (!b->d_flush) {
+        b->flush_bytes = (size_t)256 << 20;                  // twice the 126 MB L2
+        CK(cudaMalloc(&b->d_flush, b->flush_bytes));
+    }
+    CK(cudaMemsetAsync(b->d_flush, 0xA5, b->flush_bytes, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return MCTSB_OK;
 }
 
 int mctsb_get_counters(mctsb_backend *b, mctsb_counters *out) {
