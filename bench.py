@@ -163,6 +163,11 @@ def main():
         run_reference_arm(args, rank, world)
         return
 
+    # stdout carries exactly one JSON line: anything native libraries print (NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import montecarlotreesearch_b200 as m
     from montecarlotreesearch_b200 import multi
 
@@ -304,7 +309,8 @@ def main():
         "mean_score": mean_score,
         "kernel_ms_per_step": dev_ms / args.steps,
     }
-    print(json.dumps(line), flush=True)
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
 
 
 if __name__ == "__main__":
