@@ -14,6 +14,7 @@ G, T = m.GAME_QUORIDOR, m.GAME_TICTACTOE
 
 @pytest.fixture(scope="module")
 def be():
+    m.build()          # no-op when libmctsb.so is newer than its sources
     b = m.RolloutBackend(0, m.DEFAULT_SEED)
     yield b
     b.close()
