@@ -1,3 +1,6 @@
+"""Developer tool: quick bit-exact check of the lockstep kernel body (one-lane host emulation) against the
+oracle.  Usage: PYTHONPATH=. python tests/hostemu/check_lockstep.py [n_rollouts].  The same checks run under
+pytest in tests/test_hostemu.py."""
 import numpy as np, time, sys
 from oracle.reflib import *
 from oracle.portlib import PortLib
