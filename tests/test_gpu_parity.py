@@ -250,3 +250,19 @@ def test_two_independent_kernels_agree(be, corpus):
     assert a.tobytes() == b.tobytes() and fa.tobytes() == fb.tobytes()
     a, fa = be.rollout_outcomes(G, m.POLICY_REF, m.quoridor_opening(), 4096, 99, finals=False)
     assert abs(a["score"].mean() - 0.65) < 0.03
+
+
+def test_long_paths_overflow_the_layer_budget(be, port):
+    """Maze positions whose shortest paths exceed the stored-layer budget (MCTSB_MAX_LAYERS = 24)."""
+    from tests.util import serpentine_state
+    states = np.array([serpentine_state(turn=0), serpentine_state(turn=1), serpentine_state(rows=(0, 2, 4, 7), turn=0)],
+                      dtype=m.QSTATE_DTYPE)
+    legal, info, ev = be.q_movegen(states)
+    bits = m.unpack_legal(legal)
+    out, fin = be.rollout_outcomes(G, m.POLICY_REF, states, 96, 4321)
+    for i, s in enumerate(states):
+        p = port.q_primitives(s)
+        assert p["sp_white"] > 24 and p["sp_black"] > 24
+        assert (bits[i] == p["legal"]).all() and info["sp_white"][i] == p["sp_white"] and info["sp_black"][i] == p["sp_black"]
+        exp, efin, _ = port.q_rollout_philox(s, m.DEFAULT_SEED, 4321 + 96 * i, 96, finals=True)
+        assert exp.tobytes() == out[96 * i: 96 * (i + 1)].tobytes() and efin.tobytes() == fin[96 * i: 96 * (i + 1)].tobytes()

@@ -111,3 +111,17 @@ def test_lockstep_body_vs_oracle_many_leaves(emu, port, corpus):
         assert exp.tobytes() == out[5 * j: 5 * j + 5].tobytes() and efin.tobytes() == fin[5 * j: 5 * j + 5].tobytes()
         acc, _ = port.leaf_sum(exp["score"])
         assert (int(acc["lo"]), int(acc["hi"]), int(acc["n"])) == (int(sums["lo"][j]), int(sums["hi"][j]), int(sums["n"][j]))
+
+
+def test_long_paths_overflow_the_layer_budget(emu, port):
+    """Shortest paths longer than MCTSB_MAX_LAYERS: the kernel falls back to measuring every wall."""
+    from tests.util import serpentine_state
+    for turn in (0, 1):
+        s = serpentine_state(turn=turn)
+        p = port.q_primitives(s)
+        assert p["sp_white"] > 24 and p["sp_black"] > 24
+        exp, efin, _ = port.q_rollout_philox(s, 5, 0, 64, finals=True)
+        out, fin, _, _ = emu.lockstep(s, 64, 5, 0)
+        assert exp.tobytes() == out.tobytes() and efin.tobytes() == fin.tobytes()
+        e = emu.q_primitives(s)
+        assert (e["legal"] == p["legal"]).all() and e["sp_white"] == p["sp_white"] and e["sp_black"] == p["sp_black"]

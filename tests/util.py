@@ -44,3 +44,18 @@ def golden(name):
     if name.endswith(".npy"):
         return np.load(path)
     return np.load(path)
+
+
+def serpentine_state(rows=(1, 3, 5, 6), wwalls=2, bwalls=2, turn=0):
+    """A maze: full-width horizontal barriers under the given rows with the gap alternating between column 0 and
+    column 8, so both shortest paths are far longer than the kernel's stored-layer budget (MCTSB_MAX_LAYERS)."""
+    from oracle.reflib import QSTATE_DTYPE
+    s = np.zeros((), dtype=QSTATE_DTYPE)
+    h = 0
+    for n, x in enumerate(rows):
+        for y in ((1, 3, 5, 7) if n % 2 == 0 else (0, 2, 4, 6)):
+            h |= 1 << (8 * x + y)
+    s["h_anchor"] = np.uint64(h)
+    s["wx"], s["wy"], s["bx"], s["by"] = 0, 4, 8, 4
+    s["wwalls"], s["bwalls"], s["turn"], s["move_counter"] = wwalls, bwalls, turn, 16
+    return s
