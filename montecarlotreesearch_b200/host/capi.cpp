@@ -120,6 +120,11 @@ void *mcts_host_session_create(int game, const void *packed_root, int policy, in
 
 void mcts_host_session_destroy(void *hs) { delete (HostSession *)hs; }
 
+void mcts_host_set_overlap(void *hs, int on) {
+    HostSession *h = (HostSession *)hs;
+    MCTS_batching b = h->tree->get_batching(); b.overlap = on != 0; h->tree->set_batching(b);
+}
+
 int mcts_host_grow(void *hs, int max_iter, double max_seconds, char *err, int err_cap) {
     try { ((HostSession *)hs)->tree->grow_tree(max_iter, max_seconds); return 0; }
     catch (const std::exception &e) { if (err && err_cap > 0) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; } return -1; }

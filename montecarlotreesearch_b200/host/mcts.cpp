@@ -216,6 +216,34 @@ void MCTS_tree::flush_leaves(vector<MCTS_node *> &leaves) {
     leaves.clear();
 }
 
+// Asynchronous flush: all leaves must belong to one backend game/policy (true for a game tree).
+bool MCTS_tree::submit_leaves(const vector<MCTS_node *> &leaves) {
+    if (leaves.empty()) return false;
+    const int game = leaves[0]->state->gpu_game_id(), policy = leaves[0]->state->gpu_policy_id();
+    if (game < 0) return false;
+    const size_t rec = game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate);
+    vector<unsigned char> packed(leaves.size() * rec);
+    for (size_t k = 0; k < leaves.size(); k++) {
+        if (leaves[k]->state->gpu_game_id() != game || leaves[k]->state->gpu_policy_id() != policy) return false;
+        if (!leaves[k]->state->gpu_pack(&packed[k * rec])) return false;
+    }
+    const uint32_t R = batching.rollouts_per_leaf;
+    get_backend()->submit(game, policy, packed.data(), (int)leaves.size(), R, next_rollout_ids((uint64_t)R * leaves.size()));
+    flushes++; rollouts_played += (uint64_t)R * leaves.size();
+    return true;
+}
+
+void MCTS_tree::collect_leaves(vector<MCTS_node *> &leaves) {
+    vector<double> sums(leaves.size(), 0.0);
+    get_backend()->wait(sums.data());
+    const uint32_t R = batching.rollouts_per_leaf;
+    for (size_t k = 0; k < leaves.size(); k++) {
+        leaves[k]->add_virtual(-(int)R);
+        leaves[k]->backpropagate(sums[k], (int)R);
+    }
+    leaves.clear();
+}
+
 // reference mcts.cpp:182-210: up to max_iter Selection+Expansion+Simulation+Backpropagation rounds,
 // stopped early when difftime(now, start) > max_time (whole seconds, strict).
 void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
@@ -237,8 +265,8 @@ void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
             }
         }
     } else {
-        vector<MCTS_node *> leaves;
-        while (i < max_iter) {
+        vector<MCTS_node *> leaves, inflight;
+        while (i < max_iter || !inflight.empty()) {
             for (uint32_t k = 0; k < K && i < max_iter; k++, i++) {
                 MCTS_node *node = select();
                 MCTS_node *leaf = node->is_terminal() ? node : node->expand_no_rollout();
@@ -246,11 +274,16 @@ void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
                 leaf->add_virtual((int)batching.rollouts_per_leaf);   // keep the next selection away from this path
                 leaves.push_back(leaf);
             }
-            flush_leaves(leaves);
+            if (!inflight.empty()) collect_leaves(inflight);          // the GPU ran this flush while the host selected
+            if (!leaves.empty()) {
+                if (batching.overlap && submit_leaves(leaves)) inflight.swap(leaves);
+                else flush_leaves(leaves);
+            }
             time(&now_t);
             dt = difftime(now_t, start_t);
             if (dt > max_time_in_seconds) {
                 if (g_verbose) cout << "Early stopping: Made " << i << " iterations in " << dt << " seconds." << endl;
+                if (!inflight.empty()) collect_leaves(inflight);
                 break;
             }
         }

@@ -25,6 +25,9 @@ using namespace std;
 struct MCTS_batching {
     uint32_t rollouts_per_leaf = 4;
     uint32_t leaves_per_flush = 1;
+    // leaves_per_flush > 1 only: select the next batch of leaves on the host while the previous flush is
+    // still running on the GPU (its leaves keep their virtual loss until the results arrive)
+    bool overlap = false;
 };
 
 class MCTS_tree;
@@ -74,6 +77,8 @@ class MCTS_tree {
     uint64_t flushes, rollouts_played;
     RolloutBackend *get_backend();
     void flush_leaves(vector<MCTS_node *> &leaves);
+    bool submit_leaves(const vector<MCTS_node *> &leaves);      // asynchronous half of flush_leaves; false = not batchable
+    void collect_leaves(vector<MCTS_node *> &leaves);           // wait + backpropagate
 public:
     MCTS_tree(MCTS_state *starting_state);
     MCTS_tree(MCTS_state *starting_state, RolloutBackend *backend, MCTS_batching batching);

@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--rollouts-per-leaf", type=int, default=4096)
     ap.add_argument("--leaves-per-flush", type=int, default=16)
     ap.add_argument("--max-moves", type=int, default=120)
+    ap.add_argument("--overlap", action="store_true", help="select the next batch of leaves while the previous flush runs on the GPU")
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
 
@@ -52,6 +53,8 @@ def main():
     # different Philox key per rank (root-parallel trees must be independent), same root
     tree = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
                    leaves_per_flush=args.leaves_per_flush, device=local_rank, seed=args.seed + rank)
+    if args.overlap:
+        tree.set_overlap(True)
     moves, t_grow, t_merge = [], 0.0, 0.0
     t0 = time.perf_counter()
     terminal = False

@@ -20,6 +20,7 @@ def load():
     L.mcts_host_session_create.restype = vp
     L.mcts_host_session_create.argtypes = [C.c_int, vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, vp, vp, C.c_char_p, C.c_int]
     L.mcts_host_session_destroy.argtypes = [vp]
+    L.mcts_host_set_overlap.argtypes = [vp, C.c_int]
     L.mcts_host_grow.argtypes = [vp, C.c_int, C.c_double, C.c_char_p, C.c_int]
     L.mcts_host_root_stats.argtypes = [vp, vp, vp, C.c_int]
     L.mcts_host_best_move.argtypes = [vp]
@@ -50,6 +51,9 @@ class Session:
         if self.h:
             self.lib.mcts_host_session_destroy(self.h)
             self.h = None
+
+    def set_overlap(self, on=True):
+        self.lib.mcts_host_set_overlap(self.h, int(on))
 
     def grow(self, iters, seconds=1e9):
         err = C.create_string_buffer(512)

@@ -124,6 +124,21 @@ def test_leaf_batching_with_virtual_loss(host, port):
     t.close()
 
 
+def test_overlapped_flushes(host, port):
+    """Selection of the next batch overlaps the previous flush: same bookkeeping, one flush in flight."""
+    log = []
+    t = Session(host, m.GAME_TICTACTOE, np.zeros((), dtype=m.TSTATE_DTYPE), rollouts_per_leaf=8, leaves_per_flush=16,
+                callback=oracle_backend(port, log=log))
+    t.set_overlap(True)
+    t.grow(1000)                       # 62 full flushes + one of 8 leaves
+    r = t.root_stats()
+    assert r["sims"] == 1000 * 8 and r["size"] == 1000
+    assert len(log) == 63 and log[-1][1] == 8 and t.counters() == (63, 8000)
+    assert r["children"][:, 1].sum() == 8000
+    assert 0.5 < r["score"] / r["sims"] < 0.9
+    t.close()
+
+
 def test_quoridor_tree_small(host, port, corpus):
     t = Session(host, m.GAME_QUORIDOR, corpus[4200], rollouts_per_leaf=2, callback=oracle_backend(port))
     t.grow(40)
