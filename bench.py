@@ -291,9 +291,11 @@ def main():
         "metric": METRIC if not secondary else "%s_%s_rollouts_per_sec" % (args.game, args.policy), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": ("configs[1]: Quoridor 9x9 opening position, %d independent REF-policy rollouts per GPU per step" % n) if args.workload == "opening"
-                   else ("configs[2]: mid-game corpus, 4096 states x %d REF-policy rollouts per GPU per step" % per_leaf),
-                   "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)",
+        "config": {"workload": ("Tic-Tac-Toe empty board, %d independent rollouts per GPU per step" % n) if args.game != "quoridor"
+                   else ("configs[1]: Quoridor 9x9 opening position, %d independent %s-policy rollouts per GPU per step" % (n, args.policy.upper())) if args.workload == "opening"
+                   else ("configs[2]: mid-game corpus, 4096 states x %d %s-policy rollouts per GPU per step" % (per_leaf, args.policy.upper())),
+                   "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)" if not secondary
+                             else "UNI (uniformly random legal move per ply, to the end of the game)" if args.game == "quoridor" else "reference TicTacToe_state::rollout",
                    "rollouts_per_step_per_gpu": n, "leaves": n_leaves, "seed": hex(m.DEFAULT_SEED),
                    "l2": "flushed between timed steps (256 MiB memset, outside the timed kernel); inputs are 32 B per leaf and rollout ids differ every step"},
         "roofline": {"bound": "sm_int_issue", "achieved": None if secondary else achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",

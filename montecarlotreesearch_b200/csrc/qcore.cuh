@@ -667,15 +667,30 @@ MC_HD double q_rollout_ref(QState &s, Draws &d, Layers &ls, int &plies, int &kin
 // as the 12-bit step mask plus one 64-bit anchor mask per wall orientation.  Thread-serial version
 // (host class, UNI policy); the movegen kernel spreads the 128 wall candidates over a warp.
 // ------------------------------------------------------------------------------------------------
-MC_HD void q_legal_parts(const QState &s, uint32_t &steps, uint64_t &legal_h, uint64_t &legal_v, QWork *wk) {
+// Exact pruning of the path test: a wall can only close a player in if it removes an edge of that
+// player's shortest paths in a way that changes the distance — anchors outside q_cut_masks(player) leave
+// sp(player) unchanged, hence finite.  Two layer searches + traces replace most of the ~200 flood fills
+// of a mid-game position; the surviving candidates are flood-filled for the player(s) concerned only.
+template <class Layers>
+MC_HD void q_legal_parts(const QState &s, uint32_t &steps, uint64_t &legal_h, uint64_t &legal_v, Layers &ls, QWork *wk) {
     steps = q_step_mask(s);
     uint64_t lh, lv;
     q_cheap_wall_masks(s, lh, lv);
-    legal_h = legal_v = 0;
-    for (int a = 0; a < 64; a++) {
-        if (((lh >> a) & 1ull) && q_wall_keeps_paths(s, 2 * a, wk)) legal_h |= 1ull << a;
-        if (((lv >> a) & 1ull) && q_wall_keeps_paths(s, 2 * a + 1, wk)) legal_v |= 1ull << a;
+    legal_h = lh; legal_v = lv;
+    if ((lh | lv) == 0ull) return;
+    const QCut cw = q_cut_masks(s, 0, ls, wk), cb = q_cut_masks(s, 1, ls, wk);
+    uint64_t th = lh & (cw.h | cb.h), tv = lv & (cw.v | cb.v);
+    for (int k = q_mask_first(th, tv); k >= 0; q_mask_clear(th, tv, k), k = q_mask_first(th, tv)) {
+        bool ok = true;
+        if (q_mask_has(cw.h, cw.v, k)) ok = q_sp_with_wall(s, 0, k, wk) >= 0;
+        if (ok && q_mask_has(cb.h, cb.v, k)) ok = q_sp_with_wall(s, 1, k, wk) >= 0;
+        if (!ok) { if (k & 1) legal_v &= ~(1ull << (k >> 1)); else legal_h &= ~(1ull << (k >> 1)); }
     }
+}
+
+MC_HD void q_legal_parts(const QState &s, uint32_t &steps, uint64_t &legal_h, uint64_t &legal_v, QWork *wk) {
+    LocalLayers ls;
+    q_legal_parts(s, steps, legal_h, legal_v, ls, wk);
 }
 
 // the same set as a 209-bit mask over canonical move ids (include/mctsb.h)
@@ -707,15 +722,15 @@ MC_HD int q_nth_move(const QState &s, uint32_t steps, uint64_t legal_h, uint64_t
 
 // UNI policy (no reference function; oracle = loop over the reference's public API): uniformly
 // random legal move per ply, idx = mulhi(draw, |L|), ply cap MCTSB_UNI_MAX_PLIES scoring 0.5.
-template <class Draws>
-MC_HD double q_rollout_uni(QState &s, Draws &d, int &plies, int &kind, QWork *wk) {
+template <class Draws, class Layers>
+MC_HD double q_rollout_uni(QState &s, Draws &d, Layers &ls, int &plies, int &kind, QWork *wk) {
     plies = 0; kind = 4;
     for (;;) {
         int w = q_winner(s);
         if (w) { kind = w == 1 ? 0 : 1; return w == 1 ? 1.0 : 0.0; }
         if (plies >= MCTSB_UNI_MAX_PLIES) return 0.5;
         uint32_t steps; uint64_t lh, lv;
-        q_legal_parts(s, steps, lh, lv, wk);
+        q_legal_parts(s, steps, lh, lv, ls, wk);
         int n = popc32(steps) + popc64(lh) + popc64(lv);
         if (n == 0) { kind = 3; return 0.5; }
         int mv = q_nth_move(s, steps, lh, lv, (int)mulhi_u32(d.next(), (uint32_t)n));

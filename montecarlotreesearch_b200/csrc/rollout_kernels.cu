@@ -106,11 +106,11 @@ __global__ void __launch_bounds__(kThreads) quoridor_rollout_kernel(RolloutParam
         q_unpack(s, packed);
         if (REPLAY) {
             StreamDraws d; d.init(p.streams + (size_t)r * p.stream_stride, p.stream_len);
-            score = POLICY == 1 ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+            score = POLICY == 1 ? q_rollout_uni(s, d, pool, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
             draws = d.consumed();
         } else {
             PhiloxDraws d; d.init(p.seed, p.first_rollout_id + r);
-            score = POLICY == 1 ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+            score = POLICY == 1 ? q_rollout_uni(s, d, pool, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
             draws = d.consumed();
         }
         if (p.outcomes) store_outcome(p.outcomes, r, score, plies, kind, draws);

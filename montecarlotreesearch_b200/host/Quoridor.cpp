@@ -110,10 +110,13 @@ queue<MCTS_move *> *Quoridor_state::generate_all_moves() const {
     char p = whose_turn();
     uint32_t steps; uint64_t lh, lv;
     q_legal_parts(s, steps, lh, lv, nullptr);
-    int n = popc32(steps) + popc64(lh) + popc64(lv);
-    for (int i = 0; i < n; i++) {
-        int mv = q_nth_move(s, steps, lh, lv, i);
-        Q->push(Quoridor_move::from_canonical_id(q_move_to_id(mv), p));
+    // generate_all_moves order (Quoridor.cpp:594-616): steps in reversed candidate order, then anchors
+    // row-major with the horizontal wall before the vertical one
+    for (int i = 11; i >= 0; i--)
+        if ((steps >> i) & 1u) Q->push(Quoridor_move::from_canonical_id(q_move_to_id(s.cell[s.turn] + q_step_delta(i)), p));
+    for (int a = 0; a < 64; a++) {
+        if ((lh >> a) & 1ull) Q->push(Quoridor_move::from_canonical_id(q_move_to_id(128 + 2 * a), p));
+        if ((lv >> a) & 1ull) Q->push(Quoridor_move::from_canonical_id(q_move_to_id(128 + 2 * a + 1), p));
     }
     return Q;
 }

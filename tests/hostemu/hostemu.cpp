@@ -44,7 +44,7 @@ int emu_q_rollout_streams(const mctsb_qstate *states, int policy, int n, const u
         QState s; q_unpack(s, states[i]);
         StreamDraws d; d.init(streams + (size_t)i * stride, len);
         int plies = 0, kind = 0; QWork wk = {0, 0, 0};
-        double r = policy == MCTSB_POLICY_UNI ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+        double r = policy == MCTSB_POLICY_UNI ? q_rollout_uni(s, d, pool, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
         memset(out + i, 0, sizeof *out);
         out[i].score = r; out[i].plies = (uint16_t)plies; out[i].kind = (uint8_t)kind; out[i].draws = d.consumed();
         if (finals) q_pack(s, finals[i]);
@@ -60,7 +60,7 @@ int emu_q_rollout_philox(const mctsb_qstate *state, int policy, uint64_t seed, u
         QState s; q_unpack(s, *state);
         PhiloxDraws d; d.init(seed, first_id + i);
         int plies = 0, kind = 0; QWork wk = {0, 0, 0};
-        double r = policy == MCTSB_POLICY_UNI ? q_rollout_uni(s, d, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
+        double r = policy == MCTSB_POLICY_UNI ? q_rollout_uni(s, d, pool, plies, kind, &wk) : q_rollout_ref(s, d, pool, plies, kind, &wk);
         memset(out + i, 0, sizeof *out);
         out[i].score = r; out[i].plies = (uint16_t)plies; out[i].kind = (uint8_t)kind; out[i].draws = d.consumed();
         if (finals) q_pack(s, finals[i]);
