@@ -191,6 +191,42 @@ MC_HD B81 q_flood_step(B81 r, B81 oS, B81 oE) {
 }
 #endif
 
+// The same expansion with the edge boards prepared once per search: oS9 = oS << 9 and oE1 = oE << 1 mask
+// the shifted board AFTER the shift ((r & m) << k == (r << k) & (m << k)), so every mask folds into the
+// 3-input ORs that merge the word carries: 12 IMAD + 16 LOP3, and the multiplies read r directly.
+struct QFloodMasks { B81 oS, oE, oS9, oE1; };
+
+MC_HD QFloodMasks q_flood_masks(B81 oS, B81 oE) {
+    QFloodMasks m; m.oS = oS; m.oE = oE; m.oS9 = shl<9>(oS); m.oE1 = shl<1>(oE);
+    return m;
+}
+
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ B81 q_flood_step(B81 r, const QFloodMasks &m) {
+    const uint32_t L9 = mc_shift_mul[0], L1 = mc_shift_mul[1], R9 = mc_shift_mul[2], R1 = mc_shift_mul[3];
+    uint32_t Sa_lo, Sa_hi, Sb_lo, Sb_hi, Ea_lo, Ea_hi, Eb_lo, Eb_hi;
+    mc_mulwide(r.a, L9, Sa_lo, Sa_hi); mc_mulwide(r.b, L9, Sb_lo, Sb_hi);
+    mc_mulwide(r.a, L1, Ea_lo, Ea_hi); mc_mulwide(r.b, L1, Eb_lo, Eb_hi);
+    uint32_t Sc = r.c * L9, Ec = r.c * L1;
+    uint32_t Na_lo, Na_hi, Nb_lo, Nb_hi, Nc_lo, Nc_hi, Wa_lo, Wa_hi, Wb_lo, Wb_hi, Wc_lo, Wc_hi;
+    mc_mulwide(r.a, R9, Na_lo, Na_hi); mc_mulwide(r.b, R9, Nb_lo, Nb_hi); mc_mulwide(r.c, R9, Nc_lo, Nc_hi);
+    mc_mulwide(r.a, R1, Wa_lo, Wa_hi); mc_mulwide(r.b, R1, Wb_lo, Wb_hi); mc_mulwide(r.c, R1, Wc_lo, Wc_hi);
+    (void)Na_lo; (void)Wa_lo;
+    B81 n;
+    n.a = r.a | (Sa_lo & m.oS9.a) | (Ea_lo & m.oE1.a) | ((Na_hi | Nb_lo) & m.oS.a) | ((Wa_hi | Wb_lo) & m.oE.a);
+    n.b = r.b | ((Sb_lo | Sa_hi) & m.oS9.b) | ((Eb_lo | Ea_hi) & m.oE1.b) | ((Nb_hi | Nc_lo) & m.oS.b) | ((Wb_hi | Wc_lo) & m.oE.b);
+    n.c = r.c | ((Sc | Sb_hi) & m.oS9.c) | ((Ec | Eb_hi) & m.oE1.c) | (Nc_hi & m.oS.c) | (Wc_hi & m.oE.c);
+    return n;
+}
+#else
+MC_HD B81 q_flood_step(B81 r, const QFloodMasks &m) {
+    B81 south = shl<9>(r) & m.oS9, north = shr<9>(r) & m.oS, east = shl<1>(r) & m.oE1, west = shr<1>(r) & m.oE;
+    return b81(r.a | south.a | north.a | east.a | west.a,
+               r.b | south.b | north.b | east.b | west.b,
+               r.c | south.c | north.c | east.c | west.c);
+}
+#endif
+
 // Shortest path length from `start` to `player`'s goal row ignoring pawns, -1 if walled off:
 // get_shortest_path / calculate_dists_from(stop_at_goal=true), Quoridor.cpp:46-106,161-169.
 MC_HD int q_flood_dist(B81 oS, B81 oE, int start, int player, QWork *wk) {

@@ -4,15 +4,18 @@
 
 namespace mctsb {
 
+#ifndef LS_BLOCKS_PER_SM
+#define LS_BLOCKS_PER_SM 5
+#endif
+
 template <bool REPLAY>
-__global__ void __launch_bounds__(LS_THREADS) quoridor_lockstep_kernel(RolloutParams p, unsigned long long *work_counter) {
+__global__ void __launch_bounds__(LS_THREADS, LS_BLOCKS_PER_SM) quoridor_lockstep_kernel(RolloutParams p, unsigned long long *work_counter) {
     extern __shared__ uint32_t smem[];
     lockstep_body<REPLAY>(p, work_counter, smem);
 }
 
 static constexpr size_t LS_SMEM = (size_t)MCTSB_MAX_LAYERS * 3 * LS_THREADS * sizeof(uint32_t)      // layers
-                                  + (size_t)LS_THREADS * sizeof(unsigned long long)                  // best slots
-                                  + (size_t)(LS_THREADS / 32) * LS_QCAP * sizeof(uint32_t);           // task queues
+                                  + (size_t)LS_THREADS * sizeof(unsigned long long);                 // best slots
 
 cudaError_t launch_quoridor_lockstep(const RolloutParams &p, bool replay, unsigned long long *work_counter, cudaStream_t st) {
     if (p.n_rollouts == 0) return cudaSuccess;

@@ -88,8 +88,14 @@ static constexpr int LS_THREADS = 128;
 static constexpr int LS_SHARE = 32;                     // candidates one lane may queue per batch
 static constexpr int LS_QCAP = 32 * LS_SHARE;           // queue entries per warp
 
-// per-warp shared scratch of the candidate phase
-struct WarpBuf { uint32_t *queue; unsigned long long *best; };
+// per-warp shared scratch of the candidate phase.  The task queue lives in the warp's own columns of the
+// layer area (rows of 32 entries, row stride LS_THREADS words): the layers are dead once the trace is done
+// and are rebuilt at the top of the next ply, and no other warp ever touches these columns.
+struct WarpBuf {
+    uint32_t *qbase; unsigned long long *best;
+    LS_DEV uint32_t &queue(int i) const { return qbase[(i >> 5) * LS_THREADS + (i & 31)]; }
+};
+static_assert(LS_QCAP / 32 <= 3 * MCTSB_MAX_LAYERS, "the task queue must fit in the warp's share of the layer area");
 
 // layers of one lane live in shared memory, word-interleaved across the block: no bank conflicts
 struct SmemLayers {
@@ -193,24 +199,23 @@ template <> struct LaneDraws<true> {
 // Flood fills of all lanes that have one pending, in one converged loop (a pawn-rooted search
 // with early exit, as q_flood_dist).  `go` lanes search from `start` to `player`'s goal row.
 LS_DEV int warp_flood(bool go, B81 oS, B81 oE, int start, int player, QWork &wk) {
+    const QFloodMasks fm = q_flood_masks(oS, oE);
     B81 r = b81_bit(go ? start : 0);
     const uint32_t ga = player ? MCTSB_GOAL_B_A : 0u, gc = player ? 0u : MCTSB_GOAL_W_C;
-    int dist = -1, d = 0;
-    bool busy = go;
-    if (busy && ((r.a & ga) | (r.c & gc))) { dist = 0; busy = false; }
+    bool busy = go && ((r.a & ga) | (r.c & gc)) == 0u;
+    uint32_t d = 0;                                        // expansions this lane made while still searching
     if (go) wk.flood_queries++;
     LS_UNROLL2
     while (LS_ANY(busy)) {
-        const B81 n = q_flood_step(r, oS, oE);
-        d++;
+        const B81 n = q_flood_step(r, fm);
         const bool hit = ((n.a & ga) | (n.c & gc)) != 0u;
         const bool stuck = ((n.a ^ r.a) | (n.b ^ r.b) | (n.c ^ r.c)) == 0u;
-        wk.flood_steps += busy ? 1u : 0u;
-        dist = (busy && hit) ? d : dist;
+        d += busy ? 1u : 0u;
         busy = busy && !hit && !stuck;
-        r = n;                                         // finished lanes keep stepping; their result is already taken
+        r = n;                                         // finished lanes keep stepping: a reached goal row stays reached
     }
-    return dist;
+    wk.flood_steps += d;
+    return (go && ((r.a & ga) | (r.c & gc)) != 0u) ? (int)d : -1;
 }
 
 // step-target distance fields: 8 bits per candidate slot, three words
@@ -229,10 +234,10 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
     const int lane = LS_TID & 31, warp = LS_TID >> 5;
     SmemLayers ls; ls.base = smem + LS_TID;
     WarpBuf wb;
-    {   // layout: [layers][best slots: 32 x u64 per warp][queues: LS_QCAP x u32 per warp]
+    {   // layout: [layers, overlaid by the task queues during P5][best slots: 32 x u64 per warp]
         uint32_t *after = smem + MCTSB_MAX_LAYERS * 3 * LS_THREADS;
         wb.best = reinterpret_cast<unsigned long long *>(after) + 32 * warp;
-        wb.queue = after + 2 * LS_THREADS + LS_QCAP * warp;
+        wb.qbase = smem + 32 * warp;
     }
 
     QState s; LaneDraws<REPLAY> d;
@@ -300,6 +305,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             const B81 goal_b = qb ? b81(MCTSB_GOAL_B_A, 0u, 0u) : b81(0u, 0u, MCTSB_GOAL_W_C);
             const B81 pawn_a = b81_bit(cell_a), pawn_b = b81_bit(cell_b);
             B81 ra = goal_a, rb = goal_b;
+            const QFloodMasks fm = q_flood_masks(s.openS, s.openE);
             B81 rb1 = b81(0u, 0u, 0u), rb2 = b81(0u, 0u, 0u);  // search B one and two expansions ago
             bool busy_a = playing || capped, busy_b = busy_a;
             if (busy_a) {
@@ -312,7 +318,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             while (LS_ANY(busy_a || busy_b)) {
                 j++;
                 if (busy_a) {
-                    B81 grown = q_flood_step(ra, s.openS, s.openE);
+                    B81 grown = q_flood_step(ra, fm);
                     B81 layer = andn(grown, ra);
                     wk.flood_steps++;
                     if (want_cut && !overflow_a) { if (j < MCTSB_MAX_LAYERS) ls.put(j, layer); else overflow_a = true; }
@@ -321,7 +327,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                     else if (!b81_any(layer)) busy_a = false;  // walled off: sp stays -1 (never in a legal position)
                 }
                 if (busy_b) {
-                    B81 grown = q_flood_step(rb, s.openS, s.openE);
+                    B81 grown = q_flood_step(rb, fm);
                     wk.flood_steps++;
                     if (b81_any(grown & pawn_b)) { sp_b = j; busy_b = false; }
                     else if (b81_eq(grown, rb)) busy_b = false;    // exhausted
@@ -332,7 +338,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             // Quoridor.cpp:476-497).  A target is one or two moves from the pawn, so its distance is within
             // two of the pawn's: rb2, rb1, rb and one more expansion are the cells within sp-2 .. sp+1.
             if (LS_ANY(steps != 0u)) {
-                const B81 rb_next = q_flood_step(rb, s.openS, s.openE);
+                const B81 rb_next = q_flood_step(rb, fm);
                 LS_UNROLL1
                 for (uint32_t m = steps; LS_ANY(m != 0u); m &= m - 1u) {
                     if (m) {
@@ -416,6 +422,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             const uint32_t pk_sp = (uint32_t)(sp_e & 0xff) | ((uint32_t)(sp_p & 0xff) << 8) | ((uint32_t)n_pool << 16) | ((uint32_t)j0 << 24);
             unsigned long long *slot = wb.best + lane;
             *slot = 0ull;
+            LS_SYNCWARP();                                     // every lane is done reading its layers: the queue may overwrite them
             LS_DBG(if (playing) g_dbg_pend[mode][popc64(pend_h) + popc64(pend_v)]++;)
             LS_UNROLL1
             while (LS_ANY((pend_h | pend_v) != 0ull || head_k >= 0)) {
@@ -430,7 +437,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 for (int o = 1; o < LS_WARP; o <<= 1) { int t = LS_SHFL_UP(off, o); if (lane >= o) off += t; }
                 const int total = LS_SHFL(off, LS_WARP - 1);
                 off -= mine;
-                if (head_k >= 0) wb.queue[off] = (uint32_t)lane | ((uint32_t)head_k << 5);
+                if (head_k >= 0) wb.queue(off) = (uint32_t)lane | ((uint32_t)head_k << 5);
                 {   // two independent bit iterators per trip: one FLO + one LOP per candidate
                     uint32_t ch = (uint32_t)pend_h, cv = (uint32_t)pend_v;
                     int wh = 0, wv = 0;
@@ -440,13 +447,13 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                             if (ch == 0u) { wh = 1; ch = (uint32_t)(pend_h >> 32); }
                             const int bpos = ctz32(ch);
                             ch &= ch - 1u;
-                            wb.queue[off + i] = (uint32_t)lane | ((uint32_t)(2 * (32 * wh + bpos)) << 5);
+                            wb.queue(off + i) = (uint32_t)lane | ((uint32_t)(2 * (32 * wh + bpos)) << 5);
                         }
                         if (i < mv) {
                             if (cv == 0u) { wv = 1; cv = (uint32_t)(pend_v >> 32); }
                             const int bpos = ctz32(cv);
                             cv &= cv - 1u;
-                            wb.queue[off + mh + i] = (uint32_t)lane | ((uint32_t)(2 * (32 * wv + bpos) + 1) << 5);
+                            wb.queue(off + mh + i) = (uint32_t)lane | ((uint32_t)(2 * (32 * wv + bpos) + 1) << 5);
                         }
                     }
                     if (head_k < 0) {                          // the unsent remainder stays pending
@@ -465,7 +472,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 for (int t0 = 0; t0 < total; t0 += LS_WARP) {
                     const int t = t0 + lane;
                     const bool valid = t < total;
-                    const uint32_t ent = valid ? wb.queue[t] : 0u;
+                    const uint32_t ent = valid ? wb.queue(t) : 0u;
                     const int owner = (int)(ent & 31u), k = (int)((ent >> 5) & 127u);
                     B81 oS = b81(LS_SHFL(s.openS.a, owner), LS_SHFL(s.openS.b, owner), LS_SHFL(s.openS.c, owner));
                     B81 oE = b81(LS_SHFL(s.openE.a, owner), LS_SHFL(s.openE.b, owner), LS_SHFL(s.openE.c, owner));
@@ -482,7 +489,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                     const bool pass = valid && d1 >= 0 && (o_mode == 3 || d1 - o_sp_e > 0);
                     const unsigned bal = LS_BALLOT(pass);
                     LS_SYNCWARP();
-                    if (pass) wb.queue[passed + LS_POPC(bal & ((1u << lane) - 1u))] = (ent & 0xfffu) | ((uint32_t)d1 << 12);
+                    if (pass) wb.queue(passed + LS_POPC(bal & ((1u << lane) - 1u))) = (ent & 0xfffu) | ((uint32_t)d1 << 12);
                     passed += LS_POPC(bal);
                 }
                 LS_SYNCWARP();
@@ -492,7 +499,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 for (int t0 = 0; t0 < passed; t0 += LS_WARP) {
                     const int t = t0 + lane;
                     const bool valid = t < passed;
-                    const uint32_t ent = valid ? wb.queue[t] : 0u;
+                    const uint32_t ent = valid ? wb.queue(t) : 0u;
                     const int owner = (int)(ent & 31u), k = (int)((ent >> 5) & 127u), d1 = (int)(ent >> 12);
                     B81 oS = b81(LS_SHFL(s.openS.a, owner), LS_SHFL(s.openS.b, owner), LS_SHFL(s.openS.c, owner));
                     B81 oE = b81(LS_SHFL(s.openE.a, owner), LS_SHFL(s.openE.b, owner), LS_SHFL(s.openE.c, owner));

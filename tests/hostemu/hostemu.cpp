@@ -105,7 +105,7 @@ int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t 
     unsigned long long ctr[4] = {0, 0, 0, 0};
     p.counters = ctr;
     if (sums) memset(sums, 0, sizeof(mctsb_leaf_sum) * (size_t)n_leaves);
-    std::vector<uint32_t> smem((size_t)MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS + (LS_THREADS / 32) * LS_QCAP + 64);
+    std::vector<uint32_t> smem((size_t)MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS + 64);
     unsigned long long work = 0;
     if (streams) lockstep_body<true>(p, &work, smem.data());
     else lockstep_body<false>(p, &work, smem.data());
