@@ -429,8 +429,8 @@ MC_HD bool q_force_playwall(QState &s, QWork *wk) {
 //      pawn is reached (d = sp(q));
 //   2. trace from the pawn down the layers: A_d = {pawn}, A_k = neighbours(A_{k+1}) in L_k; the edges
 //      used are exactly the edges on shortest paths (stored at the upper / left cell of the edge);
-//   3. fold the edge boards into anchor masks: cut_h / cut_v bit a <=> the horizontal / vertical wall
-//      anchored at a may change the distance (see q_trace_to_anchors for the exact rule).
+//   3. while tracing, flag the wall anchors that may change the distance (see QTrace for the exact rule);
+//      cut_h / cut_v bit a <=> the horizontal / vertical wall anchored at a must be measured.
 // m not in cut  =>  sp(q, m) == sp(q) exactly; m in cut => run the flood fill as before.
 // ------------------------------------------------------------------------------------------------
 #define MCTSB_MAX_LAYERS 24          // deeper searches fall back to "every wall may cut" (still exact)
@@ -450,42 +450,62 @@ MC_HD uint32_t b81_row(B81 v, int x) {
     return r & 0x1ffu;
 }
 
-// Trace state.  Every step walks the shortest-path cells one layer down and files the edges it uses:
-// a layer transition crossed by exactly ONE edge is a bottleneck (every shortest path uses it: removing
-// it lengthens the path for sure); edges of transitions with several edges are "multi" edges.
-struct QTrace { B81 A, S1, E1, Sm, Em; };   // frontier; south / east edges: single (bottleneck) and multi
+// Trace state.  Every step walks the shortest-path cells one layer down (a "transition") and decides
+// which wall anchors may change the distance.  A wall removes two parallel neighbouring edges.  With
+// T_j = the shortest-path cells of layer j (every one of them lies on a complete shortest path):
+//   * an edge that is alone in its transition is a bottleneck: every wall over it changes the distance;
+//   * a wall over ONE edge of a transition with several edges changes nothing;
+//   * a wall over two edges of the same transition, or of transitions that are not neighbours, is kept
+//     as "may change" (rare; measured by a flood fill);
+//   * a wall over edge e of transition (j+1 -> j) and edge f of (j -> j-1) changes the distance iff every
+//     cell v of T_j has in(v) = {e} or out(v) = {f}; at most one cell can have either, so this needs
+//     |T_j| = 2.  When T_j has any other size the wall changes nothing — that alone removes two thirds
+//     of the candidates the coarser rule "two multi edges" used to send to a flood fill.
+// FS / FE collect the flagged anchors as cell boards (anchor (x,y) at cell 9x+y: the wall covers the
+// south edges of cells c, c+1, resp. the east edges of cells c, c+9).
+struct QTrace {
+    B81 A;                 // T_j, the frontier
+    B81 FS, FE;            // flagged horizontal / vertical anchors
+    B81 SmOld, EmOld;      // multi edges of the transitions before the previous one
+    B81 SmPrev, EmPrev;    // multi edges of the previous transition
+};
 
 MC_HD void q_trace_init(QTrace &t, B81 pawn) {
-    t.A = pawn; t.S1 = t.E1 = t.Sm = t.Em = b81(0u, 0u, 0u);
+    t.A = pawn;
+    t.FS = t.FE = t.SmOld = t.EmOld = t.SmPrev = t.EmPrev = b81(0u, 0u, 0u);
 }
+
+MC_HD B81 b81_sel(bool c, B81 v) { uint32_t m = c ? 0xffffffffu : 0u; return b81(v.a & m, v.b & m, v.c & m); }
 
 MC_HD void q_trace_step(QTrace &t, B81 L, B81 oS, B81 oE) {
     B81 sS = t.A & oS & shr<9>(L);            // u in A steps south into L: edge stored at u
     B81 tN = shr<9>(t.A) & oS & L;            // u in A steps north to v = u-9 in L: edge stored at v
     B81 sE = t.A & oE & shr<1>(L);
     B81 tW = shr<1>(t.A) & oE & L;
-    B81 es = sS | tN, ee = sE | tW;
-    int cnt = popc32(es.a) + popc32(es.b) + popc32(es.c) + popc32(ee.a) + popc32(ee.b) + popc32(ee.c);
-    if (cnt == 1) { t.S1 = t.S1 | es; t.E1 = t.E1 | ee; }
-    else          { t.Sm = t.Sm | es; t.Em = t.Em | ee; }
+    const B81 es = sS | tN, ee = sE | tW;
+    const int cnt = popc32(es.a) + popc32(es.b) + popc32(es.c) + popc32(ee.a) + popc32(ee.b) + popc32(ee.c);
+    const bool single = cnt == 1;
+    const bool mid2 = popc32(t.A.a) + popc32(t.A.b) + popc32(t.A.c) == 2;     // |T_j| of the layer between the two transitions
+    // partners a multi edge of this transition pairs up with: same transition, far transitions, and
+    // the previous transition only when the layer in between has exactly two shortest-path cells
+    const B81 xs = es | t.SmOld | b81_sel(mid2, t.SmPrev), xe = ee | t.EmOld | b81_sel(mid2, t.EmPrev);
+    const B81 es1 = shr<1>(es), ee9 = shr<9>(ee);
+    const B81 pair_s = (es & shr<1>(xs)) | (xs & es1), pair_e = (ee & shr<9>(xe)) | (xe & ee9);
+    // bottleneck: both anchors over the edge; otherwise only the pairs found above
+    t.FS = t.FS | (single ? (es | es1) : pair_s);
+    t.FE = t.FE | (single ? (ee | ee9) : pair_e);
+    t.SmOld = t.SmOld | t.SmPrev; t.EmOld = t.EmOld | t.EmPrev;
+    t.SmPrev = b81_sel(!single, es); t.EmPrev = b81_sel(!single, ee);
     t.A = shl<9>(sS) | tN | shl<1>(sE) | tW;
 }
 
-// Anchors whose wall MAY change the distance.  Horizontal anchor (x,y) removes the south edges of cells
-// (x,y),(x,y+1); vertical anchor (x,y) the east edges of cells (x,y),(x+1,y).  A wall changes nothing if
-// it removes no shortest-path edge, and also nothing if it removes exactly one "multi" edge and no
-// bottleneck: the other edges of that transition keep a shortest path alive.  Everything else —
-// a bottleneck edge, or two multi edges — must be measured with a flood fill.
+// Flag boards -> 64-bit anchor masks (bit 8x+y): rows 0..7, columns 0..7 of the boards.
 MC_HD void q_trace_to_anchors(const QTrace &t, uint64_t &may_h, uint64_t &may_v) {
     uint64_t ch = 0, cv = 0;
-    uint32_t e1_prev = b81_row(t.E1, 0), em_prev = b81_row(t.Em, 0);
 #pragma unroll
     for (int x = 0; x < 8; x++) {
-        uint32_t r1 = b81_row(t.S1, x), rm = b81_row(t.Sm, x);
-        ch |= (uint64_t)((r1 | (r1 >> 1) | (rm & (rm >> 1))) & 0xffu) << (8 * x);
-        uint32_t e1_next = b81_row(t.E1, x + 1), em_next = b81_row(t.Em, x + 1);
-        cv |= (uint64_t)((e1_prev | e1_next | (em_prev & em_next)) & 0xffu) << (8 * x);
-        e1_prev = e1_next; em_prev = em_next;
+        ch |= (uint64_t)(b81_row(t.FS, x) & 0xffu) << (8 * x);
+        cv |= (uint64_t)(b81_row(t.FE, x) & 0xffu) << (8 * x);
     }
     may_h = ch; may_v = cv;
 }

@@ -37,6 +37,22 @@ int emu_q_play(const mctsb_qstate *p, int id, mctsb_qstate *out) {
     return ok;
 }
 
+// Exactness of the pruning masks: every cheap-legal wall OUTSIDE q_cut_masks(player) must leave sp(player)
+// unchanged.  Returns the number of violations; out2 = {candidates, candidates inside the mask}.
+int emu_q_cut_check(const mctsb_qstate *p, int player, int64_t *out2) {
+    QState s; q_unpack(s, *p);
+    uint64_t ch, cv; q_cheap_wall_masks(s, ch, cv);
+    LocalLayers ls;
+    QCut cut = q_cut_masks(s, player, ls, nullptr);
+    int bad = 0;
+    for (int k = q_mask_first(ch, cv); k >= 0; q_mask_clear(ch, cv, k), k = q_mask_first(ch, cv)) {
+        out2[0]++;
+        if (q_mask_has(cut.h, cut.v, k)) { out2[1]++; continue; }
+        if (q_sp_with_wall(s, player, k, nullptr) != cut.sp) bad++;
+    }
+    return bad;
+}
+
 int emu_q_rollout_streams(const mctsb_qstate *states, int policy, int n, const uint32_t *streams, uint32_t len,
                           uint32_t stride, mctsb_outcome *out, mctsb_qstate *finals, uint64_t *work3) {
     LocalLayers pool;

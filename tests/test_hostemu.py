@@ -43,6 +43,17 @@ def test_core_primitives_vs_oracle_on_corpus(emu, port, corpus):
         assert (a["legal"] == b["legal"]).all() and (a["cheap"] == b["cheap"]).all()
 
 
+def test_pruning_masks_are_exact_on_corpus(emu, corpus):
+    """every cheap-legal wall outside the shortest-path pruning mask leaves the path length unchanged
+    (brute force: one flood fill per wall, both players, the whole mid-game corpus + rollout finals)"""
+    g = golden("golden_q_replay.npz")
+    states = np.concatenate([corpus, g["final"].astype(corpus.dtype)])
+    for player in (0, 1):
+        bad, n, kept = emu.q_cut_check(states, player)
+        assert bad == 0
+        assert n > 100000 and kept < 0.45 * n        # the masks prune: most walls need no search
+
+
 def test_core_replay_vs_golden(emu, corpus):
     g = golden("golden_q_replay.npz")
     seed = int(g["seed"])
