@@ -475,8 +475,6 @@ MC_HD void q_trace_init(QTrace &t, B81 pawn) {
     t.FS = t.FE = t.SmOld = t.EmOld = t.SmPrev = t.EmPrev = b81(0u, 0u, 0u);
 }
 
-MC_HD B81 b81_sel(bool c, B81 v) { uint32_t m = c ? 0xffffffffu : 0u; return b81(v.a & m, v.b & m, v.c & m); }
-
 MC_HD void q_trace_step(QTrace &t, B81 L, B81 oS, B81 oE) {
     B81 sS = t.A & oS & shr<9>(L);            // u in A steps south into L: edge stored at u
     B81 tN = shr<9>(t.A) & oS & L;            // u in A steps north to v = u-9 in L: edge stored at v
@@ -486,16 +484,17 @@ MC_HD void q_trace_step(QTrace &t, B81 L, B81 oS, B81 oE) {
     const int cnt = popc32(es.a) + popc32(es.b) + popc32(es.c) + popc32(ee.a) + popc32(ee.b) + popc32(ee.c);
     const bool single = cnt == 1;
     const bool mid2 = popc32(t.A.a) + popc32(t.A.b) + popc32(t.A.c) == 2;     // |T_j| of the layer between the two transitions
-    // partners a multi edge of this transition pairs up with: same transition, far transitions, and
-    // the previous transition only when the layer in between has exactly two shortest-path cells
-    const B81 xs = es | t.SmOld | b81_sel(mid2, t.SmPrev), xe = ee | t.EmOld | b81_sel(mid2, t.EmPrev);
+    // partners an edge of this transition pairs up with: same transition, far transitions, the previous
+    // transition only when the layer in between has exactly two shortest-path cells — and EVERYTHING when
+    // the edge is a bottleneck (both anchors over it are flagged)
+    const uint32_t m2 = mid2 ? 0xffffffffu : 0u, m1 = single ? 0xffffffffu : 0u;
+    const B81 xs = b81(es.a | t.SmOld.a | (t.SmPrev.a & m2) | m1, es.b | t.SmOld.b | (t.SmPrev.b & m2) | m1, es.c | t.SmOld.c | (t.SmPrev.c & m2) | m1);
+    const B81 xe = b81(ee.a | t.EmOld.a | (t.EmPrev.a & m2) | m1, ee.b | t.EmOld.b | (t.EmPrev.b & m2) | m1, ee.c | t.EmOld.c | (t.EmPrev.c & m2) | m1);
     const B81 es1 = shr<1>(es), ee9 = shr<9>(ee);
-    const B81 pair_s = (es & shr<1>(xs)) | (xs & es1), pair_e = (ee & shr<9>(xe)) | (xe & ee9);
-    // bottleneck: both anchors over the edge; otherwise only the pairs found above
-    t.FS = t.FS | (single ? (es | es1) : pair_s);
-    t.FE = t.FE | (single ? (ee | ee9) : pair_e);
+    t.FS = t.FS | (es & shr<1>(xs)) | (xs & es1);
+    t.FE = t.FE | (ee & shr<9>(xe)) | (xe & ee9);
     t.SmOld = t.SmOld | t.SmPrev; t.EmOld = t.EmOld | t.EmPrev;
-    t.SmPrev = b81_sel(!single, es); t.EmPrev = b81_sel(!single, ee);
+    t.SmPrev = b81(es.a & ~m1, es.b & ~m1, es.c & ~m1); t.EmPrev = b81(ee.a & ~m1, ee.b & ~m1, ee.c & ~m1);
     t.A = shl<9>(sS) | tN | shl<1>(sE) | tW;
 }
 
