@@ -39,7 +39,7 @@ UNIT = "rollouts/s"
 ALG_OPS_PER_ROLLOUT = 13133.3 * 24 + 4532.6 * 12 + 49.1 * 200
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
 # algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
-NCU_DRAM_BYTES_PER_LAUNCH = 366848 + 776192   # profiles/r01_final_lockstep.md
+NCU_DRAM_BYTES_PER_LAUNCH = 813824 + 1280768   # profiles/r01_final_lockstep.md (ncu, one launch)
 
 
 class ClockSampler:
@@ -209,39 +209,58 @@ def main():
     # ---- device-resident throughput ("value") -------------------------------------------------------------
     be.upload_states(G, state)
     launches0 = be.counters()["kernel_launches"]
-    for w in range(args.warmup):
+    for w in range(args.warmup):                       # a warm-up step is a whole step: kernel, D2H, cross-rank merge
         be.run_resident(G, P, per_leaf, first_id(w), timed=True)
-        be.wait()
+        _, wsums = be.wait()
+        if dist is not None:
+            multi.allreduce_leaf_sums(wsums, dist, device="cuda")
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    # one nvidia-smi process per job (rank 0) watching every GPU of the job
+    sampler = ClockSampler(",".join(str(g) for g in range(world)) if world > 1 else local_rank)
+    if rank == 0:
+        sampler.start()
     barrier()
-    kernel_ms = []
-    t0 = time.perf_counter()
+    kernel_ms, merges = [], []
+
+    def merged_score(pending):
+        ms_ = pending.result()
+        return float(sum(multi.leaf_sum_to_double(lo, hi) for lo, hi in zip(ms_["lo"], ms_["hi"])))
+
     total_score = 0.0
+    step_wall = 0.0                                    # steps only: the L2 flush between them is not part of a step
     for k in range(args.steps):
-        be.flush_l2()                                  # 256 MiB memset between timed steps (not inside the kernel's events)
+        be.flush_l2()                                  # 256 MiB memset + sync between timed steps
+        ta = time.perf_counter()
         ms = be.run_resident(G, P, per_leaf, first_id(args.warmup + k), timed=True)
         score, sums = be.wait()
         if dist is not None:
-            sums = multi.allreduce_leaf_sums(sums, dist, device="cuda")   # exact integer merge over NVLink (NCCL)
-            score = np.array([multi.leaf_sum_to_double(lo, hi) for lo, hi in zip(sums["lo"], sums["hi"])])
+            # exact integer merge over NVLink (NCCL), started now and collected one step later: the next
+            # step's kernel runs while this step's statistics are exchanged
+            merges.append(multi.allreduce_leaf_sums_async(sums, dist, device="cuda"))
+            if len(merges) > 1:
+                total_score += merged_score(merges.pop(0))
+        else:
+            total_score += float(np.sum(score))
+        step_wall += time.perf_counter() - ta
         kernel_ms.append(ms)
-        total_score += float(np.sum(score))
+    ta = time.perf_counter()
+    while merges:
+        total_score += merged_score(merges.pop(0))
     barrier()
-    wall_s = time.perf_counter() - t0
-    sampler.stop()
+    step_wall += time.perf_counter() - ta              # the last merge and the closing barrier belong to the job
+    if rank == 0:
+        sampler.stop()
     launches = be.counters()["kernel_launches"] - launches0 - args.warmup
 
     dev_ms = float(sum(kernel_ms))
     if dist is not None:
         import torch
-        t = torch.tensor([dev_ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
+        t = torch.tensor([dev_ms, step_wall * 1e3], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dev_ms, wall_ms = float(t[0]), float(t[1])
-        step_ms = wall_ms            # at N>1 the step includes the all-reduce: use the bracketed wall time
+        step_ms = wall_ms            # at N>1 a step = kernel + D2H + cross-rank merge: host clock around the steps, max over ranks
     else:
-        step_ms = dev_ms
+        step_ms = dev_ms             # N=1: CUDA events around the kernel launches
     total_rollouts = n * args.steps * world
     value = total_rollouts / (step_ms * 1e-3)
     mean_score = total_score / (n * args.steps * world) if dist is not None else total_score / (n * args.steps)
@@ -303,7 +322,7 @@ def main():
                      "alu_pipe_lop3_peak": lop3_peak / 1e12, "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
                      "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3 + integer-add chains on all SMs, both pipes; alu_pipe_lop3_peak = LOP3 only); "
                              "achieved = rollouts/s x the REFERENCE algorithm's integer work per rollout (DESIGN.md 5); executed "
-                             "thread instructions per second from ncu are in profiles/ (17.7 T/s = 0.51 of this peak)"},
+                             "thread instructions per second from ncu are in profiles/ (17.2 T/s = 0.50 of this peak)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world},
         "gpu_launches": int(launches),

@@ -20,18 +20,37 @@ def shard_range(total, world, rank):
     return start, count
 
 
-def allreduce_leaf_sums(sums, dist, device=None):
-    """Exact merge of per-leaf accumulators across ranks.  `sums`: numpy structured array (lo, hi, n)."""
+class PendingLeafMerge:
+    """An all-reduce of leaf accumulators in flight (async_op): `result()` waits and returns the merged array.
+    Lets a rank launch its next flush while the previous flush's statistics cross NVLink."""
+
+    def __init__(self, tensor, work, dtype):
+        self.tensor, self.work, self.dtype = tensor, work, dtype
+
+    def result(self):
+        if self.work is not None:
+            self.work.wait()
+            self.work = None
+        out = self.tensor.cpu().numpy()
+        merged = np.zeros(out.shape[0], dtype=self.dtype)
+        merged["lo"], merged["hi"], merged["n"] = out[:, 0].astype(np.uint64), out[:, 1].astype(np.uint64), out[:, 2].astype(np.uint64)
+        return merged
+
+
+def allreduce_leaf_sums_async(sums, dist, device=None):
+    """Start the exact merge of per-leaf accumulators across ranks; returns a PendingLeafMerge."""
     import torch
     flat = np.stack([sums["lo"].astype(np.int64), sums["hi"].astype(np.int64), sums["n"].astype(np.int64)], axis=1)
     t = torch.from_numpy(np.ascontiguousarray(flat))
     if device is not None:
-        t = t.to(device)
-    dist.all_reduce(t)
-    out = t.cpu().numpy()
-    merged = np.zeros(len(sums), dtype=sums.dtype)
-    merged["lo"], merged["hi"], merged["n"] = out[:, 0].astype(np.uint64), out[:, 1].astype(np.uint64), out[:, 2].astype(np.uint64)
-    return merged
+        t = t.to(device, non_blocking=True)
+    work = dist.all_reduce(t, async_op=True)
+    return PendingLeafMerge(t, work, sums.dtype)
+
+
+def allreduce_leaf_sums(sums, dist, device=None):
+    """Exact merge of per-leaf accumulators across ranks.  `sums`: numpy structured array (lo, hi, n)."""
+    return allreduce_leaf_sums_async(sums, dist, device).result()
 
 
 def leaf_sum_to_double(lo, hi):

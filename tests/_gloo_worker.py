@@ -37,7 +37,10 @@ def main():
         o, _, _ = port.q_rollout_philox(leaves[leaf], seed, first + g, 1)
         acc, _ = port.leaf_sum(o["score"])
         sums["lo"][leaf] += acc["lo"]; sums["hi"][leaf] += acc["hi"]; sums["n"][leaf] += acc["n"]
-    merged = multi.allreduce_leaf_sums(sums, dist)
+    pending = multi.allreduce_leaf_sums_async(sums, dist)        # in flight while the rank does other work
+    merged_sync = multi.allreduce_leaf_sums(sums, dist)
+    merged = pending.result()
+    assert merged.tobytes() == merged_sync.tobytes()
 
     # (ii) root-parallel trees: same root, different Philox keys per rank, one all-reduce of the root statistics
     host = load()
