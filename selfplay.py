@@ -34,6 +34,11 @@ def main():
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
 
+    # stdout carries exactly one JSON line: native libraries' banners (NCCL version) go to stderr
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import montecarlotreesearch_b200 as m
     from montecarlotreesearch_b200 import multi
     from tests.hostlib import Session, load
@@ -42,9 +47,9 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
+    import torch
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -55,34 +60,42 @@ def main():
                    leaves_per_flush=args.leaves_per_flush, device=local_rank, seed=args.seed + rank)
     if args.overlap:
         tree.set_overlap(True)
-    moves, t_grow, t_merge = [], 0.0, 0.0
+    moves, t_grow, t_merge, t_skew = [], 0.0, 0.0, 0.0
+    if dist is not None:                               # bring the communicator up before the clock starts
+        dist.all_reduce(torch.zeros(8, dtype=torch.float64, device="cuda"))
+        torch.cuda.synchronize()
+        dist.barrier()
     t0 = time.perf_counter()
     terminal = False
     while not terminal and len(moves) < args.max_moves:
         a = time.perf_counter()
         tree.grow(args.iters)
         b = time.perf_counter()
+        t_grow += b - a
         if dist is not None:
+            dist.barrier()                             # waiting for the slowest tree of this move (skew), kept apart
+            b2 = time.perf_counter()
+            t_skew += b2 - b
             merged = multi.allreduce_root_stats(tree.export_root(), dist, device="cuda")
             tree.import_root(merged)
+            b = b2
         c = time.perf_counter()
         mv = tree.best_move()
         if dist is not None:
-            allmv = [None] * world
-            dist.all_gather_object(allmv, mv)
-            assert len(set(allmv)) == 1, "ranks disagree on the move after the all-reduce: %r" % (allmv,)
+            # every rank must have picked the same move from the merged statistics: max(mv) == -max(-mv)
+            chk = torch.tensor([mv, -mv], dtype=torch.int64, device="cuda")
+            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
+            assert int(chk[0]) == -int(chk[1]) == mv, "ranks disagree on the move after the all-reduce"
         if mv < 0:
             break
         moves.append(mv)
         terminal = tree.advance(mv)
-        t_grow += b - a
         t_merge += c - b
     wall = time.perf_counter() - t0
     flushes, rollouts = tree.counters()
     final = tree.current_state()
     tree.close()
     if dist is not None:
-        import torch
         tot = torch.tensor([float(rollouts)], dtype=torch.float64, device="cuda")
         dist.all_reduce(tot)
         rollouts_all = float(tot[0])
@@ -91,7 +104,7 @@ def main():
     else:
         rollouts_all = float(rollouts)
     if rank == 0:
-        print(json.dumps({
+        os.write(real_stdout, (json.dumps({
             "config": "configs[%d]: Quoridor self-play, %d iterations/move, flush = %d leaves x %d rollouts = %d playouts"
                       % (4 if world > 1 else 3, args.iters, args.leaves_per_flush, args.rollouts_per_leaf,
                          args.leaves_per_flush * args.rollouts_per_leaf),
@@ -100,8 +113,9 @@ def main():
             "rollouts_total": rollouts_all, "rollouts_per_sec": rollouts_all / wall, "wall_s": wall,
             "flushes_rank0": flushes, "ms_per_flush": 1e3 * t_grow / max(1, flushes),
             "allreduce_ms_per_move": 1e3 * t_merge / max(1, len(moves)),
+            "wait_for_slowest_rank_ms_per_move": 1e3 * t_skew / max(1, len(moves)),
             "move_ids": moves,
-        }), flush=True)
+        }) + "\n").encode())
 
 
 if __name__ == "__main__":
