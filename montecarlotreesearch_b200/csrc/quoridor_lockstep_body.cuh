@@ -77,13 +77,6 @@ static inline unsigned long long ls_emu_bits(double x) { unsigned long long b; m
 
 namespace mctsb {
 
-#if defined(MCTSB_HOST_EMU)
-static unsigned long long g_dbg_iters[4][130], g_dbg_pend[4][130];   // [mode][count] histograms (emulation only)
-#define LS_DBG(x) x
-#else
-#define LS_DBG(x)
-#endif
-
 static constexpr int LS_THREADS = 128;
 static constexpr int LS_SHARE = 32;                     // candidates one lane may queue per batch
 static constexpr int LS_QCAP = 32 * LS_SHARE;           // queue entries per warp
@@ -423,7 +416,6 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             unsigned long long *slot = wb.best + lane;
             *slot = 0ull;
             LS_SYNCWARP();                                     // every lane is done reading its layers: the queue may overwrite them
-            LS_DBG(if (playing) g_dbg_pend[mode][popc64(pend_h) + popc64(pend_v)]++;)
             LS_UNROLL1
             while (LS_ANY((pend_h | pend_v) != 0ull || head_k >= 0)) {
                 // -- publish: every lane queues up to LS_SHARE candidates (half horizontal, half vertical), offsets

@@ -129,10 +129,4 @@ int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t 
     return 0;
 }
 
-
-void emu_dbg_hist(unsigned long long *iters, unsigned long long *pend, int reset) {
-    memcpy(iters, g_dbg_iters, sizeof g_dbg_iters); memcpy(pend, g_dbg_pend, sizeof g_dbg_pend);
-    if (reset) { memset(g_dbg_iters, 0, sizeof g_dbg_iters); memset(g_dbg_pend, 0, sizeof g_dbg_pend); }
-}
-
-}
+}  // extern "C"
