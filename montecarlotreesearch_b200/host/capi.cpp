@@ -164,6 +164,9 @@ int mcts_host_current_state(void *hs, void *packed_out) {
     return h->tree->get_current_state()->gpu_pack(packed_out) ? 0 : -1;
 }
 
+// the Philox stream id the next flush of ANY tree in this process will start at (ids are never reused)
+uint64_t mcts_host_peek_rollout_id(void) { return next_rollout_ids(0); }
+
 void mcts_host_counters(void *hs, uint64_t *flushes, uint64_t *rollouts) {
     HostSession *h = (HostSession *)hs;
     *flushes = h->tree->get_flushes(); *rollouts = h->tree->get_rollouts_played();

@@ -375,6 +375,15 @@ double ref_grow_tree(int game, const mctsb_qstate *qs, uint32_t x_mask, uint32_t
     return std::chrono::duration<double>(t1 - t0).count();
 }
 
+#ifdef ORACLE_WITH_DROPIN
+/* drop-in build only: a reference Quoridor_state through integration/gpu_jobscheduler.cpp's packer */
+extern "C" int mctsb_dropin_pack_quoridor(const void *reference_state, mctsb_qstate *out);
+int ref_q_pack_roundtrip(const mctsb_qstate *in, mctsb_qstate *out) {
+    Quoridor_state q; load_q(q, in);
+    return mctsb_dropin_pack_quoridor(&q, out);
+}
+#endif
+
 /* ---------------- CPU baseline: RolloutJobs on the reference JobScheduler ---------------- */
 
 /* JobScheduler sched(n_threads); n_jobs x schedule(new RolloutJob(&state,&res[i])); wait

@@ -108,10 +108,13 @@ class RefLib:
     """One of the two builds of the reference.  kind = 'replay' (stream RNG) or 'native'."""
 
     def __init__(self, kind="replay"):
+        """kind = 'replay' (stream RNG), 'native' (stock RNG; the timed CPU baseline) or 'gpu_dropin' (the
+        reference's tree + games linked with integration/gpu_jobscheduler.cpp instead of its JobScheduler.cpp:
+        its RolloutJobs run on the B200 through libmctsb.so)."""
         path = os.path.join(REF_DIR, "libref_%s.so" % kind)
         if not os.path.exists(path):
             raise FileNotFoundError(
-                "%s missing: run `make -C oracle ref` where /root/reference exists" % path
+                "%s missing: run `make -C oracle ref dropin` where /root/reference exists" % path
             )
         self.kind = kind
         self.lib = L = C.CDLL(path)
@@ -128,6 +131,10 @@ class RefLib:
         L.ref_grow_tree.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_int]
         L.ref_jobscheduler_bench.restype = C.c_double
         L.ref_jobscheduler_bench.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp]
+        if kind == "gpu_dropin":
+            L.mctsb_dropin_reset.argtypes = [C.c_uint64]
+            L.mctsb_dropin_counters.argtypes = [vp, vp]
+            L.ref_q_pack_roundtrip.argtypes = [vp, vp]
         if kind == "replay":
             L.ref_q_rollout_stream.restype = C.c_double
             L.ref_q_rollout_stream.argtypes = [vp, vp, C.c_uint64, vp, vp, vp, vp, vp, vp]
@@ -279,6 +286,25 @@ class RefLib:
         n = int(min(out4[3], max_children))
         return {"seconds": secs, "root_sims": out4[0], "root_score": out4[1], "size": out4[2],
                 "children": ch[:n].copy()}
+
+    # ---- gpu_dropin build only ------------------------------------------------------------------
+    def dropin_reset(self, first_rollout_id=0):
+        self.lib.mctsb_dropin_reset(first_rollout_id)
+
+    def dropin_counters(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self.lib.mctsb_dropin_counters(C.byref(a), C.byref(b))
+        return a.value, b.value
+
+    def dropin_device_ok(self):
+        return bool(self.lib.mctsb_dropin_device_ok())
+
+    def q_pack_roundtrip(self, s):
+        """packed -> reference Quoridor_state -> the drop-in's packer -> packed"""
+        a, p = self._s(s)
+        out = np.zeros((), dtype=QSTATE_DTYPE)
+        ok = self.lib.ref_q_pack_roundtrip(p, out.ctypes.data)
+        return bool(ok), out
 
     def jobscheduler_bench(self, game, n_threads, n_jobs, qstates=None, x_mask=0, o_mask=0):
         qs = np.ascontiguousarray(qstates if qstates is not None else opening_state(), dtype=QSTATE_DTYPE).reshape(-1)

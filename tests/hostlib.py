@@ -27,6 +27,8 @@ def load():
     L.mcts_host_advance.argtypes = [vp, C.c_int]
     L.mcts_host_current_state.argtypes = [vp, vp]
     L.mcts_host_counters.argtypes = [vp, vp, vp]
+    L.mcts_host_peek_rollout_id.restype = C.c_uint64
+    L.mcts_host_peek_rollout_id.argtypes = []
     L.mcts_host_export_root.argtypes = [vp, vp, C.c_int]
     L.mcts_host_import_root.argtypes = [vp, vp, C.c_int]
     return L
