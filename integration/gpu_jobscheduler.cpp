@@ -8,7 +8,7 @@
 // mcts.cpp / Quoridor.cpp / TicTacToe.cpp, and MCTS_tree::grow_tree, MCTS_agent::genmove and the example
 // mains run their rollouts on the GPU without one edited line:
 //
-//   g++ -O2 -std=c++11 -I$REF -Iinclude -include integration/open_classes.h -c integration/gpu_jobscheduler.cpp
+//   g++ -O2 -std=c++11 -DMCTSB_DROPIN_ONLY_QUORIDOR -I$REF -Iinclude -include integration/open_classes.h -c integration/gpu_jobscheduler.cpp
 //   g++ -O2 -std=c++11 -I$REF $REF/mcts/src/mcts.cpp $REF/examples/Quoridor/{Quoridor,main}.cpp \
 //       gpu_jobscheduler.o -Lmontecarlotreesearch_b200 -lmctsb -o quoridor_gpu
 //
@@ -18,11 +18,19 @@
 // has no CPU implementation of the two games it knows.  Without a CUDA device the first rollout aborts.
 //
 // Environment: MCTSB_DEVICE (default 0), MCTSB_SEED (Philox key, default 0x2026101900000001).
+// A program that links only one of the two games (the reference Makefile builds `quoridor` and `tictactoe`
+// separately) compiles this file with -DMCTSB_DROPIN_ONLY_QUORIDOR or -DMCTSB_DROPIN_ONLY_TICTACTOE.
 #include "mctsb.h"
 #include "mcts/include/JobScheduler.h"
 #include "mcts/include/mcts.h"
+#if !defined(MCTSB_DROPIN_ONLY_TICTACTOE)
+#define DROPIN_QUORIDOR 1
 #include "examples/Quoridor/Quoridor.h"
+#endif
+#if !defined(MCTSB_DROPIN_ONLY_QUORIDOR)
+#define DROPIN_TICTACTOE 1
 #include "examples/TicTacToe/TicTacToe.h"
+#endif
 
 namespace {
 
@@ -41,6 +49,7 @@ mctsb_backend *backend() {
     return g_backend;
 }
 
+#if defined(DROPIN_QUORIDOR)
 // walls[][] + wall_connections[][] -> anchor masks.  Each connection point carries one wall, horizontal
 // (segments 'h' at (x,y),(x,y+1)) or vertical ('v' at (x,y),(x+1,y)); each segment belongs to exactly one
 // wall.  The arrays do not name the orientation, so find an assignment that uses every segment once
@@ -88,6 +97,9 @@ bool pack(const Quoridor_state &q, mctsb_qstate &p) {
     return true;
 }
 
+#endif  // DROPIN_QUORIDOR
+
+#if defined(DROPIN_TICTACTOE)
 void pack(const TicTacToe_state &t, mctsb_tstate &p) {
     p.x_mask = p.o_mask = 0;
     for (int c = 0; c < 9; c++) {
@@ -96,19 +108,26 @@ void pack(const TicTacToe_state &t, mctsb_tstate &p) {
     }
     if (t.turn == 'o') p.o_mask |= 0x8000u;
 }
+#endif
 
 // jobs[a..b) are RolloutJobs of ONE state: play them in one launch, store result i where job i asked for it
 void play_group(std::vector<Job *> &jobs, size_t a, size_t b) {
     const MCTS_state *state = static_cast<RolloutJob *>(jobs[a])->state;
     const uint32_t R = (uint32_t)(b - a);
-    int game; unsigned char packed[32];
+    int game = -1; unsigned char packed[32];
+#if defined(DROPIN_QUORIDOR)
     if (const Quoridor_state *q = dynamic_cast<const Quoridor_state *>(state)) {
         game = MCTSB_GAME_QUORIDOR;
         if (!pack(*q, *reinterpret_cast<mctsb_qstate *>(packed))) { fprintf(stderr, "gpu_jobscheduler: inconsistent wall arrays\n"); abort(); }
-    } else if (const TicTacToe_state *t = dynamic_cast<const TicTacToe_state *>(state)) {
+    }
+#endif
+#if defined(DROPIN_TICTACTOE)
+    if (game < 0) if (const TicTacToe_state *t = dynamic_cast<const TicTacToe_state *>(state)) {
         game = MCTSB_GAME_TICTACTOE;
         pack(*t, *reinterpret_cast<mctsb_tstate *>(packed));
-    } else {                                   // not one of the two games the kernels play: the job's own run()
+    }
+#endif
+    if (game < 0) {                            // not one of the two games the kernels play: the job's own run()
         for (size_t i = a; i < b; i++) jobs[i]->run();
         return;
     }
@@ -162,7 +181,9 @@ void mctsb_dropin_reset(uint64_t first_rollout_id) { g_next_id = first_rollout_i
 void mctsb_dropin_counters(uint64_t *flushes, uint64_t *rollouts) { *flushes = g_flushes; *rollouts = g_rollouts; }
 int mctsb_dropin_device_ok(void) { int n = 0; return mctsb_device_count(&n) == MCTSB_OK && n > 0; }
 // the packer alone (CPU): `reference_state` is a `const Quoridor_state *`; 1 = packed
+#if defined(DROPIN_QUORIDOR)
 int mctsb_dropin_pack_quoridor(const void *reference_state, mctsb_qstate *out) {
     return pack(*static_cast<const Quoridor_state *>(reference_state), *out) ? 1 : 0;
 }
+#endif
 }

@@ -113,3 +113,41 @@ def test_dropin_refuses_to_run_without_a_device(dropin):
             "reflib.RefLib('gpu_dropin').grow_tree(1, 10)" % os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True)
     assert r.returncode != 0 and "no CPU fallback" in r.stderr
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference"), reason="reference sources not present")
+def test_reference_example_main_links_against_the_gpu_scheduler(tmp_path):
+    """the recipe of INTEGRATION.md (C): the reference's own Quoridor REPL, its tree and its game, with the
+    drop-in object in place of JobScheduler.cpp — compiles and links without touching a reference file"""
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = "/root/reference"
+    obj = str(tmp_path / "gpu_jobscheduler.o")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-w", "-DMCTSB_DROPIN_ONLY_QUORIDOR", "-I" + ref, "-I" + os.path.join(root, "include"),
+                           "-include", os.path.join(root, "integration", "open_classes.h"),
+                           "-c", os.path.join(root, "integration", "gpu_jobscheduler.cpp"), "-o", obj])
+    exe = str(tmp_path / "quoridor_gpu")
+    subprocess.check_call(["g++", "-O1", "-std=c++11", "-w", "-pthread", "-I" + ref,
+                           ref + "/mcts/src/mcts.cpp", ref + "/examples/Quoridor/Quoridor.cpp",
+                           ref + "/examples/Quoridor/main.cpp", obj,
+                           "-L" + m.PKG_DIR, "-lmctsb", "-Wl,-rpath," + m.PKG_DIR, "-o", exe])
+    syms = subprocess.run(["nm", "-C", exe], capture_output=True, text=True).stdout
+    assert "JobScheduler::waitUntilJobsHaveFinished" in syms and "mctsb_rollout_outcomes" in syms
+    assert "thread_code" in syms and "pthread_create" not in syms          # no pool threads are ever created
+
+
+@pytest.mark.gpu
+def test_reference_repl_binary_plays_on_the_gpu():
+    """oracle/_ref/quoridor_gpu = the reference's examples/Quoridor/main.cpp + mcts.cpp + Quoridor.cpp, unmodified,
+    linked with the drop-in scheduler.  `genmove` grows the reference's tree (MAXITER 20 000 iterations x 4
+    RolloutJobs, main.cpp:6,145) with every rollout played by the CUDA kernels, then prints its move."""
+    import re
+    import subprocess
+    exe = os.path.join(reflib.REF_DIR, "quoridor_gpu")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/quoridor_gpu not built")
+    r = subprocess.run([exe], input="genmove\nwinner\nq\n", capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-400:]
+    sims = re.search(r"Number of simulations: (\d+)", r.stdout)
+    assert sims and int(sims.group(1)) >= 4 * 1000          # the tree was grown through the GPU scheduler
+    assert "Best moves:" in r.stdout and "Illegal" not in r.stdout and "illegal" not in r.stderr
