@@ -7,6 +7,7 @@
 #include "TicTacToe.h"
 #include "mctsb.h"
 #include <cstring>
+#include <deque>
 #include <memory>
 
 extern "C" {
@@ -17,7 +18,8 @@ typedef void (*mcts_rollout_cb)(int game, int policy, const void *states, int n_
 namespace {
 class CallbackBackend : public RolloutBackend {
     mcts_rollout_cb cb; void *user;
-    int g = 0, p = 0, n = 0; uint32_t R = 0; uint64_t first = 0; std::vector<unsigned char> held;
+    struct Held { int g, p, n; uint32_t R; uint64_t first; std::vector<unsigned char> states; };
+    std::deque<Held> held;
 public:
     CallbackBackend(mcts_rollout_cb cb, void *user) : cb(cb), user(user) {}
     void rollout_batch(int game, int policy, const void *states, int n_leaves, uint32_t rpl, uint64_t first_id, double *out) override {
@@ -25,10 +27,15 @@ public:
     }
     void submit(int game, int policy, const void *states, int n_leaves, uint32_t rpl, uint64_t first_id) override {
         size_t rec = game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate);
-        held.assign((const unsigned char *)states, (const unsigned char *)states + rec * n_leaves);
-        g = game; p = policy; n = n_leaves; R = rpl; first = first_id;
+        Held h{game, policy, n_leaves, rpl, first_id, {}};
+        h.states.assign((const unsigned char *)states, (const unsigned char *)states + rec * n_leaves);
+        held.push_back(std::move(h));
     }
-    void wait(double *out) override { cb(g, p, held.data(), n, R, first, out, user); }
+    void wait(double *out) override {
+        Held h = std::move(held.front()); held.pop_front();
+        cb(h.g, h.p, h.states.data(), h.n, h.R, h.first, out, user);
+    }
+    int max_in_flight() const override { return 4; }
 };
 
 struct HostSession {
@@ -122,7 +129,9 @@ void mcts_host_session_destroy(void *hs) { delete (HostSession *)hs; }
 
 void mcts_host_set_overlap(void *hs, int on) {
     HostSession *h = (HostSession *)hs;
-    MCTS_batching b = h->tree->get_batching(); b.overlap = on != 0; h->tree->set_batching(b);
+    MCTS_batching b = h->tree->get_batching();
+    b.overlap = on != 0; b.flushes_in_flight = on > 1 ? (uint32_t)on : 1;     // on = number of flushes in flight (0 = synchronous)
+    h->tree->set_batching(b);
 }
 
 int mcts_host_grow(void *hs, int max_iter, double max_seconds, char *err, int err_cap) {

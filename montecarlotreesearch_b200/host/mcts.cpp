@@ -265,7 +265,14 @@ void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
             }
         }
     } else {
-        vector<MCTS_node *> leaves, inflight;
+        vector<MCTS_node *> leaves;
+        deque<vector<MCTS_node *>> inflight;                          // flushes on the GPU, oldest first
+        size_t depth = 0;
+        if (batching.overlap) {
+            depth = batching.flushes_in_flight == 0 ? 1 : batching.flushes_in_flight;
+            const size_t cap = (size_t)get_backend()->max_in_flight();
+            if (depth > cap) depth = cap;
+        }
         while (i < max_iter || !inflight.empty()) {
             for (uint32_t k = 0; k < K && i < max_iter; k++, i++) {
                 MCTS_node *node = select();
@@ -274,16 +281,24 @@ void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
                 leaf->add_virtual((int)batching.rollouts_per_leaf);   // keep the next selection away from this path
                 leaves.push_back(leaf);
             }
-            if (!inflight.empty()) collect_leaves(inflight);          // the GPU ran this flush while the host selected
+            // the GPU ran the queued flushes while the host selected: take the oldest results when the queue is
+            // full (or nothing is left to select), then queue the new batch behind whatever is still running
+            if (!inflight.empty() && (inflight.size() >= depth || leaves.empty())) {
+                collect_leaves(inflight.front());
+                inflight.pop_front();
+            }
             if (!leaves.empty()) {
-                if (batching.overlap && submit_leaves(leaves)) inflight.swap(leaves);
-                else flush_leaves(leaves);
+                if (depth > 0 && submit_leaves(leaves)) { inflight.emplace_back(); inflight.back().swap(leaves); }
+                else {
+                    while (!inflight.empty()) { collect_leaves(inflight.front()); inflight.pop_front(); }
+                    flush_leaves(leaves);
+                }
             }
             time(&now_t);
             dt = difftime(now_t, start_t);
             if (dt > max_time_in_seconds) {
                 if (g_verbose) cout << "Early stopping: Made " << i << " iterations in " << dt << " seconds." << endl;
-                if (!inflight.empty()) collect_leaves(inflight);
+                while (!inflight.empty()) { collect_leaves(inflight.front()); inflight.pop_front(); }
                 break;
             }
         }

@@ -11,6 +11,7 @@
 #include "rollout_backend.h"
 #include <cstdint>
 #include <iomanip>
+#include <deque>
 #include <queue>
 #include <vector>
 
@@ -28,6 +29,10 @@ struct MCTS_batching {
     // leaves_per_flush > 1 only: select the next batch of leaves on the host while the previous flush is
     // still running on the GPU (its leaves keep their virtual loss until the results arrive)
     bool overlap = false;
+    // with overlap: how many flushes may be queued on the GPU at once (1 or 2; capped by the backend).  Two
+    // keep the GPU busy across the hand-over: a 65 536-playout flush occupies only 2 048 of the 2 960 resident
+    // warps of a B200, the second one fills the rest and takes over when the first drains.
+    uint32_t flushes_in_flight = 1;
 };
 
 class MCTS_tree;

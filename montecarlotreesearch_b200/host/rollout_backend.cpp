@@ -12,24 +12,44 @@ static void check(mctsb_backend *h, int st, const char *what) {
     throw BackendError(st, msg);
 }
 
-CudaRolloutBackend::CudaRolloutBackend(int device, uint64_t seed) : handle(nullptr) {
+CudaRolloutBackend::CudaRolloutBackend(int device, uint64_t seed)
+    : handle(nullptr), device(device), seed(seed), submitted(0), collected(0) {
+    for (int i = 0; i < MAX_HANDLES; i++) handles[i] = nullptr;
     check(nullptr, mctsb_create(&handle, device, seed), "mctsb_create");
+    handles[0] = handle;
 }
 
-CudaRolloutBackend::~CudaRolloutBackend() { mctsb_destroy(handle); }
+CudaRolloutBackend::~CudaRolloutBackend() {
+    for (int i = 0; i < MAX_HANDLES; i++) if (handles[i]) mctsb_destroy(handles[i]);
+}
+
+mctsb_backend *CudaRolloutBackend::slot(unsigned i) {
+    mctsb_backend *&h = handles[i % MAX_HANDLES];
+    if (!h) check(nullptr, mctsb_create(&h, device, seed), "mctsb_create");   // same device and Philox key: results depend on ids only
+    return h;
+}
 
 void CudaRolloutBackend::rollout_batch(int game, int policy, const void *packed_states, int n_leaves,
                                        uint32_t rollouts_per_leaf, uint64_t first_rollout_id, double *score_sum) {
+    if (submitted != collected) throw BackendError(MCTSB_ERR_BUSY, "rollout_batch while submissions are in flight");
     check(handle, mctsb_rollout_batch(handle, game, policy, packed_states, n_leaves, rollouts_per_leaf, first_rollout_id,
                                       score_sum, nullptr), "mctsb_rollout_batch");
 }
 
 void CudaRolloutBackend::submit(int game, int policy, const void *packed_states, int n_leaves, uint32_t rollouts_per_leaf,
                                 uint64_t first_rollout_id) {
-    check(handle, mctsb_submit(handle, game, policy, packed_states, n_leaves, rollouts_per_leaf, first_rollout_id), "mctsb_submit");
+    if (submitted - collected >= (unsigned)MAX_HANDLES) throw BackendError(MCTSB_ERR_BUSY, "too many submissions in flight");
+    mctsb_backend *h = slot(submitted);
+    check(h, mctsb_submit(h, game, policy, packed_states, n_leaves, rollouts_per_leaf, first_rollout_id), "mctsb_submit");
+    submitted++;
 }
 
-void CudaRolloutBackend::wait(double *score_sum) { check(handle, mctsb_wait(handle, score_sum, nullptr), "mctsb_wait"); }
+void CudaRolloutBackend::wait(double *score_sum) {
+    if (submitted == collected) throw BackendError(MCTSB_ERR_NOT_SUBMITTED, "wait without a submission");
+    mctsb_backend *h = slot(collected);
+    check(h, mctsb_wait(h, score_sum, nullptr), "mctsb_wait");
+    collected++;
+}
 
 static RolloutBackend *g_default = nullptr;
 static std::unique_ptr<CudaRolloutBackend> g_owned;

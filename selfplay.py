@@ -30,7 +30,8 @@ def main():
     ap.add_argument("--rollouts-per-leaf", type=int, default=4096)
     ap.add_argument("--leaves-per-flush", type=int, default=16)
     ap.add_argument("--max-moves", type=int, default=120)
-    ap.add_argument("--overlap", action="store_true", help="select the next batch of leaves while the previous flush runs on the GPU")
+    ap.add_argument("--overlap", type=int, nargs="?", const=1, default=0,
+                    help="flushes in flight: 1 = select the next batch of leaves while the previous flush runs on the GPU, 2 = two flushes queued")
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
 
@@ -59,7 +60,7 @@ def main():
     tree = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
                    leaves_per_flush=args.leaves_per_flush, device=local_rank, seed=args.seed + rank)
     if args.overlap:
-        tree.set_overlap(True)
+        tree.set_overlap(args.overlap)
     moves, t_grow, t_merge, t_skew = [], 0.0, 0.0, 0.0
     if dist is not None:                               # bring the communicator up before the clock starts
         dist.all_reduce(torch.zeros(8, dtype=torch.float64, device="cuda"))

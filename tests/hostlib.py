@@ -55,6 +55,7 @@ class Session:
             self.h = None
 
     def set_overlap(self, on=True):
+        """on = False / 0: synchronous flushes; True / 1: one flush in flight; 2: two flushes queued on the GPU"""
         self.lib.mcts_host_set_overlap(self.h, int(on))
 
     def grow(self, iters, seconds=1e9):

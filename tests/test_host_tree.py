@@ -124,12 +124,14 @@ def test_leaf_batching_with_virtual_loss(host, port):
     t.close()
 
 
-def test_overlapped_flushes(host, port):
-    """Selection of the next batch overlaps the previous flush: same bookkeeping, one flush in flight."""
+@pytest.mark.parametrize("in_flight", [1, 2, 3])
+def test_overlapped_flushes(host, port, in_flight):
+    """Selection of the next batch overlaps the previous flushes: same bookkeeping with one, two or three
+    flushes in flight (results are collected oldest first; every leaf keeps its virtual loss until then)."""
     log = []
     t = Session(host, m.GAME_TICTACTOE, np.zeros((), dtype=m.TSTATE_DTYPE), rollouts_per_leaf=8, leaves_per_flush=16,
                 callback=oracle_backend(port, log=log))
-    t.set_overlap(True)
+    t.set_overlap(in_flight)
     t.grow(1000)                       # 62 full flushes + one of 8 leaves
     r = t.root_stats()
     assert r["sims"] == 1000 * 8 and r["size"] == 1000
@@ -183,9 +185,12 @@ def test_config1_tictactoe_on_gpu_backend(host):
 
 
 @pytest.mark.gpu
-def test_config4_quoridor_selfplay_flush_on_gpu(host):
-    """BASELINE.json configs[3] shape: leaf-parallel flushes of 64k rollouts (K=16 leaves x R=4096)."""
+@pytest.mark.parametrize("in_flight", [0, 1, 2])
+def test_config4_quoridor_selfplay_flush_on_gpu(host, in_flight):
+    """BASELINE.json configs[3] shape: leaf-parallel flushes of 64k rollouts (K=16 leaves x R=4096), synchronous
+    or with one / two flushes queued on the GPU (two C-ABI handles = two streams)."""
     t = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=4096, leaves_per_flush=16)
+    t.set_overlap(in_flight)
     t.grow(160)
     r = t.root_stats()
     assert r["sims"] == 160 * 4096 and t.counters() == (10, 160 * 4096)
