@@ -129,7 +129,9 @@ def run_reference_arm(args, rank, world):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: Quoridor 9x9 opening position, REF policy rollouts (reference rollout())",
+        "config": {"workload": "configs[1]: Quoridor 9x9 opening position, independent REF-policy rollouts "
+                               "(the reference's rollout() as RolloutJobs on its JobScheduler; each step is a bounded sample of the workload)",
+                   "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)",
                    "sample_rollouts_per_step": sample_jobs, "host_threads": threads},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
                          "sample": "%d RolloutJobs per step on JobScheduler(%d), opening position, stock RNG" % (sample_jobs, threads)},
