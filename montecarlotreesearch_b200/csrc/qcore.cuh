@@ -149,51 +149,21 @@ MC_HD int q_winner(const QState &s) {
 // one BFS level of calculate_dists_from (Quoridor.cpp:80-104).
 // ------------------------------------------------------------------------------------------------
 #if defined(__CUDACC__)
-// 2^9, 2^1, 2^23, 2^31: kept in the constant bank so that ptxas cannot turn the multiplies below back into shifts
-static __constant__ uint32_t mc_shift_mul[4] = {1u << 9, 1u << 1, 1u << 23, 1u << 31};
+// 2^9, 2^1, 2^23, 2^31 (and 1): kept in the constant bank so that ptxas cannot turn the multiplies below back into shifts
+static __constant__ uint32_t mc_shift_mul[5] = {1u << 9, 1u << 1, 1u << 23, 1u << 31, 1u};
 #endif
 
 #if defined(__CUDA_ARCH__)
 __device__ __forceinline__ void mc_mulwide(uint32_t a, uint32_t b, uint32_t &lo, uint32_t &hi) {
     asm("{\n\t.reg .u64 t;\n\tmul.wide.u32 t, %2, %3;\n\tmov.b64 {%0, %1}, t;\n\t}" : "=r"(lo), "=r"(hi) : "r"(a), "r"(b));
 }
-// Device form of the step.  The straightforward version is 12 funnel shifts + 18 LOP3, all on the ALU
-// pipe, which issues at half the scheduler's rate.  Here every 81-bit shift is a 32x32->64 multiply by a
-// power of two (IMAD.WIDE on the FMA pipe: x * 2^N = {x << N, x >> (32-N)}), and the carries between
-// words are folded into the final 3-input ORs: 12 IMAD + 19 LOP3, the two pipes share the work.
-__device__ __forceinline__ B81 q_flood_step(B81 r, B81 oS, B81 oE) {
-    const uint32_t L9 = mc_shift_mul[0], L1 = mc_shift_mul[1], R9 = mc_shift_mul[2], R1 = mc_shift_mul[3];
-    uint32_t sa = r.a & oS.a, sb = r.b & oS.b, sc = r.c & oS.c;        // cells that may step south
-    uint32_t ea = r.a & oE.a, eb = r.b & oE.b, ec = r.c & oE.c;        // cells that may step east
-    uint32_t Sa_lo, Sa_hi, Sb_lo, Sb_hi, Ea_lo, Ea_hi, Eb_lo, Eb_hi;
-    mc_mulwide(sa, L9, Sa_lo, Sa_hi); mc_mulwide(sb, L9, Sb_lo, Sb_hi);
-    mc_mulwide(ea, L1, Ea_lo, Ea_hi); mc_mulwide(eb, L1, Eb_lo, Eb_hi);
-    uint32_t Sc = sc * L9, Ec = ec * L1;
-    uint32_t Na_lo, Na_hi, Nb_lo, Nb_hi, Nc_lo, Nc_hi, Wa_lo, Wa_hi, Wb_lo, Wb_hi, Wc_lo, Wc_hi;
-    mc_mulwide(r.a, R9, Na_lo, Na_hi); mc_mulwide(r.b, R9, Nb_lo, Nb_hi); mc_mulwide(r.c, R9, Nc_lo, Nc_hi);   // hi = x >> 9, lo = x << 23
-    mc_mulwide(r.a, R1, Wa_lo, Wa_hi); mc_mulwide(r.b, R1, Wb_lo, Wb_hi); mc_mulwide(r.c, R1, Wc_lo, Wc_hi);   // hi = x >> 1, lo = x << 31
-    (void)Na_lo; (void)Wa_lo;
-    B81 n;
-    n.a = r.a | Sa_lo | Ea_lo | ((Na_hi | Nb_lo) & oS.a) | ((Wa_hi | Wb_lo) & oE.a);
-    n.b = r.b | Sb_lo | Sa_hi | Eb_lo | Ea_hi | ((Nb_hi | Nc_lo) & oS.b) | ((Wb_hi | Wc_lo) & oE.b);
-    n.c = r.c | Sc | Sb_hi | Ec | Eb_hi | (Nc_hi & oS.c) | (Wc_hi & oE.c);
-    return n;
-}
-#else
-MC_HD B81 q_flood_step(B81 r, B81 oS, B81 oE) {
-    B81 south = shl<9>(r & oS);           // x -> x+1
-    B81 north = shr<9>(r) & oS;           // x -> x-1 : the cell above must have an open south edge
-    B81 east  = shl<1>(r & oE);           // y -> y+1
-    B81 west  = shr<1>(r) & oE;           // y -> y-1
-    return b81(r.a | south.a | north.a | east.a | west.a,
-               r.b | south.b | north.b | east.b | west.b,
-               r.c | south.c | north.c | east.c | west.c);
-}
 #endif
 
-// The same expansion with the edge boards prepared once per search: oS9 = oS << 9 and oE1 = oE << 1 mask
-// the shifted board AFTER the shift ((r & m) << k == (r << k) & (m << k)), so every mask folds into the
-// 3-input ORs that merge the word carries: 12 IMAD + 16 LOP3, and the multiplies read r directly.
+// The edge boards are prepared once per search: oS9 = oS << 9 and oE1 = oE << 1 mask the shifted board AFTER
+// the shift ((r & m) << k == (r << k) & (m << k)), so the multiplies read r directly and every mask folds into
+// one (shifted & mask) | accumulated LOP3.  On the device every 81-bit shift is a 32x32->64 multiply by a power
+// of two (IMAD.WIDE on the FMA pipe: x * 2^N = {x << N, x >> (32-N)}); the straightforward version is 12 funnel
+// shifts + 18 LOP3, all on the ALU pipe, which issues at half the scheduler's rate.
 struct QFloodMasks { B81 oS, oE, oS9, oE1; };
 
 MC_HD QFloodMasks q_flood_masks(B81 oS, B81 oE) {
@@ -202,20 +172,43 @@ MC_HD QFloodMasks q_flood_masks(B81 oS, B81 oE) {
 }
 
 #if defined(__CUDA_ARCH__)
+// a + b for DISJOINT bit sets (= a | b), forced onto the FMA pipe as a * 1 + b with the 1 read from the constant bank
+__device__ __forceinline__ uint32_t mc_join(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(mc_shift_mul[4]), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t mc_madlo(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// (x & mask) | acc as ONE LOP3 (ptxas otherwise peels the first AND and the last OR off the chain)
+__device__ __forceinline__ uint32_t mc_andor(uint32_t x, uint32_t mask, uint32_t acc) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xf8;" : "=r"(d) : "r"(acc), "r"(x), "r"(mask));   // LUT 0xf8 = a | (b & c)
+    return d;
+}
+// The word carries of a multi-word shift never overlap the bits shifted within the word, so they are joined
+// by ADDITION on the FMA pipe (IMAD) instead of by OR on the half-rate ALU pipe: 18 IMAD + 12 LOP3, each LOP3
+// being (shifted & mask) | accumulated.
 __device__ __forceinline__ B81 q_flood_step(B81 r, const QFloodMasks &m) {
     const uint32_t L9 = mc_shift_mul[0], L1 = mc_shift_mul[1], R9 = mc_shift_mul[2], R1 = mc_shift_mul[3];
     uint32_t Sa_lo, Sa_hi, Sb_lo, Sb_hi, Ea_lo, Ea_hi, Eb_lo, Eb_hi;
     mc_mulwide(r.a, L9, Sa_lo, Sa_hi); mc_mulwide(r.b, L9, Sb_lo, Sb_hi);
     mc_mulwide(r.a, L1, Ea_lo, Ea_hi); mc_mulwide(r.b, L1, Eb_lo, Eb_hi);
-    uint32_t Sc = r.c * L9, Ec = r.c * L1;
+    const uint32_t Sb = mc_join(Sb_lo, Sa_hi), Sc = mc_madlo(r.c, L9, Sb_hi);
+    const uint32_t Eb = mc_join(Eb_lo, Ea_hi), Ec = mc_madlo(r.c, L1, Eb_hi);
     uint32_t Na_lo, Na_hi, Nb_lo, Nb_hi, Nc_lo, Nc_hi, Wa_lo, Wa_hi, Wb_lo, Wb_hi, Wc_lo, Wc_hi;
     mc_mulwide(r.a, R9, Na_lo, Na_hi); mc_mulwide(r.b, R9, Nb_lo, Nb_hi); mc_mulwide(r.c, R9, Nc_lo, Nc_hi);
     mc_mulwide(r.a, R1, Wa_lo, Wa_hi); mc_mulwide(r.b, R1, Wb_lo, Wb_hi); mc_mulwide(r.c, R1, Wc_lo, Wc_hi);
     (void)Na_lo; (void)Wa_lo;
+    const uint32_t Na = mc_join(Na_hi, Nb_lo), Nb = mc_join(Nb_hi, Nc_lo);
+    const uint32_t Wa = mc_join(Wa_hi, Wb_lo), Wb = mc_join(Wb_hi, Wc_lo);
     B81 n;
-    n.a = r.a | (Sa_lo & m.oS9.a) | (Ea_lo & m.oE1.a) | ((Na_hi | Nb_lo) & m.oS.a) | ((Wa_hi | Wb_lo) & m.oE.a);
-    n.b = r.b | ((Sb_lo | Sa_hi) & m.oS9.b) | ((Eb_lo | Ea_hi) & m.oE1.b) | ((Nb_hi | Nc_lo) & m.oS.b) | ((Wb_hi | Wc_lo) & m.oE.b);
-    n.c = r.c | ((Sc | Sb_hi) & m.oS9.c) | ((Ec | Eb_hi) & m.oE1.c) | (Nc_hi & m.oS.c) | (Wc_hi & m.oE.c);
+    n.a = mc_andor(Wa, m.oE.a, mc_andor(Na, m.oS.a, mc_andor(Ea_lo, m.oE1.a, mc_andor(Sa_lo, m.oS9.a, r.a))));
+    n.b = mc_andor(Wb, m.oE.b, mc_andor(Nb, m.oS.b, mc_andor(Eb, m.oE1.b, mc_andor(Sb, m.oS9.b, r.b))));
+    n.c = mc_andor(Wc_hi, m.oE.c, mc_andor(Nc_hi, m.oS.c, mc_andor(Ec, m.oE1.c, mc_andor(Sc, m.oS9.c, r.c))));
     return n;
 }
 #else
@@ -234,8 +227,9 @@ MC_HD int q_flood_dist(B81 oS, B81 oE, int start, int player, QWork *wk) {
     const uint32_t ga = player ? MCTSB_GOAL_B_A : 0u, gc = player ? 0u : MCTSB_GOAL_W_C;
     if (wk) wk->flood_queries++;
     if ((r.a & ga) | (r.c & gc)) return 0;
+    const QFloodMasks fm = q_flood_masks(oS, oE);
     for (int d = 1;; d++) {
-        B81 n = q_flood_step(r, oS, oE);
+        B81 n = q_flood_step(r, fm);
         if (wk) wk->flood_steps++;
         if ((n.a & ga) | (n.c & gc)) return d;
         if (b81_eq(n, r)) return -1;
@@ -520,11 +514,12 @@ MC_HD QCut q_cut_masks(const QState &s, int player, Layers &ls, QWork *wk) {
     const B81 oS = s.openS, oE = s.openE;
     if (wk) wk->flood_queries++;
     // 1. layers from the goal row
+    const QFloodMasks fm = q_flood_masks(oS, oE);
     B81 reached = goal;
     int d = 0;
     bool found = b81_any(pawn & goal), dead = false;
     while (!found && !dead) {
-        B81 grown = q_flood_step(reached, oS, oE);
+        B81 grown = q_flood_step(reached, fm);
         B81 layer = andn(grown, reached);
         if (wk) wk->flood_steps++;
         d++;
