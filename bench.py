@@ -39,7 +39,7 @@ UNIT = "rollouts/s"
 ALG_OPS_PER_ROLLOUT = 13133.3 * 24 + 4532.6 * 12 + 49.1 * 200
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
 # algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
-NCU_DRAM_BYTES_PER_LAUNCH = 815872 + 1320960   # profiles/r01_final_lockstep.md (ncu, one launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 818944 + 520704   # profiles/r01_final_lockstep.md (ncu, one launch)
 
 
 class ClockSampler:
@@ -324,7 +324,7 @@ def main():
                      "alu_pipe_lop3_peak": lop3_peak / 1e12, "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
                      "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3 + integer-add chains on all SMs, both pipes; alu_pipe_lop3_peak = LOP3 only); "
                              "achieved = rollouts/s x the REFERENCE algorithm's integer work per rollout (DESIGN.md 5); executed "
-                             "thread instructions per second from ncu are in profiles/ (18.1 T/s = 0.52 of this peak)"},
+                             "thread instructions per second from ncu are in profiles/ (18.7 T/s = 0.54 of this peak)"},
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world},
         "gpu_launches": int(launches),
