@@ -13,14 +13,22 @@ void mcts_set_verbose(bool on) { g_verbose = on; }
 
 /*** MCTS_node ***/
 
-// reference mcts.cpp:15-21 — actions and terminal flag are computed eagerly; the node owns state, move,
-// children and whatever stays in untried_actions (mcts.cpp:23-35)
+// reference mcts.cpp:15-21; the node owns state, move, children and whatever stays in untried_actions
+// (mcts.cpp:23-35).  The reference fills untried_actions in the constructor; here the list is generated the
+// first time the node is asked for it — same list, same order, but a leaf at the fringe of the tree (most
+// nodes: they are played out once and never selected again) never pays for move generation.
 MCTS_node::MCTS_node(MCTS_node *parent, MCTS_state *state, const MCTS_move *move, MCTS_tree *tree)
     : terminal(false), size(0), number_of_simulations(0), score(0.0), state(state), move(move),
       children(new vector<MCTS_node *>()), parent(parent), untried_actions(NULL), tree(tree), virtual_visits(0) {
-    children->reserve(STARTING_NUMBER_OF_CHILDREN);
-    untried_actions = state->actions_to_try();
     terminal = state->is_terminal();
+}
+
+queue<MCTS_move *> *MCTS_node::actions() const {
+    if (untried_actions == NULL) {
+        untried_actions = state->actions_to_try();
+        children->reserve(STARTING_NUMBER_OF_CHILDREN);
+    }
+    return untried_actions;
 }
 
 MCTS_node::~MCTS_node() {
@@ -28,11 +36,13 @@ MCTS_node::~MCTS_node() {
     delete move;
     for (MCTS_node *c : *children) delete c;
     delete children;
-    while (!untried_actions->empty()) { delete untried_actions->front(); untried_actions->pop(); }
-    delete untried_actions;
+    if (untried_actions != NULL) {
+        while (!untried_actions->empty()) { delete untried_actions->front(); untried_actions->pop(); }
+        delete untried_actions;
+    }
 }
 
-bool MCTS_node::is_fully_expanded() const { return terminal || untried_actions->empty(); }   // mcts.cpp:92-94
+bool MCTS_node::is_fully_expanded() const { return terminal || actions()->empty(); }   // mcts.cpp:92-94
 bool MCTS_node::is_terminal() const { return terminal; }
 unsigned int MCTS_node::get_size() const { return size; }
 const MCTS_move *MCTS_node::get_move() const { return move; }
@@ -40,7 +50,7 @@ const MCTS_state *MCTS_node::get_current_state() const { return state; }
 
 // Expansion only: pop the FRONT of the FIFO (children appear in actions_to_try order, mcts.cpp:46-54)
 MCTS_node *MCTS_node::expand_no_rollout() {
-    if (terminal || untried_actions->empty()) return NULL;
+    if (terminal || actions()->empty()) return NULL;
     MCTS_move *next_move = untried_actions->front();
     untried_actions->pop();
     MCTS_state *next = state->next_state(next_move);

@@ -47,10 +47,11 @@ class MCTS_node {
     const MCTS_move *move;
     vector<MCTS_node *> *children;
     MCTS_node *parent;
-    queue<MCTS_move *> *untried_actions;
+    mutable queue<MCTS_move *> *untried_actions;   // generated on first use (actions())
     MCTS_tree *tree;                       // owner (batching parameters, backend, rollout ids); may be NULL
     unsigned int virtual_visits;           // pending simulations counted as losses while a flush is in flight
     void backpropagate(double w, int n);
+    queue<MCTS_move *> *actions() const;
     void add_virtual(int n);
     MCTS_node *expand_no_rollout();        // Expansion without Simulation; NULL when nothing to expand
 public:
