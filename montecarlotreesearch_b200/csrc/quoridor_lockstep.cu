@@ -14,8 +14,7 @@ __global__ void __launch_bounds__(LS_THREADS, LS_BLOCKS_PER_SM) quoridor_lockste
     lockstep_body<REPLAY>(p, work_counter, smem);
 }
 
-static constexpr size_t LS_SMEM = (size_t)MCTSB_MAX_LAYERS * 3 * LS_THREADS * sizeof(uint32_t)      // layers
-                                  + (size_t)LS_THREADS * sizeof(unsigned long long);                 // best slots
+static constexpr size_t LS_SMEM = (size_t)LS_SMEM_WORDS * sizeof(uint32_t);
 
 cudaError_t launch_quoridor_lockstep(const RolloutParams &p, bool replay, unsigned long long *work_counter, cudaStream_t st) {
     if (p.n_rollouts == 0) return cudaSuccess;

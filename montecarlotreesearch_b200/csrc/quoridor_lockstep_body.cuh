@@ -31,6 +31,16 @@
 #include <string.h>
 #define LS_DEV inline
 #define LS_NOINLINE
+#if defined(MCTSB_EMU_WARP32)                            // tests/hostemu/simt.h: 32 fibers per warp, real votes and shuffles
+#define LS_ANY(x) simt::any((x), __LINE__)
+#define LS_BALLOT(x) simt::ballot((x), __LINE__)
+#define LS_SHFL(v, l) simt::shfl((v), (l), __LINE__)
+#define LS_SHFL_UP(v, o) simt::shfl_up((v), (o), __LINE__)
+#define LS_REDUCE_ADD(v) simt::reduce_add((v), __LINE__)
+#define LS_SYNCWARP() simt::syncwarp(__LINE__)
+#define LS_WARP 32
+#define LS_TID simt::tid()
+#else
 #define LS_ANY(x) (x)
 #define LS_BALLOT(x) ((x) ? 1u : 0u)
 #define LS_SHFL(v, l) (v)
@@ -38,13 +48,14 @@
 #define LS_REDUCE_ADD(v) (v)
 #define LS_SYNCWARP()
 #define LS_WARP 1
+#define LS_TID 0
+#endif
 #define LS_ATOMIC_MAX(p, v) do { if (*(p) < (v)) *(p) = (v); } while (0)
 #define LS_POPC(x) __builtin_popcount(x)
 #define LS_FFS(x) __builtin_ffs((int)(x))
 #define LS_HIBIT(x) (31 - __builtin_clz(x))
 #define LS_UMULHI(a, b) mulhi_u32(a, b)
 #define LS_LDG(p) (*(p))
-#define LS_TID 0
 #define LS_ATOMIC_ADD(p, v) ls_emu_add(p, v)
 static inline unsigned long long ls_emu_add(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p += v; return o; }
 #define LS_D2ULL(x) ((unsigned long long)(x))
@@ -81,6 +92,8 @@ namespace mctsb {
 static constexpr int LS_THREADS = 128;
 static constexpr int LS_SHARE = 32;                     // candidates one lane may queue per batch
 static constexpr int LS_QCAP = 32 * LS_SHARE;           // queue entries per warp
+// dynamic shared memory of a block, in words: [layers, overlaid by the task queues during P5][best slots: one u64 per thread]
+static constexpr int LS_SMEM_WORDS = MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS;
 
 // per-warp shared scratch of the candidate phase.  The task queue lives in the warp's own columns of the
 // layer area (rows of 32 entries, row stride LS_THREADS words): the layers are dead once the trace is done

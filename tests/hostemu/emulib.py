@@ -9,8 +9,9 @@ from .build import build
 
 
 class EmuLib:
-    def __init__(self):
-        self.lib = L = C.CDLL(build())
+    def __init__(self, warp32=False):
+        """warp32=True: the build whose lockstep body runs on emulated 32-lane warps (simt.h fibers)."""
+        self.lib = L = C.CDLL(build(warp32=warp32))
         vp = C.c_void_p
         L.emu_q_primitives.argtypes = [vp] * 6
         L.emu_q_sp_with_wall.argtypes = [vp, C.c_int, C.c_int]
@@ -23,7 +24,7 @@ class EmuLib:
         L.emu_t_rollout_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, vp]
         L.emu_t_rollout_streams.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]
         L.emu_t_winner.argtypes = [C.c_uint32, C.c_uint32]
-        L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp]
+        L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int]
 
     def q_primitives(self, s):
         a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
@@ -102,8 +103,9 @@ class EmuLib:
         self.lib.emu_t_rollout_streams(a.ctypes.data, a.size, st.ctypes.data, st.shape[1], st.shape[1], out.ctypes.data)
         return out
 
-    def lockstep(self, states, R, seed, first_id, streams=None):
-        """The production kernel body with a one-lane warp: Philox mode (streams=None) or replay."""
+    def lockstep(self, states, R, seed, first_id, streams=None, blocks=1):
+        """The production kernel body on the host (one-lane warp, or `blocks` emulated thread blocks of 32-lane
+        warps in the warp32 build): Philox mode (streams=None) or replay."""
         from oracle.reflib import LEAFSUM_DTYPE
         a = np.ascontiguousarray(states, dtype=QSTATE_DTYPE).reshape(-1)
         if streams is not None:
@@ -118,5 +120,5 @@ class EmuLib:
         sums = np.zeros(a.size, dtype=LEAFSUM_DTYPE)
         ctr = np.zeros(4, dtype=np.uint64)
         self.lib.emu_lockstep(a.ctypes.data, a.size, R, seed, first_id, sp, sl, ss, out.ctypes.data, fin.ctypes.data,
-                              sums.ctypes.data, ctr.ctypes.data)
+                              sums.ctypes.data, ctr.ctypes.data, blocks)
         return out, fin, sums, ctr

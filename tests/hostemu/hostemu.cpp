@@ -2,6 +2,9 @@
 // so that the kernel logic can be checked bit-for-bit against the oracle on a machine without a
 // GPU.  It is built by tests/hostemu/build.py into tests/hostemu/_hostemu.so, is never linked
 // into the product library and is not reachable through the C ABI.
+#if defined(MCTSB_EMU_WARP32)
+#include "simt.h"
+#endif
 #include "../../montecarlotreesearch_b200/csrc/qcore.cuh"
 #include "../../montecarlotreesearch_b200/csrc/ttt_core.cuh"
 #include "../../montecarlotreesearch_b200/csrc/quoridor_lockstep_body.cuh"
@@ -110,10 +113,21 @@ int emu_t_rollout_streams(const mctsb_tstate *st, int n, const uint32_t *streams
 int emu_t_winner(uint32_t x, uint32_t o) { return t_winner(x & 0x1ff, o & 0x1ff); }
 
 
-// The production lockstep kernel body run with a one-lane warp (see quoridor_lockstep_body.cuh).
+// The production lockstep kernel body on the host: with a one-lane warp (votes and shuffles are the identity),
+// or — built with -DMCTSB_EMU_WARP32 — on `blocks` emulated thread blocks of LS_THREADS fibers each
+// (tests/hostemu/simt.h: real 32-lane votes, shuffles, shared-memory queues and the global work counter).
+#if defined(MCTSB_EMU_WARP32)
+struct EmuLaunch { RolloutParams p; unsigned long long *work; std::vector<std::vector<uint32_t>> *smem; bool replay; };
+static void emu_thread(void *a) {
+    EmuLaunch *L = (EmuLaunch *)a;
+    uint32_t *sm = (*L->smem)[simt::block()].data();
+    if (L->replay) lockstep_body<true>(L->p, L->work, sm); else lockstep_body<false>(L->p, L->work, sm);
+}
+#endif
+
 int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t seed, uint64_t first_id,
                  const uint32_t *streams, uint32_t stream_len, uint32_t stream_stride,
-                 mctsb_outcome *out, mctsb_qstate *finals, mctsb_leaf_sum *sums, uint64_t *counters4) {
+                 mctsb_outcome *out, mctsb_qstate *finals, mctsb_leaf_sum *sums, uint64_t *counters4, int blocks) {
     RolloutParams p; memset(&p, 0, sizeof p);
     p.states = states; p.n_leaves = (uint32_t)n_leaves; p.rollouts_per_leaf = R; p.n_rollouts = (uint64_t)n_leaves * R;
     p.seed = seed; p.first_rollout_id = first_id; p.streams = streams; p.stream_len = stream_len; p.stream_stride = stream_stride;
@@ -121,12 +135,22 @@ int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t 
     unsigned long long ctr[4] = {0, 0, 0, 0};
     p.counters = ctr;
     if (sums) memset(sums, 0, sizeof(mctsb_leaf_sum) * (size_t)n_leaves);
-    std::vector<uint32_t> smem((size_t)MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS + 64);
     unsigned long long work = 0;
+#if defined(MCTSB_EMU_WARP32)
+    if (blocks < 1) blocks = 1;
+    std::vector<std::vector<uint32_t>> smem((size_t)blocks, std::vector<uint32_t>(LS_SMEM_WORDS + 64, 0xdeadbeefu));
+    EmuLaunch L; L.p = p; L.work = &work; L.smem = &smem; L.replay = streams != nullptr;
+    simt::launch(blocks, LS_THREADS, emu_thread, &L);
+#else
+    (void)blocks;
+    std::vector<uint32_t> smem(LS_SMEM_WORDS + 64);
     if (streams) lockstep_body<true>(p, &work, smem.data());
     else lockstep_body<false>(p, &work, smem.data());
+#endif
     if (counters4) for (int i = 0; i < 4; i++) counters4[i] = ctr[i];
     return 0;
 }
+
+int emu_warp_width() { return LS_WARP; }
 
 }  // extern "C"

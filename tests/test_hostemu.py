@@ -136,3 +136,52 @@ def test_long_paths_overflow_the_layer_budget(emu, port):
         assert exp.tobytes() == out.tobytes() and efin.tobytes() == fin.tobytes()
         e = emu.q_primitives(s)
         assert (e["legal"] == p["legal"]).all() and e["sp_white"] == p["sp_white"] and e["sp_black"] == p["sp_black"]
+
+
+# ---- the same body on emulated 32-lane warps (tests/hostemu/simt.h): votes, shuffles, the shared task queue,
+# ---- the atomicMax fold and the global work counter are real here ----------------------------------------
+@pytest.fixture(scope="module")
+def emu32():
+    from tests.hostemu.emulib import EmuLib
+    e = EmuLib(warp32=True)
+    assert e.lib.emu_warp_width() == 32
+    return e
+
+
+def test_lockstep_warp32_vs_reference_golden(emu32, corpus):
+    g = golden("golden_q_opening.npz")
+    out, _, sums, _ = emu32.lockstep(opening_state(), 512, int(g["seed"]), 0, blocks=2)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    assert int(sums["n"][0]) == 512
+    g = golden("golden_q_replay.npz")
+    streams = np.stack([philox_stream(int(g["seed"]), int(i), 16384) for i in g["id"]])
+    out, fin, _, _ = emu32.lockstep(corpus[g["index"]], 1, 0, 0, streams=streams, blocks=1)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    assert fin.tobytes() == g["final"].tobytes()
+
+
+def test_lockstep_warp32_ragged_mixed_leaves(emu32, port, corpus):
+    """Leaves change inside a warp (7 rollouts per leaf, 33+ distinct leaves per warp boundary), mid-game positions
+    next to terminal and wall-less ones, three blocks racing for the work counter: every playout and every
+    exact leaf sum equals the oracle's."""
+    rng = np.random.default_rng(23)
+    idx = rng.choice(len(corpus), 150, replace=False)
+    st = corpus[idx].copy()
+    st[5]["wx"] = 8                      # a terminal leaf in the middle of a warp
+    st[40]["wwalls"] = 0; st[40]["bwalls"] = 0
+    out, fin, sums, _ = emu32.lockstep(st, 7, 777, 31, blocks=3)
+    for j in range(len(st)):
+        exp, efin, _ = port.q_rollout_philox(st[j], 777, 31 + 7 * j, 7, finals=True)
+        assert exp.tobytes() == out[7 * j: 7 * j + 7].tobytes() and efin.tobytes() == fin[7 * j: 7 * j + 7].tobytes()
+        acc, _ = port.leaf_sum(exp["score"])
+        assert (int(acc["lo"]), int(acc["hi"]), int(acc["n"])) == (int(sums["lo"][j]), int(sums["hi"][j]), int(sums["n"][j]))
+
+
+def test_lockstep_warp32_long_paths(emu32, port):
+    from tests.util import serpentine_state
+    s = serpentine_state(turn=0)
+    exp, efin, _ = port.q_rollout_philox(s, 5, 0, 96, finals=True)
+    out, fin, _, _ = emu32.lockstep(s, 96, 5, 0, blocks=1)
+    assert exp.tobytes() == out.tobytes() and efin.tobytes() == fin.tobytes()
