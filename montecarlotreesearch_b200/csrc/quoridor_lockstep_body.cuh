@@ -92,8 +92,10 @@ namespace mctsb {
 static constexpr int LS_THREADS = 128;
 static constexpr int LS_SHARE = 32;                     // candidates one lane may queue per batch
 static constexpr int LS_QCAP = 32 * LS_SHARE;           // queue entries per warp
-// dynamic shared memory of a block, in words: [layers, overlaid by the task queues during P5][best slots: one u64 per thread]
-static constexpr int LS_SMEM_WORDS = MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS;
+// dynamic shared memory of a block, in words:
+// [layers of search A, overlaid by the task queues during P5][best slots: one u64 per thread][ring: last three reach sets of search B]
+static constexpr int LS_RING = 3;
+static constexpr int LS_SMEM_WORDS = MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS + (LS_RING + 1) * 3 * LS_THREADS;   // ring + one scratch slot
 
 // per-warp shared scratch of the candidate phase.  The task queue lives in the warp's own columns of the
 // layer area (rows of 32 entries, row stride LS_THREADS words): the layers are dead once the trace is done
@@ -114,6 +116,8 @@ struct SmemLayers {
         return b81(base[(3 * j + 0) * LS_THREADS], base[(3 * j + 1) * LS_THREADS], base[(3 * j + 2) * LS_THREADS]);
     }
 };
+
+LS_DEV uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
 
 LS_DEV mctsb_qstate ls_load_qstate(const void *base, uint32_t idx) {
     const uint4 *p = reinterpret_cast<const uint4 *>(base) + 2ull * idx;
@@ -204,25 +208,31 @@ template <> struct LaneDraws<true> {
 };
 
 // Flood fills of all lanes that have one pending, in one converged loop (a pawn-rooted search
-// with early exit, as q_flood_dist).  `go` lanes search from `start` to `player`'s goal row.
+// with early exit, as q_flood_dist).  `go` lanes search from `start` to `player`'s goal row.  A trip of the
+// loop makes TWO expansions and tests once: reach sets only grow, so a goal row reached by the first
+// expansion is still reached after the second, and a search that stopped growing shows as n2 == n1.
+// Finished lanes keep stepping (their result is already recorded).
 LS_DEV int warp_flood(bool go, B81 oS, B81 oE, int start, int player, QWork &wk) {
     const QFloodMasks fm = q_flood_masks(oS, oE);
     B81 r = b81_bit(go ? start : 0);
     const uint32_t ga = player ? MCTSB_GOAL_B_A : 0u, gc = player ? 0u : MCTSB_GOAL_W_C;
     bool busy = go && ((r.a & ga) | (r.c & gc)) == 0u;
-    uint32_t d = 0;                                        // expansions this lane made while still searching
+    int d = (go && !busy) ? 0 : -1;                        // expansions to the goal row, -1 = walled off (or idle lane)
+    int j = 0;                                             // warp-uniform: expansions made so far
     if (go) wk.flood_queries++;
-    LS_UNROLL2
+    LS_UNROLL1
     while (LS_ANY(busy)) {
-        const B81 n = q_flood_step(r, fm);
-        const bool hit = ((n.a & ga) | (n.c & gc)) != 0u;
-        const bool stuck = ((n.a ^ r.a) | (n.b ^ r.b) | (n.c ^ r.c)) == 0u;
-        d += busy ? 1u : 0u;
-        busy = busy && !hit && !stuck;
-        r = n;                                         // finished lanes keep stepping: a reached goal row stays reached
+        const B81 n1 = q_flood_step(r, fm);
+        const B81 n2 = q_flood_step(n1, fm);
+        const bool hit1 = ((n1.a & ga) | (n1.c & gc)) != 0u, hit2 = ((n2.a & ga) | (n2.c & gc)) != 0u;
+        const bool stuck = b81_eq(n2, n1);
+        j += 2;
+        if (busy && hit2) d = hit1 ? j - 1 : j;
+        busy = busy && !hit2 && !stuck;
+        r = n2;
     }
-    wk.flood_steps += d;
-    return (go && ((r.a & ga) | (r.c & gc)) != 0u) ? (int)d : -1;
+    if (d > 0) wk.flood_steps += (uint32_t)d;
+    return d;
 }
 
 // step-target distance fields: 8 bits per candidate slot, three words
@@ -240,11 +250,13 @@ template <bool REPLAY>
 LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_counter, uint32_t *smem) {
     const int lane = LS_TID & 31, warp = LS_TID >> 5;
     SmemLayers ls; ls.base = smem + LS_TID;
+    SmemLayers ring;
     WarpBuf wb;
-    {   // layout: [layers, overlaid by the task queues during P5][best slots: 32 x u64 per warp]
+    {   // layout: [layers, overlaid by the task queues during P5][best slots: 32 x u64 per warp][ring of search B]
         uint32_t *after = smem + MCTSB_MAX_LAYERS * 3 * LS_THREADS;
         wb.best = reinterpret_cast<unsigned long long *>(after) + 32 * warp;
         wb.qbase = smem + 32 * warp;
+        ring.base = after + 2 * LS_THREADS + LS_TID;
     }
 
     QState s; LaneDraws<REPLAY> d;
@@ -318,39 +330,47 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             const B81 pawn_a = b81_bit(cell_a), pawn_b = b81_bit(cell_b);
             B81 ra = goal_a, rb = goal_b;
             const QFloodMasks fm = q_flood_masks(s.openS, s.openE);
-            B81 rb1 = b81(0u, 0u, 0u), rb2 = b81(0u, 0u, 0u);  // search B one and two expansions ago
-            bool busy_a = playing || capped, busy_b = busy_a;
-            if (busy_a) {
-                wk.flood_queries += 2;
-                if (b81_any(pawn_a & goal_a)) { sp_a = 0; busy_a = false; }
-                if (b81_any(pawn_b & goal_b)) { sp_b = 0; busy_b = false; }
-            }
-            int j = 0;
+            // One loop for both searches, no lane-private branches.  da / db: 0xffffffff while the search is still
+            // looking for its pawn, then the number of expansions it took (an unsigned minimum keeps the first
+            // hit); lanes with nothing to search start at 0.  A lane whose search has ended keeps stepping: what it
+            // writes afterwards lands in slots nobody reads.  Search A stores every layer in the lane's column;
+            // search B stores its reach set in a ring of three while it is still looking (afterwards: in a fourth,
+            // scratch slot) — the distances of the step targets are read off the last three below.  A pawn that is
+            // walled off (never in a legal position, but callers may hand in anything) ends with the trip cap:
+            // 81 expansions exhaust every board.
+            const bool searching = playing || capped;
+            uint32_t da = (searching && !b81_any(pawn_a & goal_a)) ? 0xffffffffu : 0u;
+            uint32_t db = (searching && !b81_any(pawn_b & goal_b)) ? 0xffffffffu : 0u;
+            if (searching) wk.flood_queries += 2;
+            ring.put(0, goal_b);
+            uint32_t j = 0; int slot = 0;                      // warp-uniform: expansions so far, ring slot of R_j
             LS_UNROLL1
-            while (LS_ANY(busy_a || busy_b)) {
-                j++;
-                if (busy_a) {
-                    B81 grown = q_flood_step(ra, fm);
-                    B81 layer = andn(grown, ra);
-                    wk.flood_steps++;
-                    if (want_cut && !overflow_a) { if (j < MCTSB_MAX_LAYERS) ls.put(j, layer); else overflow_a = true; }
-                    ra = grown;
-                    if (b81_any(layer & pawn_a)) { sp_a = j; busy_a = false; }
-                    else if (!b81_any(layer)) busy_a = false;  // walled off: sp stays -1 (never in a legal position)
-                }
-                if (busy_b) {
-                    B81 grown = q_flood_step(rb, fm);
-                    wk.flood_steps++;
-                    if (b81_any(grown & pawn_b)) { sp_b = j; busy_b = false; }
-                    else if (b81_eq(grown, rb)) busy_b = false;    // exhausted
-                    rb2 = rb1; rb1 = rb; rb = grown;
-                }
+            while (LS_ANY((int)(da | db) < 0) && j < 81u) {
+                j++; slot = slot == LS_RING - 1 ? 0 : slot + 1;
+                const B81 grown_a = q_flood_step(ra, fm);
+                const B81 layer = andn(grown_a, ra);
+                if (j < MCTSB_MAX_LAYERS) ls.put((int)j, layer);
+                da = umin32(da, b81_any(layer & pawn_a) ? j : 0xffffffffu);
+                ra = grown_a;
+                const B81 grown_b = q_flood_step(rb, fm);
+                ring.put((int)db < 0 ? slot : LS_RING, grown_b);
+                db = umin32(db, b81_any(grown_b & pawn_b) ? j : 0xffffffffu);
+                rb = grown_b;
             }
+            if (searching) { sp_a = (int)da; sp_b = (int)db; }   // -1: walled off
+            if (sp_a > 0) wk.flood_steps += (uint32_t)sp_a;
+            if (sp_b > 0) wk.flood_steps += (uint32_t)sp_b;
+            overflow_a = sp_a >= MCTSB_MAX_LAYERS;
             // Distances of the legal step targets (get_best_step_move measures each with its own BFS,
             // Quoridor.cpp:476-497).  A target is one or two moves from the pawn, so its distance is within
             // two of the pawn's: rb2, rb1, rb and one more expansion are the cells within sp-2 .. sp+1.
             if (LS_ANY(steps != 0u)) {
-                const B81 rb_next = q_flood_step(rb, fm);
+                const B81 z = b81(0u, 0u, 0u);
+                const int spb = sp_b < 0 ? 0 : sp_b;
+                const B81 rb0 = ring.get(spb % LS_RING);                      // cells within sp_b of the goal row
+                const B81 rb1 = spb >= 1 ? ring.get((spb + 2) % LS_RING) : z;  // within sp_b - 1
+                const B81 rb2 = spb >= 2 ? ring.get((spb + 1) % LS_RING) : z;  // within sp_b - 2
+                const B81 rb_next = q_flood_step(rb0, fm);
                 LS_UNROLL1
                 for (uint32_t m = steps; LS_ANY(m != 0u); m &= m - 1u) {
                     if (m) {
@@ -358,7 +378,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                         uint32_t dist = 0xffu;
                         if (sp_b >= 0)
                             dist = b81_test(rb2, t) ? (uint32_t)(sp_b - 2) : b81_test(rb1, t) ? (uint32_t)(sp_b - 1)
-                                 : b81_test(rb, t) ? (uint32_t)sp_b : b81_test(rb_next, t) ? (uint32_t)(sp_b + 1) : (uint32_t)(sp_b + 2);
+                                 : b81_test(rb0, t) ? (uint32_t)sp_b : b81_test(rb_next, t) ? (uint32_t)(sp_b + 1) : (uint32_t)(sp_b + 2);
                         td_or(td0, td1, td2, i, dist);
                     }
                 }

@@ -136,7 +136,7 @@ int main(int argc, char **argv) {
     mctsb_qstate open; memset(&open, 0, sizeof open); open.wx = 0; open.wy = 4; open.bx = 8; open.by = 4; open.wwalls = open.bwalls = 10;
     // accumulators, per ply-trip of a warp
     double trips = 0;
-    double p2_cur = 0, p2_seq = 0, p2_sum_lane = 0, p2_lanes = 0;
+    double p2_cur = 0, p2_seq = 0, p2_sum_lane = 0, p2_lanes = 0, p2_ma = 0, p2_mb = 0, p2_mn = 0;
     double p2_cached_cur = 0, p2_cached_seq = 0; double xa = 0, xb = 0, xa_l = 0, xb_l = 0, xa_n = 0, xb_n = 0, xtrips_a = 0, xtrips_b = 0, xb_wall = 0, xb_nowall = 0; double st_norm = 0, st_build = 0, st_fastplies = 0, st_allfast = 0, st_lanes_fast = 0, st_lanes = 0; double cls[4] = {0,0,0,0}; double st2_norm = 0, st2_build = 0, st2_allfast = 0;   // searches skipped for lanes whose walls did not change (goal fields valid)
     double tr_cur = 0, tr_need = 0, tr_lane_sum = 0;
     double s1_trips = 0, s1_steps = 0, s1_tasks = 0, s1_lane_steps = 0;
@@ -169,13 +169,13 @@ int main(int argc, char **argv) {
                 q_play_encoded(s[l], mv); plies[l]++;
             }
             // ---- P2
-            int mx = 0, mxs = 0, cmx = 0, cmxs = 0;
+            int mx = 0, mxs = 0, cmx = 0, cmxs = 0, xma = 0, xmb = 0;
             for (int l = 0; l < 32; l++) if (L[l].playing || L[l].mode == -1) {
                 int a = std::max(L[l].sp_e, 0), b = std::max(L[l].sp_p, 0);
-                mx = std::max(mx, std::max(a, b)); mxs = std::max(mxs, a + b); p2_sum_lane += a + b; p2_lanes += 2;
+                mx = std::max(mx, std::max(a, b)); mxs = std::max(mxs, a + b); xma = std::max(xma, a); xmb = std::max(xmb, b); p2_sum_lane += a + b; p2_lanes += 2;
                 if (L[l].dirty) { cmx = std::max(cmx, std::max(a, b)); cmxs = std::max(cmxs, a + b); }
             }
-            p2_cur += mx; p2_seq += mxs; p2_cached_cur += cmx; p2_cached_seq += cmxs;
+            p2_ma += xma; p2_mb += xmb; p2_mn += std::min(xma, xmb); p2_cur += mx; p2_seq += mxs; p2_cached_cur += cmx; p2_cached_seq += cmxs;
             if (trip < 50) { ply_hist_p2[trip] += mx; ply_cnt[trip] += 1; }
             {   // static-phase policy S0: fields built at the first ply with both wall counts zero, reused afterwards
                 int nm = 0, bm = 0; bool anyslow = false, anylane = false;
@@ -260,6 +260,7 @@ int main(int argc, char **argv) {
     printf("warps %d, ply-trips per warp %.2f\n", nwarps, trips / nwarps);
     printf("per ROLLOUT (warp-level trips / 32 lanes):\n");
     printf("P2 iterations: current(max of max) %.2f | sequential(max of sum) %.2f | mean lane sum %.2f  [kernel measured 32.27]\n", p2_cur / R, p2_seq / R, p2_sum_lane / R / 32 * 1);
+    printf("P2 separate loops: A %.2f + B %.2f single-step trips; both-loop min(ma,mb) %.2f then single-loop rest %.2f\n", p2_ma / R, p2_mb / R, p2_mn / R, (p2_cur - p2_mn) / R);
     printf("P2 with goal-field caching (only lanes whose walls changed): max %.2f | seq %.2f\n", p2_cached_cur / R, p2_cached_seq / R);
     printf("static policy S0 (both zero): normal iters %.2f + extra build iters %.2f; all-fast ply-trips per warp %.2f; fast lane share %.3f\n", st_norm / R, st_build / R, st_allfast / nwarps, st_lanes_fast / st_lanes);
     printf("policy S2 (valid tracking): normal iters %.2f + build extra %.2f; all-fast ply-trips per warp %.2f\n", st2_norm / R, st2_build / R, st2_allfast / nwarps);
