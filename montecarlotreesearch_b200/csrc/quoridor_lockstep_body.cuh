@@ -90,31 +90,31 @@ static inline unsigned long long ls_emu_bits(double x) { unsigned long long b; m
 namespace mctsb {
 
 static constexpr int LS_THREADS = 128;
-static constexpr int LS_SHARE = 32;                     // candidates one lane may queue per batch
+static constexpr int LS_SHARE = 64;                     // candidates one lane may queue per batch (a quarter per pending word)
 static constexpr int LS_QCAP = 32 * LS_SHARE;           // queue entries per warp
 // dynamic shared memory of a block, in words:
 // [layers of search A, overlaid by the task queues during P5][best slots: one u64 per thread][ring: last three reach sets of search B]
 static constexpr int LS_RING = 3;
 static constexpr int LS_SMEM_WORDS = MCTSB_MAX_LAYERS * 3 * LS_THREADS + 2 * LS_THREADS + (LS_RING + 1) * 3 * LS_THREADS;   // ring + one scratch slot
 
-// per-warp shared scratch of the candidate phase.  The task queue lives in the warp's own columns of the
-// layer area (rows of 32 entries, row stride LS_THREADS words): the layers are dead once the trace is done
-// and are rebuilt at the top of the next ply, and no other warp ever touches these columns.
+// Shared memory is warp-major: every warp owns one contiguous region [layers of search A | best slots | ring of
+// search B], and inside it a board word is a row of 32 lanes (no bank conflicts).  The task queue of the candidate
+// phase lies over the warp's layer area, entry i at word i: the layers are dead once the trace is done and are
+// rebuilt at the top of the next ply, and no other warp ever touches the region.
+static constexpr int LS_WARP_LAYER_WORDS = MCTSB_MAX_LAYERS * 3 * 32;
+static constexpr int LS_WARP_WORDS = LS_WARP_LAYER_WORDS + 2 * 32 + (LS_RING + 1) * 3 * 32;
+static_assert(LS_WARP_WORDS * (LS_THREADS / 32) == LS_SMEM_WORDS, "shared memory layout");
 struct WarpBuf {
     uint32_t *qbase; unsigned long long *best;
-    LS_DEV uint32_t &queue(int i) const { return qbase[(i >> 5) * LS_THREADS + (i & 31)]; }
+    LS_DEV uint32_t &queue(int i) const { return qbase[i]; }
 };
-static_assert(LS_QCAP / 32 <= 3 * MCTSB_MAX_LAYERS, "the task queue must fit in the warp's share of the layer area");
+static_assert(LS_QCAP <= LS_WARP_LAYER_WORDS, "the task queue must fit in the warp's layer area");
 
-// layers of one lane live in shared memory, word-interleaved across the block: no bank conflicts
+// boards of one lane: three rows of the warp's region per slot
 struct SmemLayers {
-    uint32_t *base;   // &smem[tid]
-    LS_DEV void put(int j, B81 v) {
-        base[(3 * j + 0) * LS_THREADS] = v.a; base[(3 * j + 1) * LS_THREADS] = v.b; base[(3 * j + 2) * LS_THREADS] = v.c;
-    }
-    LS_DEV B81 get(int j) const {
-        return b81(base[(3 * j + 0) * LS_THREADS], base[(3 * j + 1) * LS_THREADS], base[(3 * j + 2) * LS_THREADS]);
-    }
+    uint32_t *base;   // &region[lane]
+    LS_DEV void put(int j, B81 v) { base[(3 * j + 0) * 32] = v.a; base[(3 * j + 1) * 32] = v.b; base[(3 * j + 2) * 32] = v.c; }
+    LS_DEV B81 get(int j) const { return b81(base[(3 * j + 0) * 32], base[(3 * j + 1) * 32], base[(3 * j + 2) * 32]); }
 };
 
 LS_DEV uint32_t umin32(uint32_t a, uint32_t b) { return a < b ? a : b; }
@@ -235,28 +235,39 @@ LS_DEV int warp_flood(bool go, B81 oS, B81 oE, int start, int player, QWork &wk)
     return d;
 }
 
-// step-target distance fields: 8 bits per candidate slot, three words
-LS_DEV void td_or(uint32_t &td0, uint32_t &td1, uint32_t &td2, int i, uint32_t v) {
-    uint32_t f = v << (8 * (i & 3));
-    if (i < 4) td0 |= f; else if (i < 8) td1 |= f; else td2 |= f;
+// The 12 pawn-step candidates (q_step_delta order) all lie within 20 cells of the mover's pawn, so a 64-bit
+// window of a board that starts 20 cells before the pawn holds every target at a fixed bit: window position of
+// candidate i = 20 + q_step_delta(i) = {11, 2, 29, 38, 19, 18, 21, 22, 10, 12, 28, 30}.
+LS_DEV void b81_window(B81 v, int wi, int sh, uint32_t &lo, uint32_t &hi) {
+    // bits [32 * wi + sh, +64) of the 160-bit string (0, a, b, c, 0)
+    const uint32_t w0 = wi == 0 ? 0u : wi == 1 ? v.a : v.b;
+    const uint32_t w1 = wi == 0 ? v.a : wi == 1 ? v.b : v.c;
+    const uint32_t w2 = wi == 0 ? v.b : wi == 1 ? v.c : 0u;
+    lo = sh ? fsr(w0, w1, sh) : w0; hi = sh ? fsr(w1, w2, sh) : w1;
 }
-LS_DEV int td_get(uint32_t td0, uint32_t td1, uint32_t td2, int i) {
-    uint32_t w = i < 4 ? td0 : i < 8 ? td1 : td2;
-    return (int)((w >> (8 * (i & 3))) & 0xffu);
+// candidate mask (bit i = candidate i) -> window coordinates, and back
+LS_DEV void steps_to_window(uint32_t m, uint32_t &lo, uint32_t &hi) {
+    lo = ((m & 0x0d0u) << 15) | ((m & 0x001u) << 11) | ((m & 0x002u) << 1) | ((m & 0x004u) << 27) | ((m & 0x020u) << 13) |
+         ((m & 0x100u) << 2) | ((m & 0x200u) << 3) | ((m & 0x400u) << 18) | ((m & 0x800u) << 19);
+    hi = (m & 0x008u) << 3;
+}
+LS_DEV uint32_t window_to_steps(uint32_t lo, uint32_t hi) {
+    return ((lo >> 15) & 0x0d0u) | ((lo >> 11) & 0x001u) | ((lo >> 1) & 0x002u) | ((lo >> 27) & 0x004u) | ((lo >> 13) & 0x020u) |
+           ((lo >> 2) & 0x100u) | ((lo >> 3) & 0x200u) | ((lo >> 18) & 0x400u) | ((lo >> 19) & 0x800u) | ((hi >> 3) & 0x008u);
 }
 
 // ------------------------------------------------------------------------------------------------
 template <bool REPLAY>
 LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_counter, uint32_t *smem) {
     const int lane = LS_TID & 31, warp = LS_TID >> 5;
-    SmemLayers ls; ls.base = smem + LS_TID;
-    SmemLayers ring;
+    SmemLayers ls, ring;
     WarpBuf wb;
-    {   // layout: [layers, overlaid by the task queues during P5][best slots: 32 x u64 per warp][ring of search B]
-        uint32_t *after = smem + MCTSB_MAX_LAYERS * 3 * LS_THREADS;
-        wb.best = reinterpret_cast<unsigned long long *>(after) + 32 * warp;
-        wb.qbase = smem + 32 * warp;
-        ring.base = after + 2 * LS_THREADS + LS_TID;
+    {   // the warp's region: [layers, overlaid by the task queue during P5][best slots: 32 x u64][ring of search B + scratch slot]
+        uint32_t *region = smem + warp * LS_WARP_WORDS;
+        ls.base = region + lane;
+        wb.qbase = region;
+        wb.best = reinterpret_cast<unsigned long long *>(region + LS_WARP_LAYER_WORDS);
+        ring.base = region + LS_WARP_LAYER_WORDS + 2 * 32 + lane;
     }
 
     QState s; LaneDraws<REPLAY> d;
@@ -323,7 +334,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
         const int cell_a = qa ? s.cell[1] : s.cell[0], cell_b = qa ? s.cell[0] : s.cell[1];
         const B81 goal_a = qa ? b81(MCTSB_GOAL_B_A, 0u, 0u) : b81(0u, 0u, MCTSB_GOAL_W_C);
         int sp_a = -1, sp_b = -1;
-        uint32_t td0 = 0, td1 = 0, td2 = 0;                    // step target distances, 8 bits per candidate slot
+        int best_target = -1;                                  // get_best_step_move's choice (cell), -1 none
         bool overflow_a = false;
         {
             const B81 goal_b = qb ? b81(MCTSB_GOAL_B_A, 0u, 0u) : b81(0u, 0u, MCTSB_GOAL_W_C);
@@ -361,9 +372,11 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             if (sp_a > 0) wk.flood_steps += (uint32_t)sp_a;
             if (sp_b > 0) wk.flood_steps += (uint32_t)sp_b;
             overflow_a = sp_a >= MCTSB_MAX_LAYERS;
-            // Distances of the legal step targets (get_best_step_move measures each with its own BFS,
-            // Quoridor.cpp:476-497).  A target is one or two moves from the pawn, so its distance is within
-            // two of the pawn's: rb2, rb1, rb and one more expansion are the cells within sp-2 .. sp+1.
+            // get_best_step_move (Quoridor.cpp:476-497) measures every legal step target with its own BFS and keeps
+            // the first strict minimum in reversed candidate order.  A target is one or two moves from the pawn, so
+            // its distance is within two of the pawn's: the reach sets R(sp-2) < R(sp-1) < R(sp) < R(sp+1) of search
+            // B sort the targets into five distance classes.  All twelve candidates are classified at once in a
+            // 64-bit window around the pawn; the nearest non-empty class wins, the highest candidate index in it.
             if (LS_ANY(steps != 0u)) {
                 const B81 z = b81(0u, 0u, 0u);
                 const int spb = sp_b < 0 ? 0 : sp_b;
@@ -371,17 +384,16 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 const B81 rb1 = spb >= 1 ? ring.get((spb + 2) % LS_RING) : z;  // within sp_b - 1
                 const B81 rb2 = spb >= 2 ? ring.get((spb + 1) % LS_RING) : z;  // within sp_b - 2
                 const B81 rb_next = q_flood_step(rb0, fm);
-                LS_UNROLL1
-                for (uint32_t m = steps; LS_ANY(m != 0u); m &= m - 1u) {
-                    if (m) {
-                        const int i = ctz32(m), t = cell_b + q_step_delta(i);
-                        uint32_t dist = 0xffu;
-                        if (sp_b >= 0)
-                            dist = b81_test(rb2, t) ? (uint32_t)(sp_b - 2) : b81_test(rb1, t) ? (uint32_t)(sp_b - 1)
-                                 : b81_test(rb0, t) ? (uint32_t)sp_b : b81_test(rb_next, t) ? (uint32_t)(sp_b + 1) : (uint32_t)(sp_b + 2);
-                        td_or(td0, td1, td2, i, dist);
-                    }
-                }
+                const int wpos = cell_b + 12, wi = wpos >> 5, sh = wpos & 31;      // window start = cell_b - 20, in (0, a, b, c, 0)
+                uint32_t slo, shi, lo, hi;
+                steps_to_window(steps, slo, shi);
+                uint32_t wlo = slo, whi = shi;                                   // farthest class: every legal step
+                b81_window(rb_next, wi, sh, lo, hi); if (((lo & slo) | (hi & shi)) != 0u) { wlo = lo & slo; whi = hi & shi; }
+                b81_window(rb0, wi, sh, lo, hi);     if (((lo & slo) | (hi & shi)) != 0u) { wlo = lo & slo; whi = hi & shi; }
+                b81_window(rb1, wi, sh, lo, hi);     if (((lo & slo) | (hi & shi)) != 0u) { wlo = lo & slo; whi = hi & shi; }
+                b81_window(rb2, wi, sh, lo, hi);     if (((lo & slo) | (hi & shi)) != 0u) { wlo = lo & slo; whi = hi & shi; }
+                const uint32_t cls = window_to_steps(wlo, whi);
+                if (sp_b >= 0 && cls != 0u) best_target = cell_b + q_step_delta(LS_HIBIT(cls));
             }
         }
         // rollouts that used their 50 plies are scored (evaluate_position, Quoridor.cpp:629-664; A = White there)
@@ -444,8 +456,13 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
         // the reference's choice — best gain / first accepted, earliest in the shuffled pool on ties.
         int chosen = -1;                                       // chosen wall k, -1 none
         {
-            uint64_t pend_h = 0, pend_v = 0;
-            if (mode == 1 || mode == 2) { pend_h = cheap_h & cut_h; pend_v = cheap_v & cut_v; }
+            // pending candidates, four words: [0] horizontal anchors 0..31, [1] horizontal 32..63, [2] vertical 0..31,
+            // [3] vertical 32..63; candidate k = 2 * anchor + orientation
+            uint32_t pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0;
+            if (mode == 1 || mode == 2) {
+                const uint64_t ph = cheap_h & cut_h, pv = cheap_v & cut_v;
+                pend0 = (uint32_t)ph; pend1 = (uint32_t)(ph >> 32); pend2 = (uint32_t)pv; pend3 = (uint32_t)(pv >> 32);
+            }
             // first legal (:773-788): the head of the shuffle goes alone; only if it is illegal the rest follows
             int head_k = mode == 3 ? q_pool_select(cheap_h, cheap_v, j0) : -1;
             bool head_only = mode == 3;
@@ -456,41 +473,37 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             *slot = 0ull;
             LS_SYNCWARP();                                     // every lane is done reading its layers: the queue may overwrite them
             LS_UNROLL1
-            while (LS_ANY((pend_h | pend_v) != 0ull || head_k >= 0)) {
-                // -- publish: every lane queues up to LS_SHARE candidates (half horizontal, half vertical), offsets
+            while (LS_ANY((pend0 | pend1 | pend2 | pend3) != 0u || head_k >= 0)) {
+                // -- publish: every lane queues up to LS_SHARE candidates (a quarter from each pending word), offsets
                 //    by an exclusive warp scan.  Order inside the queue is free: every queued candidate is measured.
-                const int nh = popc64(pend_h), nv = popc64(pend_v);
-                const int mh = head_k >= 0 ? 0 : (nh < LS_SHARE / 2 ? nh : LS_SHARE / 2);
-                const int mv = head_k >= 0 ? 0 : (nv < LS_SHARE / 2 ? nv : LS_SHARE / 2);
-                const int mine = head_k >= 0 ? 1 : mh + mv;
+                const bool is_head = head_k >= 0;
+                int c0 = LS_POPC(pend0), c1 = LS_POPC(pend1), c2 = LS_POPC(pend2), c3 = LS_POPC(pend3);
+                c0 = c0 < LS_SHARE / 4 ? c0 : LS_SHARE / 4; c1 = c1 < LS_SHARE / 4 ? c1 : LS_SHARE / 4;
+                c2 = c2 < LS_SHARE / 4 ? c2 : LS_SHARE / 4; c3 = c3 < LS_SHARE / 4 ? c3 : LS_SHARE / 4;
+                const int mine = is_head ? 1 : c0 + c1 + c2 + c3;
                 int off = mine;
                 LS_UNROLL1
                 for (int o = 1; o < LS_WARP; o <<= 1) { int t = LS_SHFL_UP(off, o); if (lane >= o) off += t; }
                 const int total = LS_SHFL(off, LS_WARP - 1);
                 off -= mine;
-                if (head_k >= 0) wb.queue(off) = (uint32_t)lane | ((uint32_t)head_k << 5);
-                {   // two independent bit iterators per trip: one FLO + one LOP per candidate
-                    uint32_t ch = (uint32_t)pend_h, cv = (uint32_t)pend_v;
-                    int wh = 0, wv = 0;
-                    LS_UNROLL1
-                    for (int i = 0; LS_ANY(i < mh || i < mv); i++) {
-                        if (i < mh) {
-                            if (ch == 0u) { wh = 1; ch = (uint32_t)(pend_h >> 32); }
-                            const int bpos = ctz32(ch);
-                            ch &= ch - 1u;
-                            wb.queue(off + i) = (uint32_t)lane | ((uint32_t)(2 * (32 * wh + bpos)) << 5);
-                        }
-                        if (i < mv) {
-                            if (cv == 0u) { wv = 1; cv = (uint32_t)(pend_v >> 32); }
-                            const int bpos = ctz32(cv);
-                            cv &= cv - 1u;
-                            wb.queue(off + mh + i) = (uint32_t)lane | ((uint32_t)(2 * (32 * wv + bpos) + 1) << 5);
-                        }
+                if (is_head) { wb.queue(off) = (uint32_t)lane | ((uint32_t)head_k << 5); c0 = c1 = c2 = c3 = 0; }
+                {
+                    uint32_t *qp = wb.qbase + off;
+                    // one short bit-iterator loop per word: entry = owner lane | k << 5, k = kbase + 2 * bit
+#define LS_PUBLISH_WORD(PEND, CNT, KBASE)                                                        \
+                    {                                                                            \
+                        uint32_t m = PEND; int c = CNT; const uint32_t e0 = (uint32_t)lane | ((uint32_t)(KBASE) << 5); \
+                        LS_UNROLL1                                                               \
+                        while (LS_ANY(c > 0)) {                                                  \
+                            if (c > 0) { *qp++ = e0 | ((uint32_t)ctz32(m) << 6); m &= m - 1u; c--; } \
+                        }                                                                        \
+                        PEND = m;                                                                \
                     }
-                    if (head_k < 0) {                          // the unsent remainder stays pending
-                        pend_h = wh == 0 ? ((uint64_t)ch | (pend_h & 0xffffffff00000000ull)) : ((uint64_t)ch << 32);
-                        pend_v = wv == 0 ? ((uint64_t)cv | (pend_v & 0xffffffff00000000ull)) : ((uint64_t)cv << 32);
-                    }
+                    LS_PUBLISH_WORD(pend0, c0, 0)
+                    LS_PUBLISH_WORD(pend1, c1, 64)
+                    LS_PUBLISH_WORD(pend2, c2, 1)
+                    LS_PUBLISH_WORD(pend3, c3, 65)
+#undef LS_PUBLISH_WORD
                 }
                 const bool head_sent = head_k >= 0;
                 head_k = -1;
@@ -568,8 +581,9 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                 }
                 LS_SYNCWARP();
                 if (head_sent && head_only && *slot == 0ull) {   // the head was not legal: the others, in key order (rare)
-                    pend_h = cheap_h; pend_v = cheap_v;
-                    q_mask_clear(pend_h, pend_v, q_pool_select(cheap_h, cheap_v, j0));
+                    uint64_t ph = cheap_h, pv = cheap_v;
+                    q_mask_clear(ph, pv, q_pool_select(cheap_h, cheap_v, j0));
+                    pend0 = (uint32_t)ph; pend1 = (uint32_t)(ph >> 32); pend2 = (uint32_t)pv; pend3 = (uint32_t)(pv >> 32);
                     head_only = false;
                 }
             }
@@ -583,14 +597,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
             bool best_step = s.nwalls[en] == 0;
             if (!best_step) { d.pos++; best_step = u_step < MCTSB_THR_0_80; } else { u_rand = u_step; }
             if (best_step) {
-                // get_best_step_move: reversed candidate order, first strict minimum (Quoridor.cpp:476-497)
-                int mn = 9999999;
-                LS_UNROLL1
-                for (uint32_t m = steps; m; ) {
-                    int i = LS_HIBIT(m); m &= ~(1u << i);
-                    int dist = td_get(td0, td1, td2, i);
-                    if (dist != 0xff && dist < mn) { mn = dist; target = cell_b + q_step_delta(i); }
-                }
+                target = best_target;                            // classified with the reach sets of search B (P2)
             } else {
                 d.pos++;                                         // rand() (Quoridor.cpp:796)
                 int ns = LS_POPC(steps);
