@@ -64,13 +64,29 @@ MC_HD bool b81_any(B81 x) { return (x.a | x.b | x.c) != 0; }
 template <int N> MC_HD B81 shl(B81 v) { return b81(v.a << N, fsl(v.a, v.b, N), fsl(v.b, v.c, N)); }
 template <int N> MC_HD B81 shr(B81 v) { return b81(fsr(v.a, v.b, N), fsr(v.b, v.c, N), v.c >> N); }
 
-// `bits` (< 2^18) shifted to cell `pos` (0..80) as a board; bits running past cell 95 are dropped
+// `bits` (< 2^18) shifted to cell `pos` (0..80) as a board; bits running past cell 95 are dropped.
+// Branch-free: the word index only steers selects (lanes of a warp call this with different cells).
 MC_HD B81 b81_shifted(uint32_t bits, int pos) {
-    int w = pos >> 5, sh = pos & 31;
-    uint32_t lo = bits << sh, hi = sh ? bits >> (32 - sh) : 0u;
-    return w == 0 ? b81(lo, hi, 0u) : w == 1 ? b81(0u, lo, hi) : b81(0u, 0u, lo);
+    const int w = pos >> 5, sh = pos & 31;
+    const uint32_t lo = bits << sh, hi = (bits >> 1) >> (31 - sh);        // hi = bits >> (32 - sh), 0 when sh == 0
+    const bool w0 = w == 0, w1 = w == 1;
+    return b81(w0 ? lo : 0u, w0 ? hi : (w1 ? lo : 0u), w1 ? hi : (w0 ? 0u : lo));
 }
-MC_HD B81 b81_bit(int pos) { return b81_shifted(1u, pos); }
+MC_HD B81 b81_bit(int pos) {
+    const int w = pos >> 5;
+    const uint32_t bit = 1u << (pos & 31);
+    return b81(w == 0 ? bit : 0u, w == 1 ? bit : 0u, w == 2 ? bit : 0u);
+}
+// the edge boards with candidate wall k = 2 * anchor + orientation added (get_shortest_path(player, wall),
+// Quoridor.cpp:138-156): a horizontal wall closes the south edges of cells pos, pos+1, a vertical one the east
+// edges of cells pos, pos+9.  One mask, applied to the board the orientation selects.
+MC_HD void b81_add_wall(B81 &oS, B81 &oE, int k) {
+    const int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
+    const uint32_t vert = 0u - (uint32_t)(k & 1);                         // all ones for a vertical wall
+    const B81 m = b81_shifted((k & 1) ? 0x201u : 0x3u, pos);
+    oS = b81(oS.a & ~(m.a & ~vert), oS.b & ~(m.b & ~vert), oS.c & ~(m.c & ~vert));
+    oE = b81(oE.a & ~(m.a & vert), oE.b & ~(m.b & vert), oE.c & ~(m.c & vert));
+}
 MC_HD bool b81_test(B81 v, int pos) {
     uint32_t w = pos < 32 ? v.a : pos < 64 ? v.b : v.c;
     return (w >> (pos & 31)) & 1u;
@@ -246,10 +262,8 @@ MC_HD int q_sp(QState &s, int player, QWork *wk) {
 // get_shortest_path(player, extra wall), Quoridor.cpp:138-156: the wall is added to a register copy
 // of the edge boards, nothing to undo.  k = 2*anchor + (0 horizontal | 1 vertical).
 MC_HD int q_sp_with_wall(const QState &s, int player, int k, QWork *wk) {
-    int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
     B81 oS = s.openS, oE = s.openE;
-    if (k & 1) oE = andn(oE, b81_shifted(0x201u, pos));
-    else       oS = andn(oS, b81_shifted(0x3u, pos));
+    b81_add_wall(oS, oE, k);
     return q_flood_dist(oS, oE, s.cell[player], player, wk);
 }
 

@@ -5,7 +5,7 @@
 namespace mctsb {
 
 #ifndef LS_BLOCKS_PER_SM
-#define LS_BLOCKS_PER_SM 4
+#define LS_BLOCKS_PER_SM 5
 #endif
 
 template <bool REPLAY>

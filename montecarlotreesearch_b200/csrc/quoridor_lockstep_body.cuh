@@ -523,10 +523,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                     const uint32_t oc = LS_SHFL(pk_cells, owner), osp = LS_SHFL(pk_sp, owner);
                     const int o_turn = (int)((oc >> 16) & 0xffu), o_mode = (int)(oc >> 24);
                     const int o_sp_e = (int)(int8_t)(osp & 0xffu);
-                    {   // the candidate wall on the owner's boards
-                        int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
-                        if (k & 1) oE = andn(oE, b81_shifted(0x201u, pos)); else oS = andn(oS, b81_shifted(0x3u, pos));
-                    }
+                    b81_add_wall(oS, oE, k);                   // the candidate wall on the owner's boards
                     const int p1 = o_mode == 3 ? 0 : 1 - o_turn;
                     const int c1 = (int)((p1 ? (oc >> 8) : oc) & 0xffu);
                     const int d1 = warp_flood(valid, oS, oE, c1, p1, wk);
@@ -554,10 +551,7 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
                     const int o_turn = (int)((oc >> 16) & 0xffu), o_mode = (int)(oc >> 24);
                     const int o_sp_e = (int)(int8_t)(osp & 0xffu), o_sp_p = (int)(int8_t)((osp >> 8) & 0xffu);
                     const int o_n = (int)((osp >> 16) & 0xffu), o_j0 = (int)(osp >> 24);
-                    {
-                        int anchor = k >> 1, pos = 9 * (anchor >> 3) + (anchor & 7);
-                        if (k & 1) oE = andn(oE, b81_shifted(0x201u, pos)); else oS = andn(oS, b81_shifted(0x3u, pos));
-                    }
+                    b81_add_wall(oS, oE, k);
                     const int p2 = o_mode == 3 ? 1 : o_turn;
                     const int c2 = (int)((p2 ? (oc >> 8) : oc) & 0xffu);
                     const int d2 = warp_flood(valid, oS, oE, c2, p2, wk);
