@@ -107,6 +107,9 @@ int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const R
 }
 
 int upload_states(mctsb_backend *b, int game, const void *states, int n) {
+    // every upload overwrites d_states: what mctsb_run_resident would play is no longer what the caller made
+    // resident, so the resident marker is dropped (mctsb_upload_states sets it again after its own upload)
+    b->res_game = -1; b->res_leaves = 0;
     size_t bytes = (size_t)n * state_size(game);
     TRY(grow_bytes(b, &b->d_states, &b->cap_states, bytes));
     TRY(grow_pinned(b, &b->h_in, &b->cap_h_in, bytes));

@@ -5,8 +5,9 @@
 // cannot be reproduced on a GPU and is racy even on the CPU.  Here draw k of rollout r is a pure
 // function of (seed, r, k): Philox4x32-10 with counter {k>>2, lo32(r), hi32(r), 0} and key
 // {lo32(seed), hi32(seed)}, word k&3 — independent of lane, block or GPU placement.  The draw ->
-// value conventions (U() = u32*2^-32, rand() = u32 & 0x7fffffff, forward Fisher-Yates with
-// mulhi) are documented once in include/mctsb.h / DESIGN.md.
+// value conventions (U() = u32*2^-32, rand() = u32 & 0x7fffffff, the keyed shuffle: head of the pool
+// by mulhi, every other element ordered by its own draw) are documented once in include/mctsb.h /
+// DESIGN.md.
 #pragma once
 #include <stdint.h>
 

@@ -291,13 +291,13 @@ LS_DEV void lockstep_body(const RolloutParams &p, unsigned long long *work_count
         //      (Refilling lane by lane mixes ply 5 with ply 45 in one warp: 29.2 M instead of 32.3 M rollouts/s
         //      on the opening position, 70 M instead of 99 M on the mid-game corpus.)
         {
-            unsigned want = LS_BALLOT(!have && !exhausted);
+            unsigned want = LS_BALLOT(!have && !exhausted && (uint32_t)lane < p.lanes_per_batch);
             if (want && !LS_ANY(have)) {
                 unsigned long long base = 0;
                 int leader = LS_FFS(want) - 1;
                 if (lane == leader) base = LS_ATOMIC_ADD(work_counter, (unsigned long long)LS_POPC(want));
                 base = LS_SHFL(base, leader);
-                if (!have && !exhausted) {
+                if ((want >> lane) & 1u) {
                     r = base + (unsigned long long)LS_POPC(want & ((1u << lane) - 1u));
                     if (r >= p.n_rollouts) exhausted = true;
                     else {

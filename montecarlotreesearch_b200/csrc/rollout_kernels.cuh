@@ -6,6 +6,8 @@
 
 namespace mctsb {
 
+#define MCTSB_MAX_DEVICES 64           // per-device launch configuration slots
+
 struct RolloutParams {
     const void *states;            // mctsb_qstate[n_leaves] or mctsb_tstate[n_leaves]
     uint32_t n_leaves;
@@ -21,6 +23,7 @@ struct RolloutParams {
     mctsb_outcome *outcomes;       // [n_rollouts]
     void *finals;                  // mctsb_qstate[n_rollouts]
     unsigned long long *counters;  // [4]: rollouts, plies, flood_steps, flood_queries
+    uint32_t lanes_per_batch;      // lockstep kernel: rollouts a warp takes per batch (1..32; set by the launch)
 };
 
 // REF policy, production kernel (quoridor_lockstep.cu): one thread = one rollout, the 32 rollouts of a

@@ -24,7 +24,7 @@ class EmuLib:
         L.emu_t_rollout_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, vp]
         L.emu_t_rollout_streams.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]
         L.emu_t_winner.argtypes = [C.c_uint32, C.c_uint32]
-        L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int]
+        L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int]
 
     def q_primitives(self, s):
         a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
@@ -103,7 +103,7 @@ class EmuLib:
         self.lib.emu_t_rollout_streams(a.ctypes.data, a.size, st.ctypes.data, st.shape[1], st.shape[1], out.ctypes.data)
         return out
 
-    def lockstep(self, states, R, seed, first_id, streams=None, blocks=1):
+    def lockstep(self, states, R, seed, first_id, streams=None, blocks=1, lanes=32):
         """The production kernel body on the host (one-lane warp, or `blocks` emulated thread blocks of 32-lane
         warps in the warp32 build): Philox mode (streams=None) or replay."""
         from oracle.reflib import LEAFSUM_DTYPE
@@ -120,5 +120,5 @@ class EmuLib:
         sums = np.zeros(a.size, dtype=LEAFSUM_DTYPE)
         ctr = np.zeros(4, dtype=np.uint64)
         self.lib.emu_lockstep(a.ctypes.data, a.size, R, seed, first_id, sp, sl, ss, out.ctypes.data, fin.ctypes.data,
-                              sums.ctypes.data, ctr.ctypes.data, blocks)
+                              sums.ctypes.data, ctr.ctypes.data, blocks, lanes)
         return out, fin, sums, ctr

@@ -127,11 +127,11 @@ static void emu_thread(void *a) {
 
 int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t seed, uint64_t first_id,
                  const uint32_t *streams, uint32_t stream_len, uint32_t stream_stride,
-                 mctsb_outcome *out, mctsb_qstate *finals, mctsb_leaf_sum *sums, uint64_t *counters4, int blocks) {
+                 mctsb_outcome *out, mctsb_qstate *finals, mctsb_leaf_sum *sums, uint64_t *counters4, int blocks, int lanes) {
     RolloutParams p; memset(&p, 0, sizeof p);
     p.states = states; p.n_leaves = (uint32_t)n_leaves; p.rollouts_per_leaf = R; p.n_rollouts = (uint64_t)n_leaves * R;
     p.seed = seed; p.first_rollout_id = first_id; p.streams = streams; p.stream_len = stream_len; p.stream_stride = stream_stride;
-    p.sums = sums; p.outcomes = out; p.finals = finals;
+    p.sums = sums; p.outcomes = out; p.finals = finals; p.lanes_per_batch = lanes > 0 ? (uint32_t)lanes : 32u;
     unsigned long long ctr[4] = {0, 0, 0, 0};
     p.counters = ctr;
     if (sums) memset(sums, 0, sizeof(mctsb_leaf_sum) * (size_t)n_leaves);

@@ -266,3 +266,60 @@ def test_long_paths_overflow_the_layer_budget(be, port):
         assert (bits[i] == p["legal"]).all() and info["sp_white"][i] == p["sp_white"] and info["sp_black"][i] == p["sp_black"]
         exp, efin, _ = port.q_rollout_philox(s, m.DEFAULT_SEED, 4321 + 96 * i, 96, finals=True)
         assert exp.tobytes() == out[96 * i: 96 * (i + 1)].tobytes() and efin.tobytes() == fin[96 * i: 96 * (i + 1)].tobytes()
+
+
+def test_every_launch_shape_plays_the_same_rollouts(be):
+    """Launch sizes that take different grid shapes (a few lanes per warp, one balanced wave, two equal batches,
+    the persistent grid): rollout id r is the same playout in all of them, and the exact sums add up."""
+    s = m.quoridor_opening()
+    big, _ = be.rollout_outcomes(G, m.POLICY_REF, s, 200000, 5000, finals=False)          # persistent grid, 32 lanes
+    for n in (1, 4, 33, 1000, 70001, 120000):
+        out, _ = be.rollout_outcomes(G, m.POLICY_REF, s, n, 5000, finals=False)
+        assert out.tobytes() == big[:n].tobytes(), n
+    _, whole = be.rollout_batch(G, m.POLICY_REF, s, 70001, 5000)
+    lo = hi = cnt = 0
+    for first, n in ((5000, 1), (5001, 4), (5005, 995), (6000, 69001)):
+        _, part = be.rollout_batch(G, m.POLICY_REF, s, n, first)
+        lo += int(part["lo"][0]); hi += int(part["hi"][0]); cnt += int(part["n"][0])
+    assert (lo + (hi << 29), cnt) == (int(whole["lo"][0]) + (int(whole["hi"][0]) << 29), 70001)
+
+
+def test_resident_states_are_invalidated_by_other_uploads(be, corpus):
+    """mctsb_run_resident plays what mctsb_upload_states made resident — any other call that re-uploads leaf
+    states drops the marker instead of silently mixing new and stale positions."""
+    be.upload_states(G, corpus[:64])
+    be.run_resident(G, m.POLICY_REF, 8, 0)
+    _, a = be.wait()
+    assert int(a["n"].sum()) == 64 * 8
+    be.rollout_batch(G, m.POLICY_REF, corpus[100:110], 4, 0)          # overwrites the device copy of the states
+    with pytest.raises(m.BackendError) as e:
+        be.run_resident(G, m.POLICY_REF, 8, 0)
+    assert e.value.status == 5
+    be.upload_states(G, corpus[:64])
+    be.run_resident(G, m.POLICY_REF, 8, 0)
+    _, b = be.wait()
+    assert a.tobytes() == b.tobytes()
+
+
+def test_two_host_threads_two_handles(be, corpus):
+    """Distinct handles are independent: two host threads drive their own handle at the same time (the launch
+    configuration is per device and built under a lock), results equal the single-threaded ones."""
+    import threading
+    states = corpus[:200]
+    want, _ = be.rollout_outcomes(G, m.POLICY_REF, states, 6, 77, finals=False)
+    got, errs = {}, []
+
+    def work(tag):
+        try:
+            h = m.RolloutBackend(0, m.DEFAULT_SEED)
+            for _ in range(3):
+                got[tag], _ = h.rollout_outcomes(G, m.POLICY_REF, states, 6, 77, finals=False)
+            h.close()
+        except Exception as ex:  # pragma: no cover
+            errs.append(ex)
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs
+    assert got[0].tobytes() == want.tobytes() and got[1].tobytes() == want.tobytes()
