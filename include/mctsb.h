@@ -33,7 +33,8 @@ typedef enum {
     MCTSB_ERR_BAD_STATE = 4,   /* a packed state record is not a reachable position               */
     MCTSB_ERR_NOT_SUBMITTED = 5, /* wait without a pending submit                                 */
     MCTSB_ERR_BUSY = 6,        /* submit while a previous submit has not been waited for          */
-    MCTSB_ERR_OOM = 7
+    MCTSB_ERR_OOM = 7,
+    MCTSB_ERR_COMM = 8         /* an NCCL call failed / libnccl.so.2 is not present: multi-GPU exchange only       */
 } mctsb_status;
 
 /* ---- games and rollout policies ------------------------------------------------------- */
@@ -131,6 +132,17 @@ int mctsb_submit(mctsb_backend *b, int game, int policy,
                  uint32_t rollouts_per_leaf, uint64_t first_rollout_id);
 int mctsb_wait(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums);
 
+/* The same pair for a tree that also wants the NEXT Expansion prepared on the device: with
+ * MCTSB_SUBMIT_LEGAL (Quoridor only) the leaf states that were just uploaded for their rollouts are also run
+ * through the move-generation kernel, and mctsb_wait_x returns their 209-bit legal-move masks (4 words per
+ * leaf, canonical move ids) next to the sums.  Replaces the `state->actions_to_try()` the reference's node
+ * constructor runs on the CPU for every new node (mcts.cpp:19 -> generate_all_moves, Quoridor.cpp:594-616):
+ * when a leaf is selected again, its move list is already there.  `legal` may be NULL. */
+#define MCTSB_SUBMIT_LEGAL 1u
+int mctsb_submit_x(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
+                   uint32_t rollouts_per_leaf, uint64_t first_rollout_id, uint32_t flags);
+int mctsb_wait_x(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums, uint64_t *legal /* n_leaves*4 or NULL */);
+
 /* Synchronous convenience: submit + wait (the shape of MCTS_node::rollout(), mcts.cpp:57-81). */
 int mctsb_rollout_batch(mctsb_backend *b, int game, int policy,
                         const void *leaf_states, int n_leaves,
@@ -204,6 +216,28 @@ int mctsb_get_counters(mctsb_backend *b, mctsb_counters *out);
 
 /* Helpers shared by hosts: exact sum -> double, and the reference's score for one record. */
 double mctsb_leaf_sum_to_double(const mctsb_leaf_sum *s);
+
+/* ---- multi-GPU exchange -------------------------------------------------------
+ * The path shards by rollout id with no data-path collective; the one exchange is a sum over GPUs of a few
+ * hundred bytes: the root-child statistics of root-parallel trees before the reference's final choice rule
+ * (MCTS_tree::select_best_child with c = 0, mcts.cpp:104-129,268-270) runs on identical numbers on every
+ * rank, or the exact per-leaf accumulators of a sharded batch.  NCCL over NVLink; libnccl.so.2 is loaded on
+ * the first call (MCTSB_ERR_COMM when absent), a single-GPU user never needs it.
+ *   one process per GPU : rank 0 calls mctsb_comm_unique_id, ships the 128 bytes to the others by any
+ *                         means, every rank calls mctsb_comm_init_rank on its handle;
+ *   one process, n GPUs : mctsb_comm_init_all over the n handles (one per device); reductions issued from
+ *                         one thread go through mctsb_allreduce_root_stats_group.
+ * The reductions are in place over host buffers, blocking, on the handle's stream; they fail with
+ * MCTSB_ERR_NOT_SUBMITTED without a communicator and MCTSB_ERR_BUSY while a submit is pending. */
+#define MCTSB_COMM_ID_BYTES 128
+int mctsb_comm_unique_id(void *id128);
+int mctsb_comm_init_rank(mctsb_backend *b, const void *id128, int world, int rank);
+int mctsb_comm_init_all(mctsb_backend **handles, int n);
+int mctsb_comm_destroy(mctsb_backend *b);
+int mctsb_comm_info(const mctsb_backend *b, int *world, int *rank);
+int mctsb_allreduce_root_stats(mctsb_backend *b, double *stats /* in/out */, int n);
+int mctsb_allreduce_leaf_sums(mctsb_backend *b, mctsb_leaf_sum *sums /* in/out */, int n_leaves);
+int mctsb_allreduce_root_stats_group(mctsb_backend **handles, double **stats, int n_handles, int n);
 
 #ifdef __cplusplus
 }

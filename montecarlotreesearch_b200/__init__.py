@@ -36,7 +36,12 @@ EXPORTS = [
     "mctsb_device_count", "mctsb_submit", "mctsb_wait", "mctsb_rollout_batch", "mctsb_rollout_outcomes",
     "mctsb_rollout_replay", "mctsb_q_movegen", "mctsb_q_play", "mctsb_upload_states", "mctsb_run_resident",
     "mctsb_int_issue_peak", "mctsb_lop3_peak", "mctsb_flush_l2", "mctsb_get_counters", "mctsb_leaf_sum_to_double",
+    "mctsb_submit_x", "mctsb_wait_x",
+    "mctsb_comm_unique_id", "mctsb_comm_init_rank", "mctsb_comm_init_all", "mctsb_comm_destroy", "mctsb_comm_info",
+    "mctsb_allreduce_root_stats", "mctsb_allreduce_leaf_sums", "mctsb_allreduce_root_stats_group",
 ]
+SUBMIT_LEGAL = 1
+COMM_ID_BYTES = 128
 
 
 class BackendError(RuntimeError):
@@ -75,6 +80,16 @@ def load_library():
     L.mctsb_device_count.argtypes = [C.POINTER(i32)]
     L.mctsb_submit.argtypes = [vp, i32, i32, vp, i32, u32, u64]
     L.mctsb_wait.argtypes = [vp, vp, vp]
+    L.mctsb_submit_x.argtypes = [vp, i32, i32, vp, i32, u32, u64, u32]
+    L.mctsb_wait_x.argtypes = [vp, vp, vp, vp]
+    L.mctsb_comm_unique_id.argtypes = [vp]
+    L.mctsb_comm_init_rank.argtypes = [vp, vp, i32, i32]
+    L.mctsb_comm_init_all.argtypes = [C.POINTER(vp), i32]
+    L.mctsb_comm_destroy.argtypes = [vp]
+    L.mctsb_comm_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32)]
+    L.mctsb_allreduce_root_stats.argtypes = [vp, vp, i32]
+    L.mctsb_allreduce_leaf_sums.argtypes = [vp, vp, i32]
+    L.mctsb_allreduce_root_stats_group.argtypes = [C.POINTER(vp), C.POINTER(vp), i32, i32]
     L.mctsb_rollout_batch.argtypes = [vp, i32, i32, vp, i32, u32, u64, vp, vp]
     L.mctsb_rollout_outcomes.argtypes = [vp, i32, i32, vp, i32, u32, u64, vp, vp]
     L.mctsb_rollout_replay.argtypes = [vp, i32, i32, vp, i32, vp, u32, u32, vp, vp]
@@ -124,7 +139,7 @@ class RolloutBackend:
     def _ck(self, st):
         if st != 0:
             msg = self.lib.mctsb_strerror(st).decode()
-            if st == 2:
+            if st in (2, 8):
                 msg += " / " + self.lib.mctsb_last_cuda_error(self.handle).decode()
             raise BackendError(st, msg)
 
@@ -149,6 +164,40 @@ class RolloutBackend:
     def rollout_batch(self, game, policy, states, rollouts_per_leaf, first_rollout_id=0):
         self.submit(game, policy, states, rollouts_per_leaf, first_rollout_id)
         return self.wait()
+
+    def submit_x(self, game, policy, states, rollouts_per_leaf, first_rollout_id=0, flags=SUBMIT_LEGAL):
+        a = self._states(game, states)
+        self._ck(self.lib.mctsb_submit_x(self.handle, game, policy, a.ctypes.data, a.size, rollouts_per_leaf, first_rollout_id, flags))
+        self._pending_n = a.size
+
+    def wait_x(self):
+        """-> (score sums, exact sums, legal-move masks (n, 4) of the submitted leaves)"""
+        n = self._pending_n
+        score = np.zeros(n, dtype=np.float64)
+        sums = np.zeros(n, dtype=LEAFSUM_DTYPE)
+        legal = np.zeros((n, 4), dtype=np.uint64)
+        self._ck(self.lib.mctsb_wait_x(self.handle, score.ctypes.data, sums.ctypes.data, legal.ctypes.data))
+        return score, sums, legal
+
+    # -- multi-GPU exchange (NCCL behind the C ABI) -------------------------------------------------
+    def comm_init_rank(self, unique_id, world, rank):
+        buf = (C.c_ubyte * COMM_ID_BYTES).from_buffer_copy(bytes(unique_id))
+        self._ck(self.lib.mctsb_comm_init_rank(self.handle, buf, world, rank))
+
+    def comm_info(self):
+        w, r = C.c_int(0), C.c_int(0)
+        self._ck(self.lib.mctsb_comm_info(self.handle, C.byref(w), C.byref(r)))
+        return w.value, r.value
+
+    def allreduce_root_stats(self, vec):
+        v = np.ascontiguousarray(vec, dtype=np.float64).copy()
+        self._ck(self.lib.mctsb_allreduce_root_stats(self.handle, v.ctypes.data, v.size))
+        return v
+
+    def allreduce_leaf_sums(self, sums):
+        s = np.ascontiguousarray(sums, dtype=LEAFSUM_DTYPE).copy()
+        self._ck(self.lib.mctsb_allreduce_leaf_sums(self.handle, s.ctypes.data, s.size))
+        return s
 
     def rollout_outcomes(self, game, policy, states, rollouts_per_leaf, first_rollout_id=0, finals=True):
         a = self._states(game, states)
@@ -218,6 +267,25 @@ class RolloutBackend:
         c = np.zeros((), dtype=COUNTERS_DTYPE)
         self._ck(self.lib.mctsb_get_counters(self.handle, c.ctypes.data))
         return {k: int(c[k]) for k in COUNTERS_DTYPE.names}
+
+
+def comm_unique_id():
+    """128 opaque bytes identifying a new communicator: made by one rank, shipped to the others by any means."""
+    L = load_library()
+    buf = (C.c_ubyte * COMM_ID_BYTES)()
+    st = L.mctsb_comm_unique_id(buf)
+    if st != 0:
+        raise BackendError(st, L.mctsb_strerror(st).decode())
+    return bytes(buf)
+
+
+def comm_init_all(backends):
+    """One process, one RolloutBackend per device: a communicator over all of them."""
+    L = backends[0].lib
+    arr = (C.c_void_p * len(backends))(*[b.handle for b in backends])
+    st = L.mctsb_comm_init_all(arr, len(backends))
+    if st != 0:
+        raise BackendError(st, L.mctsb_strerror(st).decode() + " / " + L.mctsb_last_cuda_error(backends[0].handle).decode())
 
 
 def unpack_legal(mask4):

@@ -65,7 +65,7 @@ def build_host(force=False, verbose=False):
     deps = [os.path.join(hdir, f) for f in os.listdir(hdir)] + all_inputs()
     if not force and not _stale(HOSTLIB, deps):
         return HOSTLIB
-    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-pthread", "-I", os.path.join(ROOT, "include"),
+    cmd = ["g++", "-O2", "-ftree-vectorize", "-fno-math-errno", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-pthread", "-I", os.path.join(ROOT, "include"),
            "-o", HOSTLIB] + srcs + ["-L", PKG, "-lmctsb", "-Wl,-rpath,$ORIGIN"]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:

@@ -3,39 +3,13 @@
 // does with JobScheduler + RolloutJob, done with one stream, pinned staging buffers and kernels.
 // There is no CPU fallback anywhere in this file: without a CUDA device creation fails.
 #include "rollout_kernels.cuh"
+#include "mctsb_backend_internal.cuh"
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <new>
 
 using namespace mctsb;
-
-struct mctsb_backend {
-    int device;
-    uint64_t seed;
-    cudaStream_t stream;
-    cudaEvent_t ev0, ev1;
-    // device buffers (grown on demand, never shrunk)
-    void *d_states; size_t cap_states;               // bytes
-    mctsb_leaf_sum *d_sums; size_t cap_sums;         // elements
-    mctsb_outcome *d_outcomes; size_t cap_outcomes;  // elements
-    void *d_finals; size_t cap_finals;               // bytes
-    uint32_t *d_streams; size_t cap_streams;         // elements
-    void *d_aux; size_t cap_aux;                     // bytes (movegen / play outputs)
-    unsigned long long *d_counters;                  // [8]: 0-3 rollouts, plies, flood steps, flood queries; 7 = work counter of the lockstep kernel
-    uint32_t *d_sink;                                // int-peak microbenchmark
-    void *d_flush; size_t flush_bytes;                // L2 flush scratch (bench hygiene)
-    // pinned host staging
-    void *h_in; size_t cap_h_in;
-    void *h_out; size_t cap_h_out;
-    // pending submit
-    bool pending; int pend_game; uint32_t pend_leaves;
-    // resident state
-    int res_game; uint32_t res_leaves;
-    uint64_t launches;
-    bool use_simple_kernel;                          // MCTSB_SIMPLE_KERNEL=1: REF policy on the v1 kernel (A/B cross-check)
-    char cuda_err[256];
-};
 
 namespace {
 
@@ -133,6 +107,7 @@ const char *mctsb_strerror(int status) {
         case MCTSB_ERR_BAD_STATE: return "packed state is not a valid position";
         case MCTSB_ERR_NOT_SUBMITTED: return "wait without a pending submit";
         case MCTSB_ERR_BUSY: return "a submitted batch has not been waited for";
+        case MCTSB_ERR_COMM: return "multi-GPU exchange failed (NCCL), see mctsb_last_cuda_error";
         case MCTSB_ERR_OOM: return "out of device or pinned memory";
         default: return "unknown status";
     }
@@ -178,7 +153,8 @@ int mctsb_destroy(mctsb_backend *b) {
     cudaSetDevice(b->device);
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_states); cudaFree(b->d_sums); cudaFree(b->d_outcomes); cudaFree(b->d_finals);
-    cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink); cudaFree(b->d_flush);
+    mctsb_comm_destroy(b);
+    cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink); cudaFree(b->d_flush); if (b->h_legal) cudaFreeHost(b->h_legal);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->ev0) cudaEventDestroy(b->ev0);
@@ -205,9 +181,10 @@ double mctsb_leaf_sum_to_double(const mctsb_leaf_sum *s) {
     return r * inv;
 }
 
-int mctsb_submit(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
-                 uint32_t rollouts_per_leaf, uint64_t first_rollout_id) {
+int mctsb_submit_x(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
+                   uint32_t rollouts_per_leaf, uint64_t first_rollout_id, uint32_t flags) {
     if (!b || !leaf_states || n_leaves <= 0 || rollouts_per_leaf == 0 || !valid_game_policy(game, policy)) return MCTSB_ERR_BAD_ARG;
+    if ((flags & ~MCTSB_SUBMIT_LEGAL) || ((flags & MCTSB_SUBMIT_LEGAL) && game != MCTSB_GAME_QUORIDOR)) return MCTSB_ERR_BAD_ARG;
     if (b->pending) return MCTSB_ERR_BUSY;
     if (game == MCTSB_GAME_QUORIDOR && !valid_qstates((const mctsb_qstate *)leaf_states, n_leaves)) return MCTSB_ERR_BAD_STATE;
     CK(cudaSetDevice(b->device));
@@ -221,13 +198,30 @@ int mctsb_submit(mctsb_backend *b, int game, int policy, const void *leaf_states
     p.sums = b->d_sums; p.counters = b->d_counters;
     TRY(launch_rollouts(b, game, policy, false, p));
     CK(cudaMemcpyAsync(b->h_out, b->d_sums, (size_t)n_leaves * sizeof(mctsb_leaf_sum), cudaMemcpyDeviceToHost, b->stream));
+    b->pend_legal = false;
+    if (flags & MCTSB_SUBMIT_LEGAL) {                 // the uploaded leaves through the move-generation kernel, same stream
+        const size_t bytes = (size_t)n_leaves * 4 * sizeof(uint64_t);
+        TRY(grow_bytes(b, &b->d_aux, &b->cap_aux, bytes));
+        TRY(grow_pinned(b, &b->h_legal, &b->cap_h_legal, bytes));
+        cudaError_t e = launch_quoridor_movegen((const mctsb_qstate *)b->d_states, n_leaves, (uint64_t *)b->d_aux, nullptr, nullptr, b->stream);
+        if (e != cudaSuccess) return fail_cuda(b, e, "movegen kernel launch");
+        b->launches++;
+        CK(cudaMemcpyAsync(b->h_legal, b->d_aux, bytes, cudaMemcpyDeviceToHost, b->stream));
+        b->pend_legal = true;
+    }
     b->pending = true; b->pend_game = game; b->pend_leaves = (uint32_t)n_leaves;
     return MCTSB_OK;
 }
 
-int mctsb_wait(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums) {
+int mctsb_submit(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
+                 uint32_t rollouts_per_leaf, uint64_t first_rollout_id) {
+    return mctsb_submit_x(b, game, policy, leaf_states, n_leaves, rollouts_per_leaf, first_rollout_id, 0u);
+}
+
+int mctsb_wait_x(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums, uint64_t *legal) {
     if (!b) return MCTSB_ERR_BAD_ARG;
     if (!b->pending) return MCTSB_ERR_NOT_SUBMITTED;
+    if (legal && !b->pend_legal) return MCTSB_ERR_BAD_ARG;          // masks were not asked for at submit time
     CK(cudaSetDevice(b->device));
     b->pending = false;
     CK(cudaStreamSynchronize(b->stream));
@@ -236,8 +230,11 @@ int mctsb_wait(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums) {
         if (sums) sums[i] = h[i];
         if (score_sum) score_sum[i] = mctsb_leaf_sum_to_double(&h[i]);
     }
+    if (legal) memcpy(legal, b->h_legal, (size_t)b->pend_leaves * 4 * sizeof(uint64_t));
     return MCTSB_OK;
 }
+
+int mctsb_wait(mctsb_backend *b, double *score_sum, mctsb_leaf_sum *sums) { return mctsb_wait_x(b, score_sum, sums, nullptr); }
 
 int mctsb_rollout_batch(mctsb_backend *b, int game, int policy, const void *leaf_states, int n_leaves,
                         uint32_t rollouts_per_leaf, uint64_t first_rollout_id, double *score_sum, mctsb_leaf_sum *sums) {

@@ -26,14 +26,14 @@ Quoridor_move *Quoridor_move::from_canonical_id(int id, char player) {
     return new Quoridor_move((short)((id - 145) / 8), (short)((id - 145) % 8), player, 'v');
 }
 
-Quoridor_state::Quoridor_state() : rollout_policy(MCTSB_POLICY_REF) {   // Quoridor.cpp:17-23
+Quoridor_state::Quoridor_state() : rollout_policy(MCTSB_POLICY_REF), have_legal_mask(false) {   // Quoridor.cpp:17-23
     mctsb_qstate p;
     memset(&p, 0, sizeof p);
     p.wx = 0; p.wy = 4; p.bx = 8; p.by = 4; p.wwalls = 10; p.bwalls = 10;
     q_unpack(s, p);
 }
 
-Quoridor_state::Quoridor_state(const mctsb_qstate &packed, int rollout_policy) : rollout_policy(rollout_policy) {
+Quoridor_state::Quoridor_state(const mctsb_qstate &packed, int rollout_policy) : rollout_policy(rollout_policy), have_legal_mask(false) {
     if (!q_unpack(s, packed)) throw std::invalid_argument("Quoridor_state: packed record is not a position");
 }
 
@@ -109,7 +109,13 @@ queue<MCTS_move *> *Quoridor_state::generate_all_moves() const {
     queue<MCTS_move *> *Q = new queue<MCTS_move *>();
     char p = whose_turn();
     uint32_t steps; uint64_t lh, lv;
-    q_legal_parts(s, steps, lh, lv, nullptr);
+    if (have_legal_mask) {
+        // the move-generation kernel already answered (gpu_set_legal): ids 81..144 = horizontal anchors,
+        // 145..208 = vertical anchors (inverse of q_parts_to_mask); the step candidates need no search
+        steps = q_step_mask(s);
+        lh = (legal_mask[1] >> 17) | (legal_mask[2] << 47);
+        lv = (legal_mask[2] >> 17) | (legal_mask[3] << 47);
+    } else q_legal_parts(s, steps, lh, lv, nullptr);
     // generate_all_moves order (Quoridor.cpp:594-616): steps in reversed candidate order, then anchors
     // row-major with the horizontal wall before the vertical one
     for (int i = 11; i >= 0; i--)
@@ -125,8 +131,22 @@ queue<MCTS_move *> *Quoridor_state::actions_to_try() const { return generate_all
 
 MCTS_state *Quoridor_state::next_state(const MCTS_move *move) const {   // Quoridor.cpp:506-510
     Quoridor_state *n = new Quoridor_state(*this);
+    n->have_legal_mask = false;
     n->play_move((const Quoridor_move *) move);
     return n;
+}
+
+// a move out of generate_all_moves(): play it without asking legal_move again (two flood fills for a wall)
+MCTS_state *Quoridor_state::next_state_of_listed_move(const MCTS_move *move) const {
+    Quoridor_state *n = new Quoridor_state(*this);
+    n->have_legal_mask = false;
+    q_play_id(n->s, ((const Quoridor_move *) move)->canonical_id());
+    return n;
+}
+
+void Quoridor_state::gpu_set_legal(const uint64_t *mask4) {
+    memcpy(legal_mask, mask4, sizeof legal_mask);
+    have_legal_mask = true;
 }
 
 double Quoridor_state::evaluate() const { return q_eval(s, nullptr); }

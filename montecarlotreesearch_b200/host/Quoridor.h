@@ -29,6 +29,7 @@ struct Quoridor_move : public MCTS_move {
 class Quoridor_state : public MCTS_state {
     mutable mctsb::QState s;           // mutable: the cached shortest paths are filled lazily, as wdists/bdists are
     int rollout_policy;                // MCTSB_POLICY_REF (default) or MCTSB_POLICY_UNI
+    uint64_t legal_mask[4]; bool have_legal_mask;   // the device's answer to generate_all_moves for this position, if it came
 public:
     Quoridor_state();
     explicit Quoridor_state(const mctsb_qstate &packed, int rollout_policy = 0);
@@ -57,6 +58,8 @@ public:
     int gpu_game_id() const override { return MCTSB_GAME_QUORIDOR; }
     int gpu_policy_id() const override { return rollout_policy; }
     bool gpu_pack(void *dst) const override;
+    void gpu_set_legal(const uint64_t *mask4) override;
+    MCTS_state *next_state_of_listed_move(const MCTS_move *move) const override;
 };
 
 #endif

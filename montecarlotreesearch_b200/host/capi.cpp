@@ -6,6 +6,7 @@
 #include "Quoridor.h"
 #include "TicTacToe.h"
 #include "mctsb.h"
+#include "../csrc/qcore.cuh"
 #include <cstring>
 #include <deque>
 #include <memory>
@@ -20,10 +21,27 @@ class CallbackBackend : public RolloutBackend {
     mcts_rollout_cb cb; void *user;
     struct Held { int g, p, n; uint32_t R; uint64_t first; std::vector<unsigned char> states; };
     std::deque<Held> held;
+    bool expand = false, have_legal = false;
+    std::vector<uint64_t> legal;
+    // the masks the move-generation kernel would return, from the same shared rule code compiled for the host:
+    // lets a machine without a GPU exercise the tree's mask -> move list path
+    void masks(int game, const void *states, int n) {
+        have_legal = expand && game == MCTSB_GAME_QUORIDOR;
+        if (!have_legal) return;
+        legal.assign((size_t)n * 4, 0);
+        for (int i = 0; i < n; i++) {
+            mctsb::QState q;
+            mctsb::q_unpack(q, ((const mctsb_qstate *)states)[i]);
+            mctsb::q_legal_moves(q, &legal[4 * (size_t)i]);
+        }
+    }
 public:
     CallbackBackend(mcts_rollout_cb cb, void *user) : cb(cb), user(user) {}
+    void set_expand(bool on) override { expand = on; }
+    const uint64_t *last_legal() const override { return have_legal ? legal.data() : nullptr; }
     void rollout_batch(int game, int policy, const void *states, int n_leaves, uint32_t rpl, uint64_t first_id, double *out) override {
         cb(game, policy, states, n_leaves, rpl, first_id, out, user);
+        masks(game, states, n_leaves);
     }
     void submit(int game, int policy, const void *states, int n_leaves, uint32_t rpl, uint64_t first_id) override {
         size_t rec = game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate);
@@ -34,6 +52,7 @@ public:
     void wait(double *out) override {
         Held h = std::move(held.front()); held.pop_front();
         cb(h.g, h.p, h.states.data(), h.n, h.R, h.first, out, user);
+        masks(h.g, h.states.data(), h.n);
     }
     int max_in_flight() const override { return 4; }
 };
@@ -134,6 +153,48 @@ void mcts_host_set_overlap(void *hs, int on) {
     h->tree->set_batching(b);
 }
 
+void mcts_host_set_gpu_expand(void *hs, int on) {
+    HostSession *h = (HostSession *)hs;
+    MCTS_batching b = h->tree->get_batching();
+    b.gpu_expand = on != 0;
+    h->tree->set_batching(b);
+}
+
+// wall seconds inside grow_tree so far, and the part of them inside backend calls (the rest is the host tree)
+void mcts_host_times(void *hs, double *total, double *backend) {
+    HostSession *h = (HostSession *)hs;
+    *total = h->tree->get_seconds_total(); *backend = h->tree->get_seconds_backend();
+}
+
+// ---- multi-GPU exchange: NCCL behind the C ABI, reached through the session's CUDA backend -----------------
+int mcts_host_comm_unique_id(void *id128) { return mctsb_comm_unique_id(id128); }
+
+static int comm_fail(const std::exception &e, char *err, int err_cap) {
+    if (err && err_cap > 0) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; }
+    return -1;
+}
+
+int mcts_host_comm_init_rank(void *hs, const void *id128, int world, int rank, char *err, int err_cap) {
+    try {
+        CudaRolloutBackend *be = dynamic_cast<CudaRolloutBackend *>(((HostSession *)hs)->backend.get());
+        if (!be) throw std::runtime_error("the session does not run on the CUDA backend");
+        be->comm_init_rank(id128, world, rank);
+        return 0;
+    } catch (const std::exception &e) { return comm_fail(e, err, err_cap); }
+}
+
+// root-parallel trees: sum the root-child statistics over the ranks (MCTS_tree::merge_root_stats)
+int mcts_host_merge_root(void *hs, char *err, int err_cap) {
+    try { ((HostSession *)hs)->tree->merge_root_stats(); return 0; }
+    catch (const std::exception &e) { return comm_fail(e, err, err_cap); }
+}
+
+// the same sum over any small vector of doubles (move agreement checks, totals)
+int mcts_host_allreduce(void *hs, double *v, int n, char *err, int err_cap) {
+    try { ((HostSession *)hs)->backend->allreduce_sum(v, n); return 0; }
+    catch (const std::exception &e) { return comm_fail(e, err, err_cap); }
+}
+
 int mcts_host_grow(void *hs, int max_iter, double max_seconds, char *err, int err_cap) {
     try { ((HostSession *)hs)->tree->grow_tree(max_iter, max_seconds); return 0; }
     catch (const std::exception &e) { if (err && err_cap > 0) { strncpy(err, e.what(), err_cap - 1); err[err_cap - 1] = 0; } return -1; }
@@ -175,6 +236,8 @@ int mcts_host_current_state(void *hs, void *packed_out) {
 
 // the Philox stream id the next flush of ANY tree in this process will start at (ids are never reused)
 uint64_t mcts_host_peek_rollout_id(void) { return next_rollout_ids(0); }
+// tests only: two trees that must draw the same streams are started from the same id
+void mcts_host_set_next_rollout_id(uint64_t id) { set_next_rollout_id(id); }
 
 void mcts_host_counters(void *hs, uint64_t *flushes, uint64_t *rollouts) {
     HostSession *h = (HostSession *)hs;

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <chrono>
 #include <ctime>
 
 static bool g_verbose = true;
@@ -19,7 +20,7 @@ void mcts_set_verbose(bool on) { g_verbose = on; }
 // nodes: they are played out once and never selected again) never pays for move generation.
 MCTS_node::MCTS_node(MCTS_node *parent, MCTS_state *state, const MCTS_move *move, MCTS_tree *tree)
     : terminal(false), size(0), number_of_simulations(0), score(0.0), state(state), move(move),
-      children(new vector<MCTS_node *>()), parent(parent), untried_actions(NULL), tree(tree), virtual_visits(0) {
+      children(new vector<MCTS_node *>()), index_in_parent(0), parent(parent), untried_actions(NULL), tree(tree), virtual_visits(0) {
     terminal = state->is_terminal();
 }
 
@@ -27,6 +28,7 @@ queue<MCTS_move *> *MCTS_node::actions() const {
     if (untried_actions == NULL) {
         untried_actions = state->actions_to_try();
         children->reserve(STARTING_NUMBER_OF_CHILDREN);
+        const_cast<MCTS_node *>(this)->child_stats.reserve(STARTING_NUMBER_OF_CHILDREN);
     }
     return untried_actions;
 }
@@ -53,9 +55,11 @@ MCTS_node *MCTS_node::expand_no_rollout() {
     if (terminal || actions()->empty()) return NULL;
     MCTS_move *next_move = untried_actions->front();
     untried_actions->pop();
-    MCTS_state *next = state->next_state(next_move);
+    MCTS_state *next = state->next_state_of_listed_move(next_move);    // the move comes from this state's own list
     MCTS_node *child = new MCTS_node(this, next, next_move, tree);
+    child->index_in_parent = (uint32_t)children->size();
     children->push_back(child);
+    child_stats.push_back(MCTS_child_stat{0.0, 0.0, 0.0});
     return child;
 }
 
@@ -80,7 +84,7 @@ void MCTS_node::rollout() {
         double sum = 0.0;
         be->rollout_batch(game, state->gpu_policy_id(), packed, 1, R, next_rollout_ids(R), &sum);
         if (tree) { tree->flushes++; tree->rollouts_played += R; }
-        backpropagate(sum, (int)R);
+        backpropagate(sum, R);
         return;
     }
     // a game the backend does not know: its own virtual rollout(), validated like mcts.cpp:68-75
@@ -90,41 +94,78 @@ void MCTS_node::rollout() {
         if (r >= 0.0 && r <= 1.0) sum += r;
         else cerr << "Warning: Invalid result when aggregating parallel rollouts" << endl;
     }
-    backpropagate(sum, (int)R);
+    backpropagate(sum, R);
+}
+
+void MCTS_node::mirror_to_parent() {
+    if (parent == NULL) return;
+    MCTS_child_stat &c = parent->child_stats[index_in_parent];
+    c.score = score; c.visits = (double)(number_of_simulations + virtual_visits); c.virtual_visits = (double)virtual_visits;
+}
+
+void MCTS_node::rebuild_child_stats() {
+    child_stats.resize(children->size());
+    for (size_t i = 0; i < children->size(); i++) {
+        MCTS_node *c = children->at(i);
+        c->index_in_parent = (uint32_t)i;
+        child_stats[i] = MCTS_child_stat{c->score, (double)(c->number_of_simulations + c->virtual_visits), (double)c->virtual_visits};
+    }
 }
 
 // reference mcts.cpp:83-90: score += w; n += n; every ancestor's `size` counts the event
-void MCTS_node::backpropagate(double w, int n) {
+void MCTS_node::backpropagate(double w, uint64_t n) {
     for (MCTS_node *node = this; node != NULL; node = node->parent) {
         node->score += w;
-        node->number_of_simulations += (unsigned)n;
+        node->number_of_simulations += n;
+        node->mirror_to_parent();
         if (node->parent != NULL) node->parent->size++;
     }
 }
 
-void MCTS_node::add_virtual(int n) {
-    for (MCTS_node *node = this; node != NULL; node = node->parent) node->virtual_visits = (unsigned)((int)node->virtual_visits + n);
+void MCTS_node::add_virtual(int64_t n) {
+    for (MCTS_node *node = this; node != NULL; node = node->parent) {
+        node->virtual_visits = (uint64_t)((int64_t)node->virtual_visits + n);
+        node->mirror_to_parent();
+    }
 }
 
 // reference mcts.cpp:104-130.  UCT on the win rate of the side to move AT THIS NODE; first strict
 // maximum wins; c <= 0 means pure win rate.  Simulations still in flight (virtual_visits) count as
-// losses for the side choosing here — zero unless leaves_per_flush > 1.
+// losses for the side choosing here — zero unless leaves_per_flush > 1.  Reads the parent's own array of
+// child statistics, never the children.
+__attribute__((target_clones("avx2", "default")))
 MCTS_node *MCTS_node::select_best_child(double c) const {
     if (children->empty()) return NULL;
     if (children->size() == 1) return children->at(0);
     double best = -1;
-    MCTS_node *argmax = NULL;
+    size_t argmax = children->size();
     const bool p1 = state->player1_turn();
     const double n_parent = (double)(number_of_simulations + virtual_visits);
-    for (MCTS_node *child : *children) {
-        double n = (double)(child->number_of_simulations + child->virtual_visits);
-        double s = child->score + (p1 ? 0.0 : (double)child->virtual_visits);
-        double winrate = s / n;
-        if (!p1) winrate = 1.0 - winrate;
-        double uct = c > 0 ? winrate + c * sqrt(log(n_parent) / n) : winrate;
-        if (uct > best) { best = uct; argmax = child; }
+    const double log_parent = c > 0 ? log(n_parent) : 0.0;      // the same value for every child (mcts.cpp:121 computes it per child)
+    const MCTS_child_stat *cs = child_stats.data();
+    const size_t e = children->size();
+    // pass 1: every child's value, the reference's expression term by term (IEEE division and square root give
+    // the same bits in vector and scalar form, so the compiler may run this loop four children at a time)
+    static thread_local vector<double> value;
+    value.resize(e);
+    double *v = value.data();
+    const double virt_as_loss = p1 ? 0.0 : 1.0, sign = p1 ? 1.0 : -1.0, base = p1 ? 0.0 : 1.0;
+    if (c > 0) {
+        for (size_t i = 0; i < e; i++) {
+            const double n = cs[i].visits;
+            const double s = cs[i].score + virt_as_loss * cs[i].virtual_visits;
+            v[i] = (base + sign * (s / n)) + c * sqrt(log_parent / n);
+        }
+    } else {
+        for (size_t i = 0; i < e; i++) {
+            const double n = cs[i].visits;
+            const double s = cs[i].score + virt_as_loss * cs[i].virtual_visits;
+            v[i] = base + sign * (s / n);
+        }
     }
-    return argmax;
+    // pass 2: first strict maximum (mcts.cpp:123)
+    for (size_t i = 0; i < e; i++) if (v[i] > best) { best = v[i]; argmax = i; }
+    return argmax < children->size() ? children->at(argmax) : NULL;
 }
 
 // reference mcts.cpp:132-157
@@ -135,6 +176,7 @@ MCTS_node *MCTS_node::advance_tree(const MCTS_move *m) {
         else delete child;
     }
     children->clear();
+    child_stats.clear();
     if (next == NULL) {
         if (g_verbose) cout << "INFO: Didn't find child node. Had to start over." << endl;
         next = new MCTS_node(NULL, state->next_state(m), NULL, tree);
@@ -161,6 +203,7 @@ void MCTS_node::print_stats() const {
     std::sort(children->begin(), children->end(), [p1](const MCTS_node *a, const MCTS_node *b) {
         return a->calculate_winrate(p1) > b->calculate_winrate(p1);
     });
+    const_cast<MCTS_node *>(this)->rebuild_child_stats();
     cout << "Best moves:" << endl;
     for (unsigned i = 0; i < children->size() && i < TOPK; i++)
         cout << "  " << i + 1 << ". " << children->at(i)->move->sprint() << "  -->  "
@@ -171,13 +214,13 @@ void MCTS_node::print_stats() const {
 
 /*** MCTS_tree ***/
 
-MCTS_tree::MCTS_tree(MCTS_state *starting_state) : root(NULL), backend(NULL), flushes(0), rollouts_played(0) {
+MCTS_tree::MCTS_tree(MCTS_state *starting_state) : root(NULL), backend(NULL), flushes(0), rollouts_played(0), seconds_total(0), seconds_backend(0) {
     assert(starting_state != NULL);
     root = new MCTS_node(NULL, starting_state, NULL, this);
 }
 
 MCTS_tree::MCTS_tree(MCTS_state *starting_state, RolloutBackend *backend, MCTS_batching batching)
-    : root(NULL), backend(backend), batching(batching), flushes(0), rollouts_played(0) {
+    : root(NULL), backend(backend), batching(batching), flushes(0), rollouts_played(0), seconds_total(0), seconds_backend(0) {
     assert(starting_state != NULL);
     root = new MCTS_node(NULL, starting_state, NULL, this);
 }
@@ -196,6 +239,39 @@ MCTS_node *MCTS_tree::select(double c) {
     return node;
 }
 
+namespace {
+struct BackendTimer {                        // adds the lifetime of the object to a seconds counter
+    double &acc; std::chrono::steady_clock::time_point t0;
+    explicit BackendTimer(double &acc) : acc(acc), t0(std::chrono::steady_clock::now()) {}
+    ~BackendTimer() { acc += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+}
+
+// Expansion prepared on the device (MCTS_batching::gpu_expand): the backend's move-generation kernel ran over
+// the leaves of the submission that was just collected; every leaf keeps its mask for the day it is expanded.
+void MCTS_tree::apply_legal_masks(const vector<MCTS_node *> &leaves, size_t first, size_t count) {
+    if (!batching.gpu_expand) return;
+    const uint64_t *legal = get_backend()->last_legal();
+    if (legal == NULL) return;
+    for (size_t k = 0; k < count; k++) {
+        MCTS_node *leaf = leaves[first + k];
+        if (leaf->untried_actions == NULL && !leaf->terminal) leaf->state->gpu_set_legal(legal + 4 * k);
+    }
+}
+
+// collect everything that is still on the GPU and give the unflushed leaves their virtual loss back: the tree
+// is consistent again (used when a backend call throws in the middle of grow_tree)
+void MCTS_tree::drain(deque<vector<MCTS_node *>> &inflight, vector<MCTS_node *> &leaves) {
+    const uint32_t R = batching.rollouts_per_leaf;
+    while (!inflight.empty()) {
+        try { collect_leaves(inflight.front()); }
+        catch (...) { for (MCTS_node *l : inflight.front()) l->add_virtual(-(int64_t)R); }
+        inflight.pop_front();
+    }
+    for (MCTS_node *l : leaves) l->add_virtual(-(int64_t)R);
+    leaves.clear();
+}
+
 // One kernel launch for all the leaves collected by grow_tree: every leaf gets rollouts_per_leaf
 // playouts; results come back as one exact sum per leaf and are back-propagated in selection order.
 void MCTS_tree::flush_leaves(vector<MCTS_node *> &leaves) {
@@ -205,7 +281,7 @@ void MCTS_tree::flush_leaves(vector<MCTS_node *> &leaves) {
     while (i < leaves.size()) {
         // group consecutive leaves that the backend can take in one call (same game/policy); others fall back
         int game = leaves[i]->state->gpu_game_id();
-        if (game < 0) { leaves[i]->add_virtual(-(int)R); leaves[i]->rollout(); i++; continue; }
+        if (game < 0) { leaves[i]->add_virtual(-(int64_t)R); leaves[i]->rollout(); i++; continue; }
         int policy = leaves[i]->state->gpu_policy_id();
         size_t rec = game == MCTSB_GAME_QUORIDOR ? sizeof(mctsb_qstate) : sizeof(mctsb_tstate), j = i;
         vector<unsigned char> packed;
@@ -215,11 +291,15 @@ void MCTS_tree::flush_leaves(vector<MCTS_node *> &leaves) {
             j++;
         }
         vector<double> sums(j - i, 0.0);
-        get_backend()->rollout_batch(game, policy, packed.data(), (int)(j - i), R, next_rollout_ids((uint64_t)R * (j - i)), sums.data());
+        {
+            BackendTimer t(seconds_backend);
+            get_backend()->rollout_batch(game, policy, packed.data(), (int)(j - i), R, next_rollout_ids((uint64_t)R * (j - i)), sums.data());
+        }
         flushes++; rollouts_played += (uint64_t)R * (j - i);
+        apply_legal_masks(leaves, i, j - i);
         for (size_t k = i; k < j; k++) {
-            leaves[k]->add_virtual(-(int)R);
-            leaves[k]->backpropagate(sums[k - i], (int)R);
+            leaves[k]->add_virtual(-(int64_t)R);
+            leaves[k]->backpropagate(sums[k - i], R);
         }
         i = j;
     }
@@ -238,18 +318,25 @@ bool MCTS_tree::submit_leaves(const vector<MCTS_node *> &leaves) {
         if (!leaves[k]->state->gpu_pack(&packed[k * rec])) return false;
     }
     const uint32_t R = batching.rollouts_per_leaf;
-    get_backend()->submit(game, policy, packed.data(), (int)leaves.size(), R, next_rollout_ids((uint64_t)R * leaves.size()));
+    {
+        BackendTimer t(seconds_backend);
+        get_backend()->submit(game, policy, packed.data(), (int)leaves.size(), R, next_rollout_ids((uint64_t)R * leaves.size()));
+    }
     flushes++; rollouts_played += (uint64_t)R * leaves.size();
     return true;
 }
 
 void MCTS_tree::collect_leaves(vector<MCTS_node *> &leaves) {
     vector<double> sums(leaves.size(), 0.0);
-    get_backend()->wait(sums.data());
+    {
+        BackendTimer t(seconds_backend);
+        get_backend()->wait(sums.data());
+    }
+    apply_legal_masks(leaves, 0, leaves.size());
     const uint32_t R = batching.rollouts_per_leaf;
     for (size_t k = 0; k < leaves.size(); k++) {
-        leaves[k]->add_virtual(-(int)R);
-        leaves[k]->backpropagate(sums[k], (int)R);
+        leaves[k]->add_virtual(-(int64_t)R);
+        leaves[k]->backpropagate(sums[k], R);
     }
     leaves.clear();
 }
@@ -258,6 +345,8 @@ void MCTS_tree::collect_leaves(vector<MCTS_node *> &leaves) {
 // stopped early when difftime(now, start) > max_time (whole seconds, strict).
 void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
     if (g_verbose) cout << "Growing tree..." << endl;
+    BackendTimer whole(seconds_total);
+    get_backend()->set_expand(batching.gpu_expand);
     time_t start_t, now_t;
     time(&start_t);
     double dt = 0;
@@ -283,12 +372,13 @@ void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
             const size_t cap = (size_t)get_backend()->max_in_flight();
             if (depth > cap) depth = cap;
         }
+        try {
         while (i < max_iter || !inflight.empty()) {
             for (uint32_t k = 0; k < K && i < max_iter; k++, i++) {
                 MCTS_node *node = select();
                 MCTS_node *leaf = node->is_terminal() ? node : node->expand_no_rollout();
                 if (leaf == NULL) leaf = node;                        // cannot happen: select() returns expandable or terminal nodes
-                leaf->add_virtual((int)batching.rollouts_per_leaf);   // keep the next selection away from this path
+                leaf->add_virtual((int64_t)batching.rollouts_per_leaf);   // keep the next selection away from this path
                 leaves.push_back(leaf);
             }
             // the GPU ran the queued flushes while the host selected: take the oldest results when the queue is
@@ -311,6 +401,11 @@ void MCTS_tree::grow_tree(int max_iter, double max_time_in_seconds) {
                 while (!inflight.empty()) { collect_leaves(inflight.front()); inflight.pop_front(); }
                 break;
             }
+        }
+        } catch (...) {
+            // a backend call failed: no virtual loss may stay behind and nothing may stay queued on the GPU
+            drain(inflight, leaves);
+            throw;
         }
     }
     if (g_verbose) {
@@ -346,7 +441,7 @@ void MCTS_tree::export_root_stats(vector<double> &out) const {
     out.assign(2 * acts.size(), 0.0);
     for (MCTS_node *c : *root->children)
         for (size_t k = 0; k < acts.size(); k++)
-            if (*acts[k] == *c->move) { out[2 * k] = c->number_of_simulations; out[2 * k + 1] = c->score; break; }
+            if (*acts[k] == *c->move) { out[2 * k] = (double)c->number_of_simulations; out[2 * k + 1] = c->score; break; }
     for (MCTS_move *m : acts) delete m;
 }
 
@@ -361,15 +456,25 @@ void MCTS_tree::import_root_stats(const vector<double> &in) {
     for (MCTS_node *c : *root->children)
         for (size_t k = 0; k < acts.size(); k++)
             if (*acts[k] == *c->move) {
-                c->number_of_simulations = (unsigned)in[2 * k]; c->score = in[2 * k + 1];
+                c->number_of_simulations = (uint64_t)in[2 * k]; c->score = in[2 * k + 1];
                 sims += in[2 * k]; score += in[2 * k + 1];
                 break;
             }
-    root->number_of_simulations = (unsigned)sims;
+    root->number_of_simulations = (uint64_t)sims;
     root->score = score;
+    root->rebuild_child_stats();
     for (MCTS_move *m : acts) delete m;
 }
 
+
+void MCTS_tree::merge_root_stats() {
+    if (get_backend()->world() == 1) return;
+    vector<double> v;
+    export_root_stats(v);
+    if (v.empty()) return;
+    get_backend()->allreduce_sum(v.data(), (int)v.size());
+    import_root_stats(v);
+}
 
 /*** MCTS_agent ***/
 

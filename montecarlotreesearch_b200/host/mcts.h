@@ -33,26 +33,43 @@ struct MCTS_batching {
     // keep the GPU busy across the hand-over: a 65 536-playout flush occupies only 2 048 of the 2 960 resident
     // warps of a B200, the second one fills the rest and takes over when the first drains.
     uint32_t flushes_in_flight = 1;
+    // Expansion prepared on the device: every flush also runs its leaves through the backend's move-generation
+    // kernel, and a leaf keeps the legal-move mask that comes back — when it is selected again its move list is
+    // read off the mask (same list, same order) instead of being generated on the CPU (mcts.cpp:19).
+    bool gpu_expand = false;
 };
 
 class MCTS_tree;
+
+// What UCT reads of a child, kept in one array per parent: selection walks 131 children per level at the
+// root of a Quoridor tree, and with a child's statistics inside the child every one of them is a cache miss.
+struct MCTS_child_stat {
+    double score;
+    double visits;          // simulations + virtual visits (exact: far below 2^53)
+    double virtual_visits;
+};
 
 class MCTS_node {
     friend class MCTS_tree;
     bool terminal;
     unsigned int size;
-    unsigned int number_of_simulations;
+    uint64_t number_of_simulations;        // the reference counts in an unsigned int (mcts.h:29): at 4 rollouts per
+                                           // iteration that lasts; at 65 536 per flush it wraps within minutes
     double score;
     MCTS_state *state;
     const MCTS_move *move;
     vector<MCTS_node *> *children;
+    vector<MCTS_child_stat> child_stats;   // child_stats[i] mirrors children->at(i)
+    uint32_t index_in_parent;
     MCTS_node *parent;
     mutable queue<MCTS_move *> *untried_actions;   // generated on first use (actions())
     MCTS_tree *tree;                       // owner (batching parameters, backend, rollout ids); may be NULL
-    unsigned int virtual_visits;           // pending simulations counted as losses while a flush is in flight
-    void backpropagate(double w, int n);
+    uint64_t virtual_visits;               // pending simulations counted as losses while a flush is in flight
+    void backpropagate(double w, uint64_t n);
     queue<MCTS_move *> *actions() const;
-    void add_virtual(int n);
+    void add_virtual(int64_t n);
+    void mirror_to_parent();
+    void rebuild_child_stats();
     MCTS_node *expand_no_rollout();        // Expansion without Simulation; NULL when nothing to expand
 public:
     MCTS_node(MCTS_node *parent, MCTS_state *state, const MCTS_move *move, MCTS_tree *tree = NULL);
@@ -69,7 +86,7 @@ public:
     void print_stats() const;
     double calculate_winrate(bool player1turn) const;
     // read-only accessors (not in the reference; used by tests and the multi-GPU root merge)
-    unsigned int get_number_of_simulations() const { return number_of_simulations; }
+    uint64_t get_number_of_simulations() const { return number_of_simulations; }
     double get_score() const { return score; }
     const vector<MCTS_node *> &get_children() const { return *children; }
 };
@@ -81,7 +98,10 @@ class MCTS_tree {
     RolloutBackend *backend;               // not owned; NULL = process default (created on first use)
     MCTS_batching batching;
     uint64_t flushes, rollouts_played;
+    double seconds_total, seconds_backend;  // wall time inside grow_tree / of it, inside backend calls (submit, wait)
     RolloutBackend *get_backend();
+    void apply_legal_masks(const vector<MCTS_node *> &leaves, size_t first, size_t count);
+    void drain(deque<vector<MCTS_node *>> &inflight, vector<MCTS_node *> &leaves);
     void flush_leaves(vector<MCTS_node *> &leaves);
     bool submit_leaves(const vector<MCTS_node *> &leaves);      // asynchronous half of flush_leaves; false = not batchable
     void collect_leaves(vector<MCTS_node *> &leaves);           // wait + backpropagate
@@ -102,10 +122,18 @@ public:
     const MCTS_node *get_root() const { return root; }
     uint64_t get_flushes() const { return flushes; }
     uint64_t get_rollouts_played() const { return rollouts_played; }
+    // where grow_tree's wall time went: all of it, and the part spent inside backend calls (copying leaves in,
+    // waiting for the GPU); the difference is the host tree — selection, expansion, backpropagation
+    double get_seconds_total() const { return seconds_total; }
+    double get_seconds_backend() const { return seconds_backend; }
     // Root-parallel merge: add other trees' root-child statistics, keyed by the
     // position of the child's move in the root's actions_to_try() order.
     void export_root_stats(vector<double> &visits_and_scores) const;     // 2 doubles per root action
     void import_root_stats(const vector<double> &visits_and_scores);     // REPLACES the children's statistics
+    // export -> sum over the GPUs the backend is joined with (RolloutBackend::allreduce_sum: NCCL behind the C
+    // ABI) -> import: afterwards select_best_child() applies the reference's final choice rule
+    // (mcts.cpp:104-129 with c = 0, :268-270) to the same numbers on every rank.  No-op for a lone backend.
+    void merge_root_stats();
 };
 
 

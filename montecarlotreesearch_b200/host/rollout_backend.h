@@ -28,6 +28,18 @@ public:
                         uint32_t rollouts_per_leaf, uint64_t first_rollout_id) = 0;
     virtual void wait(double *score_sum) = 0;
     virtual int max_in_flight() const { return 1; }
+    // Optional: prepare the next Expansion on the device.  After set_expand(true) every submission of a game the
+    // backend can generate moves for also returns the legal-move masks of its leaves (209 bits = 4 words per
+    // leaf, canonical ids of include/mctsb.h); last_legal() is valid after the wait() / rollout_batch() that
+    // returned the submission's sums, until the next call, and is NULL when no masks came back.
+    virtual void set_expand(bool on) { (void)on; }
+    virtual const uint64_t *last_legal() const { return nullptr; }
+    // Multi-GPU exchange: in-place sum of `v` over the GPUs this backend was joined with; a
+    // backend that stands alone (world() == 1) leaves `v` as it is.  Root-parallel trees call it once per move
+    // with their root-child statistics (MCTS_tree::merge_root_stats).
+    virtual int world() const { return 1; }
+    virtual int rank() const { return 0; }
+    virtual void allreduce_sum(double *v, int n) { (void)v; (void)n; }
 };
 
 class BackendError : public std::runtime_error {
@@ -44,6 +56,9 @@ class CudaRolloutBackend : public RolloutBackend {
     mctsb_backend *handles[MAX_HANDLES];
     int device; uint64_t seed;
     unsigned submitted, collected;         // FIFO positions
+    bool expand;                           // ask for legal-move masks with every Quoridor submission
+    int slot_leaves[MAX_HANDLES]; bool slot_legal[MAX_HANDLES];
+    std::vector<uint64_t> legal; bool have_legal;
     mctsb_backend *slot(unsigned i);
 public:
     explicit CudaRolloutBackend(int device = 0, uint64_t seed = 0x2026101900000001ull);   // throws BackendError without a GPU
@@ -56,7 +71,19 @@ public:
                 uint64_t first_rollout_id) override;
     void wait(double *score_sum) override;
     int max_in_flight() const override { return MAX_HANDLES; }
+    void set_expand(bool on) override { expand = on; }
+    const uint64_t *last_legal() const override { return have_legal ? legal.data() : nullptr; }
     mctsb_backend *raw() const { return handle; }
+    // NCCL behind the C ABI (mctsb_comm_*): one process per GPU joins with an id made by rank 0
+    // (comm_unique_id -> ship the bytes -> comm_init_rank); one process with a backend per GPU uses comm_init_all
+    // and reduces the vectors of all its backends together with allreduce_sum_group.
+    static std::vector<unsigned char> comm_unique_id();
+    void comm_init_rank(const void *id128, int world, int rank);
+    static void comm_init_all(const std::vector<CudaRolloutBackend *> &backends);
+    static void allreduce_sum_group(const std::vector<CudaRolloutBackend *> &backends, const std::vector<double *> &vecs, int n);
+    int world() const override;
+    int rank() const override;
+    void allreduce_sum(double *v, int n) override;
 };
 
 // Process-wide default used by MCTS_tree / MCTS_state::rollout() when none is given: created on
@@ -64,5 +91,6 @@ public:
 RolloutBackend *default_rollout_backend();
 void set_default_rollout_backend(RolloutBackend *b);    // not owned
 uint64_t next_rollout_ids(uint64_t count);              // process-wide Philox stream id allocator
+void set_next_rollout_id(uint64_t id);                  // replaying a search: start the allocator at a chosen id
 
 #endif

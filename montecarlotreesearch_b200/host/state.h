@@ -5,6 +5,7 @@
 #ifndef MCTS_STATE_H
 #define MCTS_STATE_H
 
+#include <cstdint>
 #include <iostream>
 #include <queue>
 #include <stdexcept>
@@ -38,6 +39,13 @@ public:
     virtual int gpu_game_id() const { return -1; }
     virtual int gpu_policy_id() const { return 0; }
     virtual bool gpu_pack(void *dst) const { (void)dst; return false; }
+    // The legal-move mask of this position as the backend's move-generation kernel computed it (4 words,
+    // canonical move ids): a state that keeps it answers its next actions_to_try() from the mask instead of
+    // generating the moves on the CPU.  Same list, same order.
+    virtual void gpu_set_legal(const uint64_t *mask4) { (void)mask4; }
+    // next_state for a move that came out of this state's own actions_to_try(): legal by construction, so a
+    // game may skip the legality test the reference repeats in play_move (Quoridor.cpp:345).
+    virtual MCTS_state *next_state_of_listed_move(const MCTS_move *move) const { return next_state(move); }
 };
 
 

@@ -2,15 +2,20 @@
 """selfplay.py — BASELINE.json configs[3] and [4]: Quoridor full-game MCTS self-play.
 
   1 GPU  (configs[3]): host tree (C++, montecarlotreesearch_b200/host) + B200 rollout backend, every tree
-          flush is K leaves x R rollouts = 65 536 playouts in one kernel launch.
+          flush is K leaves x R rollouts (default 16 x 4096 = 65 536 playouts) in one kernel launch.
   N GPUs (configs[4], launch under torchrun): root-parallel — one tree per rank, same root, different
-          Philox keys; ONE NCCL all-reduce of the root-child statistics per move (2 doubles per root
-          action, slot = position in the root's actions_to_try() order), after which every rank applies
-          the reference's final choice rule (win rate of the side to move, first maximum,
-          mcts.cpp:104-129 with c = 0) to identical numbers and plays the same move.
+          Philox keys; ONE all-reduce of the root-child statistics per move (2 doubles per root action,
+          slot = position in the root's actions_to_try() order) done by the C++ host through the C ABI
+          (MCTS_tree::merge_root_stats -> mctsb_allreduce_root_stats, NCCL over NVLink), after which every rank
+          applies the reference's final choice rule (win rate of the side to move, first maximum,
+          mcts.cpp:104-129 with c = 0, :268-270) to identical numbers and plays the same move.
+          torch.distributed only ships the 128-byte communicator id and provides the start barrier.
 
-Prints one JSON line (rank 0): rollouts/s over the whole game, flush latency, host-tree share of wall
-time, game length and the move list.
+Prints one JSON line (rank 0): rollouts/s over the whole game, flush latency, the host tree's share of the
+search's wall time (selection + expansion + backpropagation, i.e. everything outside backend calls), game
+length, winner and the move list.  --agreement replays the game on ONE GPU with rank 0's seed (same positions,
+tree reuse as in the game) and reports how often its best child is the move the N-GPU search chose.
+The reference's loop of the same shape: examples/Quoridor/main.cpp:129-169.
 """
 import argparse
 import json
@@ -24,14 +29,48 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+def play_game(tree, args, dist_ready, follow=None):
+    """One game on `tree`.  follow = list of move ids to play instead of the tree's own choice (agreement rerun).
+    Returns (moves, own_choices, terminal, seconds in grow, seconds in merge)."""
+    moves, own, t_grow, t_merge = [], [], 0.0, 0.0
+    terminal = False
+    while not terminal and len(moves) < args.max_moves and (follow is None or len(moves) < len(follow)):
+        a = time.perf_counter()
+        tree.grow(args.iters)
+        b = time.perf_counter()
+        t_grow += b - a
+        if dist_ready:
+            tree.merge_root()                          # C++ host -> C ABI -> NCCL; blocks until every rank arrived
+        c = time.perf_counter()
+        t_merge += c - b
+        mv = tree.best_move()
+        if dist_ready and args.check_agreement_across_ranks:
+            # every rank must have picked the same move from the merged statistics: sum(mv) == world * mv and
+            # sum(mv^2) == world * mv^2 only when all values are equal
+            w = tree.allreduce(np.array([1.0, float(mv), float(mv) * mv]))
+            assert w[1] == w[0] * mv and w[2] == w[0] * mv * mv, "ranks disagree on the move after the all-reduce"
+        if mv < 0:
+            break
+        own.append(mv)
+        if follow is not None:
+            mv = follow[len(moves)]
+        moves.append(mv)
+        terminal = tree.advance(mv)
+    return moves, own, terminal, t_grow, t_merge
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=256, help="tree iterations (leaf expansions) per move")
     ap.add_argument("--rollouts-per-leaf", type=int, default=4096)
     ap.add_argument("--leaves-per-flush", type=int, default=16)
-    ap.add_argument("--max-moves", type=int, default=120)
+    ap.add_argument("--max-moves", type=int, default=400)
     ap.add_argument("--overlap", type=int, nargs="?", const=1, default=0,
                     help="flushes in flight: 1 = select the next batch of leaves while the previous flush runs on the GPU, 2 = two flushes queued")
+    ap.add_argument("--gpu-expand", type=int, default=1,
+                    help="1 = every flush also returns its leaves' legal-move masks from the move-generation kernel (no host movegen); 0 = actions_to_try() on the CPU")
+    ap.add_argument("--agreement", action="store_true", help="replay the game on one GPU at rank 0's seed and report per-move best-child agreement")
+    ap.add_argument("--check-agreement-across-ranks", type=int, default=1)
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
 
@@ -41,69 +80,62 @@ def main():
     os.dup2(2, 1)
 
     import montecarlotreesearch_b200 as m
-    from montecarlotreesearch_b200 import multi
-    from tests.hostlib import Session, load
+    from montecarlotreesearch_b200.hosttree import Session, load
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     dist = None
-    import torch
     if world > 1:
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        import torch
         import torch.distributed as dist
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     host = load()
+
+    def new_tree(seed, device):
+        t = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
+                    leaves_per_flush=args.leaves_per_flush, device=device, seed=seed)
+        if args.overlap:
+            t.set_overlap(args.overlap)
+        t.set_gpu_expand(bool(args.gpu_expand))
+        return t
+
     # different Philox key per rank (root-parallel trees must be independent), same root
-    tree = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
-                   leaves_per_flush=args.leaves_per_flush, device=local_rank, seed=args.seed + rank)
-    if args.overlap:
-        tree.set_overlap(args.overlap)
-    moves, t_grow, t_merge, t_skew = [], 0.0, 0.0, 0.0
-    if dist is not None:                               # bring the communicator up before the clock starts
-        dist.all_reduce(torch.zeros(8, dtype=torch.float64, device="cuda"))
-        torch.cuda.synchronize()
+    tree = new_tree(args.seed + rank, local_rank)
+    if dist is not None:
+        # the communicator of the C ABI: rank 0 makes the id, torch.distributed ships it (plumbing only)
+        import torch
+        uid = torch.zeros(m.COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(m.comm_unique_id()), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        tree.comm_init_rank(uid.cpu().numpy().tobytes(), world, rank)
+        tree.allreduce(np.zeros(8))                    # bring the communicator up before the clock starts
         dist.barrier()
     t0 = time.perf_counter()
-    terminal = False
-    while not terminal and len(moves) < args.max_moves:
-        a = time.perf_counter()
-        tree.grow(args.iters)
-        b = time.perf_counter()
-        t_grow += b - a
-        if dist is not None:
-            dist.barrier()                             # waiting for the slowest tree of this move (skew), kept apart
-            b2 = time.perf_counter()
-            t_skew += b2 - b
-            merged = multi.allreduce_root_stats(tree.export_root(), dist, device="cuda")
-            tree.import_root(merged)
-            b = b2
-        c = time.perf_counter()
-        mv = tree.best_move()
-        if dist is not None:
-            # every rank must have picked the same move from the merged statistics: max(mv) == -max(-mv)
-            chk = torch.tensor([mv, -mv], dtype=torch.int64, device="cuda")
-            dist.all_reduce(chk, op=dist.ReduceOp.MAX)
-            assert int(chk[0]) == -int(chk[1]) == mv, "ranks disagree on the move after the all-reduce"
-        if mv < 0:
-            break
-        moves.append(mv)
-        terminal = tree.advance(mv)
-        t_merge += c - b
+    moves, _, terminal, t_grow, t_merge = play_game(tree, args, dist is not None)
     wall = time.perf_counter() - t0
     flushes, rollouts = tree.counters()
+    sec_total, sec_backend = tree.times()
     final = tree.current_state()
+    rollouts_all = float(tree.allreduce(np.array([float(rollouts)]))[0]) if dist is not None else float(rollouts)
     tree.close()
+
+    agreement = None
+    if args.agreement and rank == 0:
+        solo = new_tree(args.seed, local_rank)
+        _, own, _, _, _ = play_game(solo, args, False, follow=moves)
+        solo.close()
+        same = sum(1 for a, b in zip(own, moves) if a == b)
+        agreement = {"moves_compared": len(own), "same_best_child": same, "fraction": same / max(1, len(own)),
+                     "what": "1-GPU search at rank 0's seed over the game's positions (tree reused along the game's moves) vs the move the %d-GPU search played" % world}
     if dist is not None:
-        tot = torch.tensor([float(rollouts)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tot)
-        rollouts_all = float(tot[0])
         dist.barrier()
         dist.destroy_process_group()
-    else:
-        rollouts_all = float(rollouts)
     if rank == 0:
         os.write(real_stdout, (json.dumps({
             "config": "configs[%d]: Quoridor self-play, %d iterations/move, flush = %d leaves x %d rollouts = %d playouts"
@@ -112,9 +144,14 @@ def main():
             "n_gpus": world, "moves": len(moves), "terminal": bool(terminal),
             "winner": "White" if int(final["wx"]) == 8 else "Black" if int(final["bx"]) == 0 else None,
             "rollouts_total": rollouts_all, "rollouts_per_sec": rollouts_all / wall, "wall_s": wall,
+            "leaves_per_flush": args.leaves_per_flush, "rollouts_per_leaf": args.rollouts_per_leaf,
+            "flushes_in_flight": args.overlap, "gpu_expand": bool(args.gpu_expand),
             "flushes_rank0": flushes, "ms_per_flush": 1e3 * t_grow / max(1, flushes),
-            "allreduce_ms_per_move": 1e3 * t_merge / max(1, len(moves)),
-            "wait_for_slowest_rank_ms_per_move": 1e3 * t_skew / max(1, len(moves)),
+            "host_tree_share_of_search_time": (sec_total - sec_backend) / sec_total if sec_total > 0 else None,
+            "search_seconds": sec_total, "backend_seconds": sec_backend,
+            "merge_ms_per_move": 1e3 * t_merge / max(1, len(moves)) if dist is not None else 0.0,
+            "merge": "MCTS_tree::merge_root_stats -> mctsb_allreduce_root_stats (NCCL behind the C ABI); includes waiting for the slowest rank" if dist is not None else None,
+            "agreement_with_1gpu_rerun": agreement,
             "move_ids": moves,
         }) + "\n").encode())
 

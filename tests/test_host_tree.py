@@ -172,6 +172,57 @@ def test_root_parallel_merge(host, port):
     a.close(); b.close()
 
 
+def _tree_signature(t):
+    r = t.root_stats()
+    return r["sims"], r["score"], r["size"], r["children"].tobytes(), t.best_move()
+
+
+@pytest.mark.parametrize("K,in_flight", [(1, 0), (8, 0), (8, 2)])
+def test_expansion_from_device_masks_builds_the_same_tree(host, port, corpus, K, in_flight):
+    """MCTS_batching::gpu_expand: a leaf's move list is read off the legal-move mask that came back with its flush
+    (here the masks come from the shared rule code compiled for the host) — same list, same order, so the tree is
+    the same tree, statistic for statistic, as with actions_to_try() on the CPU (mcts.cpp:19)."""
+    sigs = []
+    for expand in (False, True):
+        base = host.mcts_host_peek_rollout_id()
+        inner = oracle_backend(port)
+
+        def cb(game, policy, states, n_leaves, R, first_id, out, user, base=base, inner=inner):
+            inner(game, policy, states, n_leaves, R, first_id - base, out, user)
+        t = Session(host, m.GAME_QUORIDOR, corpus[4200], rollouts_per_leaf=1, leaves_per_flush=K, callback=cb)
+        t.set_overlap(in_flight)
+        t.set_gpu_expand(expand)
+        t.grow(260)                    # more iterations than root actions: second-level nodes get expanded too
+        sigs.append(_tree_signature(t))
+        mv = t.best_move()
+        t.advance(mv)
+        t.grow(60)                     # the reused subtree keeps working (children expanded from kept masks)
+        sigs[-1] += _tree_signature(t)
+        t.close()
+    assert sigs[0] == sigs[1]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K,R", [(16, 64), (256, 16)])
+def test_gpu_expanded_tree_equals_host_expanded_tree(host, K, R):
+    """The same on the B200: masks from quoridor_movegen_kernel riding on every flush (mctsb_submit_x with
+    MCTSB_SUBMIT_LEGAL) against move lists generated on the CPU; rollout ids aligned, so every statistic agrees."""
+    sigs = []
+    for expand in (False, True):
+        base = host.mcts_host_peek_rollout_id()
+        t = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=R, leaves_per_flush=K, seed=77)
+        host.mcts_host_set_next_rollout_id(0)
+        t.set_gpu_expand(expand)
+        t.grow(4 * K + 300)
+        sigs.append(_tree_signature(t))
+        t.advance(t.best_move())
+        t.grow(2 * K)
+        sigs[-1] += _tree_signature(t)
+        t.close()
+        host.mcts_host_set_next_rollout_id(base + 10 ** 9)
+    assert sigs[0] == sigs[1]
+
+
 @pytest.mark.gpu
 def test_config1_tictactoe_on_gpu_backend(host):
     """BASELINE.json configs[0]: Tic-Tac-Toe from the empty board, 10k iterations, rollouts on the B200."""
