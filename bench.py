@@ -15,8 +15,10 @@ Quoridor.cpp:809-855) of the opening position per GPU, each keyed by its own Phi
   cpu_baseline / --impl reference : the UNMODIFIED reference compiled in oracle/_ref
           (RolloutJobs on its JobScheduler with every host core) timed on this box.
 
-N>1 (torchrun): weak scaling, every rank plays its own id range; one NCCL all-reduce of the exact
-integer root statistics per step is inside the timed region.
+N>1 (torchrun): every rank plays its own id range (weak scaling: `--rollouts` per GPU; `--scaling strong`:
+`--rollouts` split over the GPUs); one all-reduce of the exact integer leaf sums per step — NCCL behind the C
+ABI (mctsb_allreduce_leaf_sums) — is inside the timed region of BOTH `value` and `e2e`.  torch.distributed
+ships the communicator id and provides the barriers.
 """
 import argparse
 import json
@@ -36,10 +38,49 @@ UNIT = "rollouts/s"
 # work, counted by the oracle (oracle/quoridor_oracle.c work counters, 4 000 rollouts under the bench seed):
 # 13 133 BFS levels ("flood-fill steps") x 24 ops + 4 533 cheap wall tests x 12 ops + 49.1 plies x 200 ops
 # (DESIGN.md "Roofline").  The kernel executes fewer steps than this: exact pruning.
-ALG_OPS_PER_ROLLOUT = 13133.3 * 24 + 4532.6 * 12 + 49.1 * 200
+# The literals are TOTALS over the counted sample, so the recount (tests/test_alg_ops.py, `bench.py --recount`) can
+# assert equality instead of trusting a rounded mean:
+#   opening: 4 000 rollouts, Philox ids 0..3999 under DEFAULT_SEED
+#   corpus : states 0, 64, 128, ... 4032 of tests/golden/corpus_q.npy x 200 rollouts each, ids 200*i ..
+ALG_SAMPLES = {
+    "opening": {"rollouts": 4000, "flood_steps": 52533142, "cheap_wall_tests": 18130320, "plies": 196382},
+    "corpus": {"rollouts": 12800, "flood_steps": 34874581, "cheap_wall_tests": 12006688, "plies": 381357},
+}
+OPS_PER_FLOOD_STEP, OPS_PER_CHEAP_TEST, OPS_PER_PLY = 24, 12, 200
+
+
+def alg_ops_per_rollout(workload):
+    c = ALG_SAMPLES[workload]
+    return (c["flood_steps"] * OPS_PER_FLOOD_STEP + c["cheap_wall_tests"] * OPS_PER_CHEAP_TEST + c["plies"] * OPS_PER_PLY) / c["rollouts"]
+
+
+def recount(workload):
+    """The oracle's work counters over the sample ALG_SAMPLES names (test infrastructure: only the recount uses it)."""
+    import montecarlotreesearch_b200 as m
+    from oracle.portlib import PortLib
+    port = PortLib()
+    tot = {"flood_steps": 0, "cheap_wall_tests": 0, "plies": 0}
+    if workload == "opening":
+        runs = [(m.quoridor_opening(), 0, 4000)]
+    else:
+        corpus = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))
+        runs = [(corpus[i], 200 * i, 200) for i in range(0, 4096, 64)]
+    n = 0
+    for state, first, count in runs:
+        _, _, w = port.q_rollout_philox(state, m.DEFAULT_SEED, first, count, work=True)
+        for k in tot:
+            tot[k] += int(w[k])
+        n += count
+    tot["rollouts"] = n
+    return tot
+
+
+ALG_OPS_PER_ROLLOUT = alg_ops_per_rollout("opening")
+# executed flood step of the kernel (qcore.cuh q_flood_step): 18 IMAD + 12 LOP3 thread instructions per 81-cell expansion
+EXEC_OPS_PER_FLOOD_STEP = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
 # algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
-NCU_DRAM_BYTES_PER_LAUNCH = 818944 + 520704   # profiles/r01_final_lockstep.md (ncu, one launch)
+NCU_DRAM_BYTES_PER_LAUNCH = 818944 + 520704   # profiles/r02_lockstep.md (ncu --set full, one launch of 2^20 rollouts)
 
 
 class ClockSampler:
@@ -99,46 +140,63 @@ def host_threads():
         return os.cpu_count() or 1
 
 
-def reference_rollouts_per_sec(target_seconds, threads):
-    """RolloutJobs on the reference's own JobScheduler (mcts.cpp:60-66), all host threads, opening state."""
+def reference_rollouts_per_sec(target_seconds, threads, states=None):
+    """RolloutJobs on the reference's own JobScheduler (mcts.cpp:60-66) with `threads` workers; the opening position
+    unless `states` (packed records, cycled over) is given.  -> (rate, jobs, seconds, mean score, std of one score)"""
     from oracle.reflib import RefLib
     ref = RefLib("native")
     calib_jobs = 200 * threads
-    secs, _ = ref.jobscheduler_bench(0, threads, calib_jobs)
+    secs, _ = ref.jobscheduler_bench(0, threads, calib_jobs, qstates=states)
     rate = calib_jobs / secs
     jobs = max(calib_jobs, int(rate * target_seconds))
-    secs, mean = ref.jobscheduler_bench(0, threads, jobs)
-    return jobs / secs, jobs, secs, mean
+    secs, mean, std = ref.jobscheduler_bench2(0, threads, jobs, qstates=states)
+    return jobs / secs, jobs, secs, mean, std
 
 
 def run_reference_arm(args, rank, world):
     if rank != 0:
         return
     threads = host_threads()
+    states = None
+    if args.workload == "corpus":
+        states = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))[:4096]
     per_step = []
     sample_jobs = 0
     for i in range(args.warmup + args.steps):
-        rate, jobs, secs, mean = reference_rollouts_per_sec(2.0 if i >= args.warmup else 0.5, threads)
+        rate, jobs, secs, mean, std = reference_rollouts_per_sec(2.0 if i >= args.warmup else 0.5, threads, states)
         if i >= args.warmup:
-            per_step.append((jobs, secs))
+            per_step.append((jobs, secs, mean))
             sample_jobs = jobs
-    total_jobs = sum(j for j, _ in per_step)
-    total_secs = sum(s for _, s in per_step)
+    total_jobs = sum(j for j, _, _ in per_step)
+    total_secs = sum(s for _, s, _ in per_step)
     value = total_jobs / total_secs
+    where = "opening position" if states is None else "mid-game corpus (4096 states, cycled)"
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * total_secs / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "int32+f64", "data": "synthetic",
-        "config": {"workload": "configs[1]: Quoridor 9x9 opening position, independent REF-policy rollouts "
-                               "(the reference's rollout() as RolloutJobs on its JobScheduler; each step is a bounded sample of the workload)",
+        "config": {"workload": ("configs[1]: Quoridor 9x9 opening position" if states is None else "configs[2]: mid-game corpus, 4096 states")
+                               + ", independent REF-policy rollouts (the reference's rollout() as RolloutJobs on its JobScheduler; each step is a bounded sample of the workload)",
                    "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)",
                    "sample_rollouts_per_step": sample_jobs, "host_threads": threads},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "reference",
-                         "sample": "%d RolloutJobs per step on JobScheduler(%d), opening position, stock RNG" % (sample_jobs, threads)},
+                         "sample": "%d RolloutJobs per step on JobScheduler(%d), %s, stock RNG" % (sample_jobs, threads, where)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
+        "mean_score": sum(j * mn for j, _, mn in per_step) / max(1, total_jobs),
     }
     print(json.dumps(line), flush=True)
+
+
+def time_batch_calls(be, G, P, states, per_leaf, first, calls):
+    """median / min host-clock milliseconds of synchronous mctsb_rollout_batch calls"""
+    ts = []
+    for k in range(calls):
+        t0 = time.perf_counter()
+        be.rollout_batch(G, P, states, per_leaf, first + k * per_leaf * len(states))
+        ts.append(1e3 * (time.perf_counter() - t0))
+    ts.sort()
+    return ts[len(ts) // 2], ts[0]
 
 
 def main():
@@ -147,19 +205,31 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--rollouts", type=int, default=1 << 20, help="rollouts per step per GPU")
+    ap.add_argument("--rollouts", type=int, default=1 << 20, help="rollouts per step per GPU (weak scaling) / per step over all GPUs (strong)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak: --rollouts per GPU per step (driver contract); strong: --rollouts per step split over the GPUs")
     ap.add_argument("--workload", default="opening", choices=["opening", "corpus"],
                     help="opening = configs[1] (headline); corpus = configs[2]: 4096 mid-game states x rollouts/4096 each")
     ap.add_argument("--policy", default="ref", choices=["ref", "uni"], help="ref = headline (reference rollout()); uni = uniformly random legal moves (secondary)")
     ap.add_argument("--game", default="quoridor", choices=["quoridor", "tictactoe"], help="tictactoe = configs[0] rollouts from the empty board (secondary)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="bounded CPU sample for cpu_baseline")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the secondary measurements of the `extra` block")
+    ap.add_argument("--recount", action="store_true", help="recount the roofline numerators with the oracle's work counters and compare with the literals (CPU only)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.recount:
+        out = {}
+        for w in ("opening", "corpus"):
+            got = recount(w)
+            out[w] = {"counted": got, "literal": ALG_SAMPLES[w], "equal": got == ALG_SAMPLES[w], "alg_ops_per_rollout": alg_ops_per_rollout(w)}
+        print(json.dumps(out))
+        sys.exit(0 if all(v["equal"] for v in out.values()) else 1)
 
     if args.impl == "reference":
         run_reference_arm(args, rank, world)
@@ -171,7 +241,6 @@ def main():
     os.dup2(2, 1)
 
     import montecarlotreesearch_b200 as m
-    from montecarlotreesearch_b200 import multi
 
     dist = None
     if world > 1:
@@ -182,15 +251,25 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     be = m.RolloutBackend(local_rank, m.DEFAULT_SEED)
+    if dist is not None:
+        # the C ABI's own communicator: rank 0 makes the id, torch.distributed ships it (plumbing only)
+        uid = torch.zeros(m.COMM_ID_BYTES, dtype=torch.uint8)
+        if rank == 0:
+            uid = torch.frombuffer(bytearray(m.comm_unique_id()), dtype=torch.uint8).clone()
+        uid = uid.cuda()
+        dist.broadcast(uid, 0)
+        be.comm_init_rank(uid.cpu().numpy().tobytes(), world, rank)
+
+    rollouts_per_gpu = args.rollouts if args.scaling == "weak" else max(1, args.rollouts // world)
     if args.workload == "corpus":
         state = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))[:4096]
-        per_leaf = max(1, args.rollouts // 4096)
+        per_leaf = max(1, rollouts_per_gpu // 4096)
     else:
         state = np.array([m.quoridor_opening()], dtype=m.QSTATE_DTYPE)
-        per_leaf = args.rollouts
+        per_leaf = rollouts_per_gpu
     if args.game == "tictactoe":
         state = np.zeros(1, dtype=m.TSTATE_DTYPE)
-        per_leaf = args.rollouts
+        per_leaf = rollouts_per_gpu
     n_leaves = len(state)
     n = per_leaf * n_leaves
     G = m.GAME_QUORIDOR if args.game == "quoridor" else m.GAME_TICTACTOE
@@ -204,6 +283,14 @@ def main():
     def first_id(step):
         return (step * world + rank) * n
 
+    def merged(sums):
+        """exact integer merge over the GPUs (no-op on one GPU): every rank gets the sums of the whole job"""
+        return be.allreduce_leaf_sums(sums) if dist is not None else sums
+
+    def score_of(sums):
+        a = np.ascontiguousarray(sums, dtype=m.LEAFSUM_DTYPE).reshape(-1)
+        return float(sum(be.lib.mctsb_leaf_sum_to_double(a[i:i + 1].ctypes.data) for i in range(a.size)))
+
     # ---- measured integer-issue peak (roofline denominator) -----------------------------------------
     int_peak, _ = be.int_issue_peak()
     lop3_peak, _ = be.lop3_peak()
@@ -214,81 +301,99 @@ def main():
     for w in range(args.warmup):                       # a warm-up step is a whole step: kernel, D2H, cross-rank merge
         be.run_resident(G, P, per_leaf, first_id(w), timed=True)
         _, wsums = be.wait()
-        if dist is not None:
-            multi.allreduce_leaf_sums(wsums, dist, device="cuda")
+        merged(wsums)
     barrier()
     # one nvidia-smi process per job (rank 0) watching every GPU of the job
     sampler = ClockSampler(",".join(str(g) for g in range(world)) if world > 1 else local_rank)
     if rank == 0:
         sampler.start()
     barrier()
-    kernel_ms, merges = [], []
-
-    def merged_score(pending):
-        ms_ = pending.result()
-        return float(sum(multi.leaf_sum_to_double(lo, hi) for lo, hi in zip(ms_["lo"], ms_["hi"])))
-
+    kernel_ms = []
     total_score = 0.0
     step_wall = 0.0                                    # steps only: the L2 flush between them is not part of a step
+    c0 = be.counters()
     for k in range(args.steps):
         be.flush_l2()                                  # 256 MiB memset + sync between timed steps
         ta = time.perf_counter()
         ms = be.run_resident(G, P, per_leaf, first_id(args.warmup + k), timed=True)
-        score, sums = be.wait()
-        if dist is not None:
-            # exact integer merge over NVLink (NCCL), started now and collected one step later: the next
-            # step's kernel runs while this step's statistics are exchanged
-            merges.append(multi.allreduce_leaf_sums_async(sums, dist, device="cuda"))
-            if len(merges) > 1:
-                total_score += merged_score(merges.pop(0))
-        else:
-            total_score += float(np.sum(score))
+        _, sums = be.wait()
+        total_score += score_of(merged(sums))          # N>1: blocking all-reduce of 24 B per leaf over NVLink, every step
         step_wall += time.perf_counter() - ta
         kernel_ms.append(ms)
     ta = time.perf_counter()
-    while merges:
-        total_score += merged_score(merges.pop(0))
     barrier()
-    step_wall += time.perf_counter() - ta              # the last merge and the closing barrier belong to the job
+    step_wall += time.perf_counter() - ta              # the closing barrier belongs to the job
+    c1 = be.counters()
     if rank == 0:
         sampler.stop()
-    launches = be.counters()["kernel_launches"] - launches0 - args.warmup
+    launches = c1["kernel_launches"] - c0["kernel_launches"]
+
+    def max_over_ranks(values):
+        if dist is None:
+            return [float(v) for v in values]
+        t = torch.tensor(values, dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(v) for v in t]
 
     dev_ms = float(sum(kernel_ms))
-    if dist is not None:
-        import torch
-        t = torch.tensor([dev_ms, step_wall * 1e3], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dev_ms, wall_ms = float(t[0]), float(t[1])
-        step_ms = wall_ms            # at N>1 a step = kernel + D2H + cross-rank merge: host clock around the steps, max over ranks
-    else:
-        step_ms = dev_ms             # N=1: CUDA events around the kernel launches
+    dev_ms, wall_ms = max_over_ranks([dev_ms, step_wall * 1e3])
+    # N=1: CUDA events around the kernel launches.  N>1: a step = kernel + D2H + cross-rank merge, host clock around the steps, max over ranks
+    step_ms = dev_ms if dist is None else wall_ms
     total_rollouts = n * args.steps * world
     value = total_rollouts / (step_ms * 1e-3)
-    mean_score = total_score / (n * args.steps * world) if dist is not None else total_score / (n * args.steps)
+    mean_score = total_score / total_rollouts
 
     # ---- end to end through the C ABI with host buffers ----------------------------------------------------
     states_host = np.ascontiguousarray(state)
-    be.rollout_batch(G, P, states_host, per_leaf, first_id(1000))
+    merged(be.rollout_batch(G, P, states_host, per_leaf, first_id(1000))[1])
     barrier()
     e2e_s = 0.0
     for k in range(args.steps):
         be.flush_l2()
+        barrier()
         t0 = time.perf_counter()
-        be.rollout_batch(G, P, states_host, per_leaf, first_id(2000 + k))    # host buffers in, H2D, kernel, D2H, host sums out
+        _, sums = be.rollout_batch(G, P, states_host, per_leaf, first_id(2000 + k))    # host buffers in, H2D, kernel, D2H, host sums out
+        merged(sums)                                                                   # ... and the job-wide sums on every rank
         e2e_s += time.perf_counter() - t0
     barrier()
-    if dist is not None:
-        import torch
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t[0])
+    (e2e_s,) = max_over_ranks([e2e_s])
     e2e_value = total_rollouts / e2e_s
+
+    # ---- secondary measurements for the driver-visible line (rank 0's GPU, after the timed regions) --------
+    extra = None
+    if not args.no_extra and not secondary and args.workload == "opening":
+        extra = {}
+        opening = np.array([m.quoridor_opening()], dtype=m.QSTATE_DTYPE)
+        if rank == 0:
+            # configs[2]: the mid-game corpus, device-resident like `value`
+            corpus = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))[:4096]
+            be.upload_states(G, corpus)
+            ms_c = []
+            for k in range(3 + 5):
+                t_ms = be.run_resident(G, P, 256, (5000 + k) * (1 << 20), timed=True)
+                be.wait()
+                if k >= 3:
+                    ms_c.append(t_ms)
+            rate_c = 5 * 4096 * 256 / (1e-3 * sum(ms_c))
+            extra["corpus"] = {"workload": "configs[2]: 4096 mid-game states x 256 REF-policy rollouts per step, device-resident, 5 steps after 3 warm-ups",
+                               "rollouts_per_sec": rate_c, "ms_per_step": sum(ms_c) / 5,
+                               "roofline_frac": rate_c * alg_ops_per_rollout("corpus") / int_peak,
+                               "alg_ops_per_rollout": alg_ops_per_rollout("corpus")}
+            # configs[3] flush shape and the per-call floor: synchronous C-ABI calls with host buffers, host clock
+            lat = {}
+            for size, calls in ((1, 200), (4, 200), (32, 200), (1024, 100), (65536, 40)):
+                time_batch_calls(be, G, P, opening, size, 7000 * (1 << 20), 5)
+                med, mn = time_batch_calls(be, G, P, opening, size, 7001 * (1 << 20), calls)
+                lat[str(size)] = {"median_ms": med, "min_ms": mn, "rollouts_per_sec": size / (1e-3 * med)}
+            extra["call_latency"] = {"what": "synchronous mctsb_rollout_batch from the opening position (host buffers, H2D + kernel + D2H), host clock; 65536 = one configs[3] flush",
+                                     "sizes": lat}
+        barrier()
 
     counters = be.counters()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    be.close()
     if rank != 0:
         return
 
@@ -297,20 +402,40 @@ def main():
     if not args.no_cpu_baseline and not secondary:
         try:
             threads = host_threads()
-            rate, jobs, secs, mean = reference_rollouts_per_sec(args.cpu_seconds, threads)
+            cstates = None if args.workload == "opening" else np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))[:4096]
+            where = "opening position" if cstates is None else "mid-game corpus (4096 states, cycled)"
+            rate, jobs, secs, mean, std = reference_rollouts_per_sec(args.cpu_seconds, threads, cstates)
+            sem = std / max(1.0, jobs) ** 0.5
             cpu = {"value": rate, "unit": UNIT, "cores": threads, "kind": "reference",
-                   "sample": "%d RolloutJobs on the reference JobScheduler(%d), opening position, %.1f s" % (jobs, threads, secs)}
+                   "sample": "%d RolloutJobs on the reference JobScheduler(%d), %s, %.1f s, stock RNG (std::default_random_engine, unshimmed)" % (jobs, threads, where, secs),
+                   "mean_score": mean, "score_std": std, "mean_score_sem": sem,
+                   "gpu_mean_minus_cpu_mean_in_sem": (mean_score - mean) / sem if sem > 0 else None,
+                   "agrees_within_3_sigma": bool(abs(mean_score - mean) <= 3 * sem) if sem > 0 else None}
+            by_threads = {}
+            for t in sorted({1, min(4, threads)}):
+                if t == threads:
+                    continue
+                r_t, j_t, s_t, _, _ = reference_rollouts_per_sec(max(1.0, args.cpu_seconds / 6), t, cstates)
+                by_threads[str(t)] = {"value": r_t, "sample": "%d RolloutJobs, %.1f s" % (j_t, s_t)}
+            by_threads[str(threads)] = {"value": rate, "sample": "%d RolloutJobs, %.1f s" % (jobs, secs)}
+            cpu["by_threads"] = by_threads         # JobScheduler(1), (4) = stock NUMBER_OF_THREADS, (nproc)
+            if extra is not None and "corpus" in extra:
+                cst = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))[:4096]
+                r_c, j_c, s_c, mean_c, _ = reference_rollouts_per_sec(max(1.0, args.cpu_seconds / 4), threads, cst)
+                extra["corpus"]["cpu_baseline"] = {"value": r_c, "unit": UNIT, "cores": threads, "kind": "reference",
+                                                   "sample": "%d RolloutJobs cycling over the 4096 corpus states, %.1f s" % (j_c, s_c), "mean_score": mean_c}
         except Exception as e:  # the compiled reference may be absent
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
 
     per_gpu_rate = (n * args.steps) / (dev_ms * 1e-3)
-    # mid-game corpus: 2 709 BFS levels, 929 cheap wall tests, 29.8 plies per rollout (oracle, 64 states x 200 rollouts)
-    alg_ops = ALG_OPS_PER_ROLLOUT if args.workload == "opening" else 2709.4 * 24 + 929.5 * 12 + 29.8 * 200
+    alg_ops = alg_ops_per_rollout(args.workload)
     achieved = per_gpu_rate * alg_ops
-    exec_steps_per_rollout = counters["flood_steps"] / max(1, counters["rollouts"])
+    d_roll = max(1, c1["rollouts"] - c0["rollouts"])
+    exec_steps_per_rollout = (c1["flood_steps"] - c0["flood_steps"]) / d_roll
+    exec_flood_ops = per_gpu_rate * exec_steps_per_rollout * EXEC_OPS_PER_FLOOD_STEP
     line = {
         "metric": METRIC if not secondary else "%s_%s_rollouts_per_sec" % (args.game, args.policy), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
         "dtype": "int32+f64", "data": "synthetic",
         "config": {"workload": ("Tic-Tac-Toe empty board, %d independent rollouts per GPU per step" % n) if args.game != "quoridor"
                    else ("configs[1]: Quoridor 9x9 opening position, %d independent %s-policy rollouts per GPU per step" % (n, args.policy.upper())) if args.workload == "opening"
@@ -318,19 +443,28 @@ def main():
                    "policy": "REF (reference Quoridor_state::rollout semantics, <=50 plies + eval)" if not secondary
                              else "UNI (uniformly random legal move per ply, to the end of the game)" if args.game == "quoridor" else "reference TicTacToe_state::rollout",
                    "rollouts_per_step_per_gpu": n, "leaves": n_leaves, "seed": hex(m.DEFAULT_SEED),
-                   "l2": "flushed between timed steps (256 MiB memset, outside the timed kernel); inputs are 32 B per leaf and rollout ids differ every step"},
+                   "l2": "flushed between timed steps (256 MiB memset, outside the timed kernel); inputs are 32 B per leaf and rollout ids differ every step",
+                   "merge": None if world == 1 else "every step: mctsb_allreduce_leaf_sums (NCCL behind the C ABI) of the exact per-leaf sums, inside the timed region of value and e2e"},
         "roofline": {"bound": "sm_int_issue", "achieved": None if secondary else achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
-                     "frac": None if secondary else achieved / int_peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "frac": None if secondary else achieved / int_peak,
+                     "frac_algorithmic": None if secondary else achieved / int_peak,
+                     "frac_executed_flood_arithmetic": exec_flood_ops / int_peak if args.game == "quoridor" else None,
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_note": "1.3 MB per 28 ms launch = 48 MB/s of stack / counter write-back against 32 B in + 24 B out per leaf algorithmic: HBM is idle, the bound is integer issue",
                      "alu_pipe_lop3_peak": lop3_peak / 1e12, "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
-                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3 + integer-add chains on all SMs, both pipes; alu_pipe_lop3_peak = LOP3 only); "
-                             "achieved = rollouts/s x the REFERENCE algorithm's integer work per rollout (DESIGN.md 5); executed "
-                             "thread instructions per second from ncu are in profiles/ (18.7 T/s = 0.54 of this peak)"},
+                     "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3 + integer-add chains on all SMs, both pipes; alu_pipe_lop3_peak = LOP3 only). "
+                             "frac (= frac_algorithmic) = rollouts/s x the REFERENCE algorithm's integer work per rollout (oracle work counters, recounted by tests/test_alg_ops.py) / peak: "
+                             "it rewards exact pruning and is not SM utilisation.  frac_executed_flood_arithmetic = flood steps the kernel executed in this run (device counters) x 30 "
+                             "thread instructions per step / peak: the share of the issue peak spent on flood-fill arithmetic proper; the rest of the instruction stream is bookkeeping (profiles/)"},
         "cpu_baseline": cpu,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world,
+                "note": "mctsb_rollout_batch with host buffers" + ("" if world == 1 else " + the cross-rank merge, every step") +
+                        "; at N=1 it differs from value only by launch + copy latency (tens of microseconds per 28 ms step) and runs other rollout ids"},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "mean_score": mean_score,
         "kernel_ms_per_step": dev_ms / args.steps,
+        "extra": extra,
     }
     sys.stdout.flush()
     os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -388,8 +388,16 @@ int ref_q_pack_roundtrip(const mctsb_qstate *in, mctsb_qstate *out) {
 
 /* JobScheduler sched(n_threads); n_jobs x schedule(new RolloutJob(&state,&res[i])); wait
  * (mcts.cpp:60-66, JobScheduler.cpp:36-46,67-73).  Returns wall seconds; *mean_score = mean result. */
+double ref_jobscheduler_bench2(int game, const mctsb_qstate *qs, int n_states, uint32_t x_mask, uint32_t o_mask,
+                               int n_threads, int n_jobs, double *mean_score, double *mean_square);
 double ref_jobscheduler_bench(int game, const mctsb_qstate *qs, int n_states, uint32_t x_mask, uint32_t o_mask,
                               int n_threads, int n_jobs, double *mean_score) {
+    return ref_jobscheduler_bench2(game, qs, n_states, x_mask, o_mask, n_threads, n_jobs, mean_score, NULL);
+}
+
+/* the same, also returning the mean of the squared results (for a standard error of the mean) */
+double ref_jobscheduler_bench2(int game, const mctsb_qstate *qs, int n_states, uint32_t x_mask, uint32_t o_mask,
+                               int n_threads, int n_jobs, double *mean_score, double *mean_square) {
     Silence q_;
     std::vector<MCTS_state *> states;
     if (game == 0) {
@@ -407,9 +415,10 @@ double ref_jobscheduler_bench(int game, const mctsb_qstate *qs, int n_states, ui
         auto t1 = std::chrono::steady_clock::now();
         secs = std::chrono::duration<double>(t1 - t0).count();
     }
-    double sum = 0.0;
-    for (int i = 0; i < n_jobs; i++) sum += res[(size_t)i];
+    double sum = 0.0, sq = 0.0;
+    for (int i = 0; i < n_jobs; i++) { sum += res[(size_t)i]; sq += res[(size_t)i] * res[(size_t)i]; }
     if (mean_score) *mean_score = sum / n_jobs;
+    if (mean_square) *mean_square = sq / n_jobs;
     for (MCTS_state *s : states) delete s;
     return secs;
 }

@@ -131,6 +131,8 @@ class RefLib:
         L.ref_grow_tree.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_int]
         L.ref_jobscheduler_bench.restype = C.c_double
         L.ref_jobscheduler_bench.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp]
+        L.ref_jobscheduler_bench2.restype = C.c_double
+        L.ref_jobscheduler_bench2.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, vp]
         if kind == "gpu_dropin":
             L.mctsb_dropin_reset.argtypes = [C.c_uint64]
             L.mctsb_dropin_counters.argtypes = [vp, vp]
@@ -312,3 +314,11 @@ class RefLib:
         secs = self.lib.ref_jobscheduler_bench(game, qs.ctypes.data, qs.size, x_mask, o_mask, n_threads,
                                                n_jobs, C.addressof(mean))
         return secs, mean.value
+
+    def jobscheduler_bench2(self, game, n_threads, n_jobs, qstates=None, x_mask=0, o_mask=0):
+        """-> (wall seconds, mean result, standard deviation of one result)"""
+        qs = np.ascontiguousarray(qstates if qstates is not None else opening_state(), dtype=QSTATE_DTYPE).reshape(-1)
+        mean, sq = C.c_double(0), C.c_double(0)
+        secs = self.lib.ref_jobscheduler_bench2(game, qs.ctypes.data, qs.size, x_mask, o_mask, n_threads,
+                                                n_jobs, C.addressof(mean), C.addressof(sq))
+        return secs, mean.value, max(0.0, sq.value - mean.value ** 2) ** 0.5

@@ -323,3 +323,79 @@ def test_two_host_threads_two_handles(be, corpus):
     [t.join() for t in ts]
     assert not errs
     assert got[0].tobytes() == want.tobytes() and got[1].tobytes() == want.tobytes()
+
+
+# ---- expansion prepared on the device, the exchange behind the C ABI, the stock-RNG distribution ------------
+def test_submit_x_returns_the_movegen_masks_next_to_the_sums(be, corpus):
+    """mctsb_submit_x(MCTSB_SUBMIT_LEGAL): same sums as the plain pair, plus the masks mctsb_q_movegen returns."""
+    st = corpus[100:100 + 333]                       # ragged: not a multiple of anything
+    legal_ref, _, _ = be.q_movegen(st)
+    score0, sums0 = be.rollout_batch(G, 0, st, 8, 12345)
+    be.submit_x(G, 0, st, 8, 12345, flags=m.SUBMIT_LEGAL)
+    score1, sums1, legal = be.wait_x()
+    assert (legal == legal_ref).all() and (sums0 == sums1).all() and (score0 == score1).all()
+    be.submit(G, 0, st[:4], 8, 0)                    # masks were not asked for: asking for them at wait time is an error
+    out = np.zeros((4, 4), dtype=np.uint64)
+    assert be.lib.mctsb_wait_x(be.handle, None, None, out.ctypes.data) != 0
+    be.rollout_batch(G, 0, st[:4], 8, 0)
+    with pytest.raises(m.BackendError):              # Tic-Tac-Toe has no move-generation kernel
+        be.submit_x(T, 0, np.zeros(1, dtype=m.TSTATE_DTYPE), 8, 0, flags=m.SUBMIT_LEGAL)
+
+
+def test_comm_single_rank_is_the_identity():
+    """A communicator of one (mctsb_comm_unique_id -> mctsb_comm_init_rank) brings NCCL up behind the C ABI: sums over
+    one rank return their input, bit for bit, and the error paths answer."""
+    b = m.RolloutBackend(0, 5)
+    v = np.array([1.5, -2.25, 3e300, 0.1])
+    with pytest.raises(m.BackendError) as e:
+        b.allreduce_root_stats(v)
+    assert e.value.status == 5                       # no communicator yet
+    assert b.comm_info() == (1, 0)
+    b.comm_init_rank(m.comm_unique_id(), 1, 0)
+    assert b.comm_info() == (1, 0)
+    assert (b.allreduce_root_stats(v) == v).all()
+    s = np.zeros(3, dtype=m.LEAFSUM_DTYPE)
+    s["lo"], s["hi"], s["n"] = [1, 2 ** 63 + 5, 7], [9, 8, 2 ** 40], [3, 3, 3]
+    assert (b.allreduce_leaf_sums(s) == s).all()
+    with pytest.raises(m.BackendError):
+        b.comm_init_rank(m.comm_unique_id(), 1, 0)   # one communicator per handle
+    b.submit(T, 0, np.zeros(1, dtype=m.TSTATE_DTYPE), 4, 0)
+    with pytest.raises(m.BackendError) as e:
+        b.allreduce_root_stats(v)
+    assert e.value.status == 6                       # busy: a submit is pending
+    b.wait()
+    b.close()
+
+
+def test_comm_over_every_device_of_the_box():
+    """One process, one handle per GPU (mctsb_comm_init_all), reductions issued as one group from one thread; the
+    merged leaf sums of rollouts sharded by id equal the single-GPU sums over the whole id range."""
+    n = m.device_count()
+    if n < 2:
+        pytest.skip("one GPU on this box")
+    bs = [m.RolloutBackend(d, m.DEFAULT_SEED) for d in range(n)]
+    m.comm_init_all(bs)
+    assert [b.comm_info() for b in bs] == [(n, r) for r in range(n)]
+    import ctypes as C
+    vecs = [np.arange(6, dtype=np.float64) * (r + 1) for r in range(n)]
+    hs = (C.c_void_p * n)(*[b.handle for b in bs])
+    ps = (C.c_void_p * n)(*[v.ctypes.data for v in vecs])
+    assert bs[0].lib.mctsb_allreduce_root_stats_group(hs, ps, n, 6) == 0
+    want = np.arange(6, dtype=np.float64) * (n * (n + 1) // 2)
+    assert all((v == want).all() for v in vecs)
+    for b in bs:
+        b.close()
+
+
+def test_mean_score_agrees_with_the_stock_rng_reference(be, ref_native):
+    """The reference with its OWN generator and std::shuffle (no shim): its mean result over RolloutJobs from the
+    opening position against the GPU's mean over 2^20 Philox-keyed rollouts.  4 sigma of the CPU sample (the GPU
+    sample's own error is 30x smaller); bench.py reports the same comparison at 3 sigma in cpu_baseline."""
+    import os
+    threads = len(os.sched_getaffinity(0))
+    jobs = 3000 * threads
+    _, mean, std = ref_native.jobscheduler_bench2(0, threads, jobs)
+    score, _ = be.rollout_batch(G, 0, np.array([m.quoridor_opening()]), 1 << 20, 1 << 40)
+    gpu_mean = float(score[0]) / (1 << 20)
+    sem = std / jobs ** 0.5
+    assert abs(gpu_mean - mean) <= 4 * sem, (gpu_mean, mean, sem)
