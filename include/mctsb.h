@@ -182,6 +182,14 @@ typedef struct mctsb_qinfo {
 int mctsb_q_movegen(mctsb_backend *b, const mctsb_qstate *states, int n,
                     uint64_t *legal /* n*4 */, mctsb_qinfo *info /* n */, double *eval /* n */);
 
+/* The reference's other action generator, generate_good_moves (Quoridor.cpp:518-592; selected instead of
+ * generate_all_moves when TEST_ALL_MOVES is not defined, Quoridor.cpp:7,618-627): moves[i*MCTSB_Q_GOOD_MAX ..]
+ * = canonical move ids in the reference's queue order, counts[i] = how many.  One warp per state, one lane
+ * per candidate wall for the "shortest path of both players with this wall" flood fills. */
+#define MCTSB_Q_GOOD_MAX 144
+int mctsb_q_goodmoves(mctsb_backend *b, const mctsb_qstate *states, int n,
+                      uint8_t *moves /* n*MCTSB_Q_GOOD_MAX */, int32_t *counts /* n */);
+
 /* Batched next_state (Quoridor.cpp:506-510 -> play_move, Quoridor.cpp:344-392): out[i] =
  * states[i] after canonical move ids[i]; ok[i] = 0 when the move is illegal (state unchanged). */
 int mctsb_q_play(mctsb_backend *b, const mctsb_qstate *states, const int32_t *move_ids, int n,

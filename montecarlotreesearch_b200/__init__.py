@@ -36,11 +36,12 @@ EXPORTS = [
     "mctsb_device_count", "mctsb_submit", "mctsb_wait", "mctsb_rollout_batch", "mctsb_rollout_outcomes",
     "mctsb_rollout_replay", "mctsb_q_movegen", "mctsb_q_play", "mctsb_upload_states", "mctsb_run_resident",
     "mctsb_int_issue_peak", "mctsb_lop3_peak", "mctsb_flush_l2", "mctsb_get_counters", "mctsb_leaf_sum_to_double",
-    "mctsb_submit_x", "mctsb_wait_x",
+    "mctsb_submit_x", "mctsb_wait_x", "mctsb_q_goodmoves",
     "mctsb_comm_unique_id", "mctsb_comm_init_rank", "mctsb_comm_init_all", "mctsb_comm_destroy", "mctsb_comm_info",
     "mctsb_allreduce_root_stats", "mctsb_allreduce_leaf_sums", "mctsb_allreduce_root_stats_group",
 ]
 SUBMIT_LEGAL = 1
+Q_GOOD_MAX = 144
 COMM_ID_BYTES = 128
 
 
@@ -95,6 +96,7 @@ def load_library():
     L.mctsb_rollout_replay.argtypes = [vp, i32, i32, vp, i32, vp, u32, u32, vp, vp]
     L.mctsb_q_movegen.argtypes = [vp, vp, i32, vp, vp, vp]
     L.mctsb_q_play.argtypes = [vp, vp, vp, i32, vp, vp]
+    L.mctsb_q_goodmoves.argtypes = [vp, vp, i32, vp, vp]
     L.mctsb_upload_states.argtypes = [vp, i32, vp, i32]
     L.mctsb_run_resident.argtypes = [vp, i32, i32, u32, u64, C.POINTER(C.c_float)]
     L.mctsb_int_issue_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
@@ -227,6 +229,14 @@ class RolloutBackend:
         ev = np.zeros(a.size, dtype=np.float64)
         self._ck(self.lib.mctsb_q_movegen(self.handle, a.ctypes.data, a.size, legal.ctypes.data, info.ctypes.data, ev.ctypes.data))
         return legal, info, ev
+
+    def q_goodmoves(self, states):
+        """generate_good_moves of every state -> list of int arrays (canonical move ids in queue order)"""
+        a = self._states(GAME_QUORIDOR, states)
+        moves = np.zeros((a.size, Q_GOOD_MAX), dtype=np.uint8)
+        counts = np.zeros(a.size, dtype=np.int32)
+        self._ck(self.lib.mctsb_q_goodmoves(self.handle, a.ctypes.data, a.size, moves.ctypes.data, counts.ctypes.data))
+        return [moves[i, :counts[i]].astype(np.int32) for i in range(a.size)]
 
     def q_play(self, states, move_ids):
         a = self._states(GAME_QUORIDOR, states)

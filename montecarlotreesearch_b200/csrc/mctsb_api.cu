@@ -309,6 +309,25 @@ int mctsb_q_movegen(mctsb_backend *b, const mctsb_qstate *states, int n, uint64_
     return MCTSB_OK;
 }
 
+int mctsb_q_goodmoves(mctsb_backend *b, const mctsb_qstate *states, int n, uint8_t *moves, int32_t *counts) {
+    if (!b || !states || !moves || !counts || n <= 0) return MCTSB_ERR_BAD_ARG;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    if (!valid_qstates(states, n)) return MCTSB_ERR_BAD_STATE;
+    CK(cudaSetDevice(b->device));
+    TRY(upload_states(b, MCTSB_GAME_QUORIDOR, states, n));
+    const size_t o_moves = 0, o_counts = ((size_t)n * MCTSB_Q_GOOD_MAX + 15) & ~(size_t)15, total = o_counts + (size_t)n * sizeof(int32_t);
+    TRY(grow_bytes(b, &b->d_aux, &b->cap_aux, total));
+    char *base = (char *)b->d_aux;
+    CK(cudaMemsetAsync(base, 0, total, b->stream));
+    cudaError_t e = launch_quoridor_goodmoves((const mctsb_qstate *)b->d_states, n, (uint8_t *)(base + o_moves), (int32_t *)(base + o_counts), b->stream);
+    if (e != cudaSuccess) return fail_cuda(b, e, "good-moves kernel launch");
+    b->launches++;
+    CK(cudaMemcpyAsync(moves, base + o_moves, (size_t)n * MCTSB_Q_GOOD_MAX, cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaMemcpyAsync(counts, base + o_counts, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, b->stream));
+    CK(cudaStreamSynchronize(b->stream));
+    return MCTSB_OK;
+}
+
 int mctsb_q_play(mctsb_backend *b, const mctsb_qstate *states, const int32_t *move_ids, int n, mctsb_qstate *out, uint8_t *ok) {
     if (!b || !states || !move_ids || !out || n <= 0) return MCTSB_ERR_BAD_ARG;
     if (b->pending) return MCTSB_ERR_BUSY;

@@ -818,6 +818,64 @@ MC_HD bool q_legal_move(const QState &s, int id) {
     return q_wall_keeps_paths(s, k, nullptr);
 }
 
+// generate_good_moves, Quoridor.cpp:518-592 — the alternative actions_to_try (compiled out of the shipped build by
+// TEST_ALL_MOVES, Quoridor.cpp:7,618-627, but a public method).  The expensive part is "shortest path of both
+// players with each cheap-legal wall added" (pe[k] enemy, po[k] ours; k = 2*anchor + orientation, -1 = closed in):
+// independent flood fills the caller computes however it likes (one lane per wall on the device, a loop on the
+// host).  What is left is this sequential pass in the reference's (row, column, h before v) order: the wall itself
+// when it costs the enemy more than us and closes nobody in; and, when it would cost US at least
+// MIN_ENC_FOR_STOPPING_ENEMY_WALLS = 3 more than the enemy and the enemy has walls left, the walls that pre-empt
+// it (crossing wall on the same anchor, same orientation one square to either side), each at most once and only
+// if fully legal.  out[] receives canonical move ids in queue order (at most MCTSB_Q_GOOD_MAX); returns the count.
+MC_HD int q_good_moves_select(const QState &s, uint32_t steps, uint64_t cheap_h, uint64_t cheap_v, int our_path, int enemy_path,
+                              const int8_t *pe, const int8_t *po, uint8_t *out) {
+    int n = 0;
+    for (int i = 11; i >= 0; i--) if ((steps >> i) & 1u) out[n++] = (uint8_t)(s.cell[s.turn] + q_step_delta(i));
+    if (s.nwalls[s.turn] <= 0) return n;
+    const bool enemy_has_walls = s.nwalls[1 - s.turn] > 0;
+    uint64_t used[2] = {0, 0};                                   // already_used[i][j][k]
+#define MCTSB_GM_CHEAP(k) ((((k) & 1 ? cheap_v : cheap_h) >> ((k) >> 1)) & 1ull)
+#define MCTSB_GM_LEGAL(k) (MCTSB_GM_CHEAP(k) && pe[k] >= 0 && po[k] >= 0)
+#define MCTSB_GM_TAKE(k) do { used[(k) & 1] |= 1ull << ((k) >> 1); out[n++] = (uint8_t)(((k) & 1 ? 145 : 81) + ((k) >> 1)); } while (0)
+#define MCTSB_GM_USED(k) ((used[(k) & 1] >> ((k) >> 1)) & 1ull)
+    for (int k = 0; k < 128; k++) {
+        if (!MCTSB_GM_CHEAP(k)) continue;
+        const int a = k >> 1, o = k & 1, row = a >> 3, col = a & 7;
+        const int enemy_enc = pe[k] - enemy_path, our_enc = po[k] - our_path;
+        if (!MCTSB_GM_USED(k) && enemy_enc > our_enc && pe[k] >= 0 && po[k] >= 0) MCTSB_GM_TAKE(k);
+        if (enemy_has_walls && our_enc - enemy_enc >= 3) {
+            const int kc = k ^ 1;                                // same anchor, crossing orientation
+            if (!MCTSB_GM_USED(kc) && MCTSB_GM_LEGAL(kc)) MCTSB_GM_TAKE(kc);
+            const int lo_ok = o == 0 ? col >= 1 : row >= 1, hi_ok = o == 0 ? col + 1 < 8 : row + 1 < 8;
+            const int k_lo = o == 0 ? k - 2 : k - 16, k_hi = o == 0 ? k + 2 : k + 16;
+            if (lo_ok && !MCTSB_GM_USED(k_lo) && MCTSB_GM_LEGAL(k_lo)) MCTSB_GM_TAKE(k_lo);
+            if (hi_ok && !MCTSB_GM_USED(k_hi) && MCTSB_GM_LEGAL(k_hi)) MCTSB_GM_TAKE(k_hi);
+        }
+    }
+#undef MCTSB_GM_CHEAP
+#undef MCTSB_GM_LEGAL
+#undef MCTSB_GM_TAKE
+#undef MCTSB_GM_USED
+    return n;
+}
+
+// the whole of generate_good_moves on one thread (host game class; the device spreads the flood fills over a warp)
+MC_HD int q_good_moves(QState &s, uint8_t *out, QWork *wk) {
+    uint64_t ch, cv;
+    q_cheap_wall_masks(s, ch, cv);
+    int8_t pe[128], po[128];
+    const int p = s.turn, e = 1 - p;
+    for (int k = 0; k < 128; k++) {
+        pe[k] = po[k] = -1;
+        if ((((k & 1) ? cv : ch) >> (k >> 1)) & 1ull) {
+            pe[k] = (int8_t)q_sp_with_wall(s, e, k, wk);
+            po[k] = (int8_t)q_sp_with_wall(s, p, k, wk);
+        }
+    }
+    const int our_path = (ch | cv) ? q_sp(s, p, wk) : 0, enemy_path = (ch | cv) ? q_sp(s, e, wk) : 0;
+    return q_good_moves_select(s, q_step_mask(s), ch, cv, our_path, enemy_path, pe, po, out);
+}
+
 MC_HD void q_play_id(QState &s, int id) {    // canonical id, already known legal
     if (id < 81) q_play_step(s, id);
     else q_play_wall(s, id < 145 ? 2 * (id - 81) : 2 * (id - 145) + 1);

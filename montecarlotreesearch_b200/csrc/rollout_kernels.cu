@@ -217,6 +217,44 @@ cudaError_t launch_quoridor_movegen(const mctsb_qstate *states, int n, uint64_t 
     return cudaGetLastError();
 }
 
+// generate_good_moves (Quoridor.cpp:518-592): one warp per position.  Lane l owns the walls anchored at l and l+32
+// in both orientations: for each that is cheap-legal it runs the two flood fills "shortest path of the enemy / of
+// the mover with this wall added" and leaves the lengths in shared memory; lane 0 then makes the reference's
+// sequential pass over the 128 candidates (q_good_moves_select) and writes the ordered move list.
+__global__ void __launch_bounds__(kThreads) quoridor_goodmoves_kernel(const mctsb_qstate *states, int n, uint8_t *moves, int32_t *counts) {
+    __shared__ int8_t paths[kThreads / 32][2][128];
+    const int wib = threadIdx.x >> 5, warp = (blockIdx.x * kThreads + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    QState s;
+    q_unpack(s, load_qstate(states, warp));
+    uint64_t ch, cv;
+    q_cheap_wall_masks(s, ch, cv);
+    const int p = s.turn, e = 1 - p;
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        const int a = 32 * (j >> 1) + lane, k = 2 * a + (j & 1);
+        int pe = -1, po = -1;
+        if ((((j & 1) ? cv : ch) >> a) & 1ull) { pe = q_sp_with_wall(s, e, k, nullptr); po = q_sp_with_wall(s, p, k, nullptr); }
+        paths[wib][0][k] = (int8_t)pe; paths[wib][1][k] = (int8_t)po;
+    }
+    __syncwarp();
+    if (lane == 0) {
+        uint8_t out[MCTSB_Q_GOOD_MAX];
+        const bool walls = (ch | cv) != 0;
+        const int our_path = walls ? q_sp(s, p, nullptr) : 0, enemy_path = walls ? q_sp(s, e, nullptr) : 0;
+        const int cnt = q_good_moves_select(s, q_step_mask(s), ch, cv, our_path, enemy_path, paths[wib][0], paths[wib][1], out);
+        for (int i = 0; i < cnt; i++) moves[(size_t)warp * MCTSB_Q_GOOD_MAX + i] = out[i];
+        counts[warp] = cnt;
+    }
+}
+
+cudaError_t launch_quoridor_goodmoves(const mctsb_qstate *states, int n, uint8_t *moves, int32_t *counts, cudaStream_t st) {
+    if (n <= 0) return cudaSuccess;
+    unsigned blocks = (unsigned)(((uint64_t)n * 32 + kThreads - 1) / kThreads);
+    quoridor_goodmoves_kernel<<<blocks, kThreads, 0, st>>>(states, n, moves, counts);
+    return cudaGetLastError();
+}
+
 // next_state (Quoridor.cpp:506-510 -> play_move, :344-392), one thread per (state, move)
 __global__ void __launch_bounds__(kThreads) quoridor_play_kernel(const mctsb_qstate *states, const int32_t *ids, int n,
                                                                  mctsb_qstate *out, uint8_t *ok) {

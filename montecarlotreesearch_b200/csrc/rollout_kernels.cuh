@@ -37,6 +37,7 @@ cudaError_t launch_ttt_rollouts(const RolloutParams &p, bool replay, cudaStream_
 // one warp = one position; the 128 wall candidates are spread over the lanes
 cudaError_t launch_quoridor_movegen(const mctsb_qstate *states, int n, uint64_t *legal4, mctsb_qinfo *info,
                                     double *eval, cudaStream_t st);
+cudaError_t launch_quoridor_goodmoves(const mctsb_qstate *states, int n, uint8_t *moves, int32_t *counts, cudaStream_t st);
 cudaError_t launch_quoridor_play(const mctsb_qstate *states, const int32_t *ids, int n, mctsb_qstate *out,
                                  uint8_t *ok, cudaStream_t st);
 

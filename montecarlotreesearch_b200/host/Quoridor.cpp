@@ -26,14 +26,14 @@ Quoridor_move *Quoridor_move::from_canonical_id(int id, char player) {
     return new Quoridor_move((short)((id - 145) / 8), (short)((id - 145) % 8), player, 'v');
 }
 
-Quoridor_state::Quoridor_state() : rollout_policy(MCTSB_POLICY_REF), have_legal_mask(false) {   // Quoridor.cpp:17-23
+Quoridor_state::Quoridor_state() : rollout_policy(MCTSB_POLICY_REF), good_moves_only(false), have_legal_mask(false) {   // Quoridor.cpp:17-23
     mctsb_qstate p;
     memset(&p, 0, sizeof p);
     p.wx = 0; p.wy = 4; p.bx = 8; p.by = 4; p.wwalls = 10; p.bwalls = 10;
     q_unpack(s, p);
 }
 
-Quoridor_state::Quoridor_state(const mctsb_qstate &packed, int rollout_policy) : rollout_policy(rollout_policy), have_legal_mask(false) {
+Quoridor_state::Quoridor_state(const mctsb_qstate &packed, int rollout_policy) : rollout_policy(rollout_policy), good_moves_only(false), have_legal_mask(false) {
     if (!q_unpack(s, packed)) throw std::invalid_argument("Quoridor_state: packed record is not a position");
 }
 
@@ -127,7 +127,18 @@ queue<MCTS_move *> *Quoridor_state::generate_all_moves() const {
     return Q;
 }
 
-queue<MCTS_move *> *Quoridor_state::actions_to_try() const { return generate_all_moves(); }   // TEST_ALL_MOVES build, Quoridor.cpp:618-627
+// generate_good_moves, Quoridor.cpp:518-592: the shared rule code does the work (q_good_moves)
+queue<MCTS_move *> *Quoridor_state::generate_good_moves() const {
+    queue<MCTS_move *> *Q = new queue<MCTS_move *>();
+    uint8_t ids[MCTSB_Q_GOOD_MAX];
+    const int n = q_good_moves(s, ids, nullptr);
+    const char p = whose_turn();
+    for (int i = 0; i < n; i++) Q->push(Quoridor_move::from_canonical_id(ids[i], p));
+    return Q;
+}
+
+// Quoridor.cpp:618-627: the shipped build defines TEST_ALL_MOVES, so generate_all_moves is the default here too
+queue<MCTS_move *> *Quoridor_state::actions_to_try() const { return good_moves_only ? generate_good_moves() : generate_all_moves(); }   // TEST_ALL_MOVES build, Quoridor.cpp:618-627
 
 MCTS_state *Quoridor_state::next_state(const MCTS_move *move) const {   // Quoridor.cpp:506-510
     Quoridor_state *n = new Quoridor_state(*this);
@@ -145,6 +156,7 @@ MCTS_state *Quoridor_state::next_state_of_listed_move(const MCTS_move *move) con
 }
 
 void Quoridor_state::gpu_set_legal(const uint64_t *mask4) {
+    if (good_moves_only) return;             // the mask answers generate_all_moves only
     memcpy(legal_mask, mask4, sizeof legal_mask);
     have_legal_mask = true;
 }

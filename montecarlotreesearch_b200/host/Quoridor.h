@@ -29,6 +29,7 @@ struct Quoridor_move : public MCTS_move {
 class Quoridor_state : public MCTS_state {
     mutable mctsb::QState s;           // mutable: the cached shortest paths are filled lazily, as wdists/bdists are
     int rollout_policy;                // MCTSB_POLICY_REF (default) or MCTSB_POLICY_UNI
+    bool good_moves_only;              // actions_to_try() = generate_good_moves() (the build without TEST_ALL_MOVES, Quoridor.cpp:7,618-627)
     uint64_t legal_mask[4]; bool have_legal_mask;   // the device's answer to generate_all_moves for this position, if it came
 public:
     Quoridor_state();
@@ -44,6 +45,10 @@ public:
     vector<MCTS_move *> get_legal_step_moves2(char p) const;        // forward candidate order  (Quoridor.cpp:457-474)
     Quoridor_move *get_best_step_move(char player) const;           // Quoridor.cpp:476-497
     queue<MCTS_move *> *generate_all_moves() const;                 // Quoridor.cpp:594-616
+    queue<MCTS_move *> *generate_good_moves() const;                // Quoridor.cpp:518-592
+    // which of the two actions_to_try() returns; inherited by every next_state (the reference chooses at compile time)
+    void set_good_moves_only(bool on) { good_moves_only = on; have_legal_mask = false; }
+    bool get_good_moves_only() const { return good_moves_only; }
     double evaluate() const;                                        // evaluate_position, Quoridor.cpp:629-664
     bool force_playwall() const;                                    // Quoridor.cpp:666-678
     void pack(mctsb_qstate &out) const;

@@ -93,6 +93,16 @@ int mcts_host_q_actions(const mctsb_qstate *s, int32_t *ids, int max_ids) {
     return n;
 }
 
+int mcts_host_q_good_actions(const mctsb_qstate *s, int32_t *ids, int max_ids) {
+    Quoridor_state q(*s);
+    q.set_good_moves_only(true);
+    queue<MCTS_move *> *Q = q.actions_to_try();
+    int n = 0;
+    while (!Q->empty()) { if (n < max_ids) ids[n] = ((Quoridor_move *)Q->front())->canonical_id(); n++; delete Q->front(); Q->pop(); }
+    delete Q;
+    return n;
+}
+
 int mcts_host_q_next(const mctsb_qstate *s, int id, mctsb_qstate *out) {
     Quoridor_state q(*s);
     Quoridor_move *m = Quoridor_move::from_canonical_id(id, q.whose_turn());
@@ -151,6 +161,14 @@ void mcts_host_set_overlap(void *hs, int on) {
     MCTS_batching b = h->tree->get_batching();
     b.overlap = on != 0; b.flushes_in_flight = on > 1 ? (uint32_t)on : 1;     // on = number of flushes in flight (0 = synchronous)
     h->tree->set_batching(b);
+}
+
+// Quoridor only, before the first grow: the tree expands generate_good_moves() instead of generate_all_moves()
+int mcts_host_set_good_moves_only(void *hs, int on) {
+    HostSession *h = (HostSession *)hs;
+    if (h->game != MCTSB_GAME_QUORIDOR || h->tree->get_size() > 0) return -1;
+    ((Quoridor_state *)h->tree->get_current_state())->set_good_moves_only(on != 0);
+    return 0;
 }
 
 void mcts_host_set_gpu_expand(void *hs, int on) {

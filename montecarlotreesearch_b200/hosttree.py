@@ -15,6 +15,8 @@ def load():
     L = C.CDLL(os.path.join(m.PKG_DIR, "libmcts_host.so"))
     vp = C.c_void_p
     L.mcts_host_q_actions.argtypes = [vp, vp, C.c_int]
+    L.mcts_host_q_good_actions.argtypes = [vp, vp, C.c_int]
+    L.mcts_host_set_good_moves_only.argtypes = [vp, C.c_int]
     L.mcts_host_q_next.argtypes = [vp, C.c_int, vp]
     L.mcts_host_q_info.argtypes = [vp, vp, vp]
     L.mcts_host_q_sprint.argtypes = [vp, C.c_int, C.c_char_p, C.c_int]
@@ -65,6 +67,10 @@ class Session:
     def set_overlap(self, on=True):
         """on = False / 0: synchronous flushes; True / 1: one flush in flight; 2: two flushes queued on the GPU"""
         self.lib.mcts_host_set_overlap(self.h, int(on))
+
+    def set_good_moves_only(self, on=True):
+        """Quoridor, before the first grow: expand generate_good_moves() (Quoridor.cpp:518-592) instead of all legal moves"""
+        assert self.lib.mcts_host_set_good_moves_only(self.h, int(bool(on))) == 0
 
     def set_gpu_expand(self, on=True):
         """every flush also returns its leaves' legal-move masks from the move-generation kernel (MCTS_batching::gpu_expand)"""

@@ -171,6 +171,17 @@ int ref_q_best_step(const mctsb_qstate *s) {
     int id = move_id(m); delete m; return id;
 }
 
+/* the reference's public generate_good_moves() (Quoridor.cpp:518-592): canonical ids in queue order */
+extern "C" int ref_q_good_moves(const mctsb_qstate *st, int32_t *ids) {
+    Silence q_;
+    Quoridor_state s; load_q(s, st);
+    queue<MCTS_move *> *Q = s.generate_good_moves();
+    int n = 0;
+    while (!Q->empty()) { Quoridor_move *m = (Quoridor_move *)Q->front(); Q->pop(); ids[n++] = move_id(m); delete m; }
+    delete Q;
+    return n;
+}
+
 /* ---------------- Quoridor rollouts (stream RNG build only) ---------------- */
 #ifndef ORACLE_SHIM_NATIVE_RNG
 

@@ -46,6 +46,7 @@ int oracle_q_sp_with_wall(const mctsb_qstate *s, int player_is_black, int wall_m
 int oracle_q_sp_from(const mctsb_qstate *s, int player_is_black, int x, int y);
 int oracle_q_play(const mctsb_qstate *s, int move_id, mctsb_qstate *out);
 int oracle_q_best_step(const mctsb_qstate *s);
+int oracle_q_good_moves(const mctsb_qstate *s, int32_t *ids /* room for MCTSB_Q_NUM_MOVES */);
 
 /* policy 0 = REF (Quoridor.cpp:809-855), 1 = UNI.  final/moves/work nullable. */
 double oracle_q_rollout(const mctsb_qstate *s, int policy, oq_draws *src, mctsb_qstate *final_state,

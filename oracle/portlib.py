@@ -43,6 +43,7 @@ class PortLib:
         L.oracle_q_sp_from.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.oracle_q_play.argtypes = [vp, C.c_int, vp]
         L.oracle_q_best_step.argtypes = [vp]
+        L.oracle_q_good_moves.argtypes = [vp, vp]
         L.oracle_q_rollout.restype = C.c_double
         L.oracle_q_rollout.argtypes = [vp, C.c_int, vp, vp, vp, vp, vp, vp]
         L.oracle_q_rollout_philox.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]
@@ -105,6 +106,13 @@ class PortLib:
     def q_best_step(self, s):
         a, p = self._s(s)
         return self.lib.oracle_q_best_step(p)
+
+    def q_good_moves(self, s):
+        """generate_good_moves (Quoridor.cpp:518-592): canonical move ids in queue order"""
+        a, p = self._s(s)
+        ids = np.zeros(209, dtype=np.int32)
+        n = self.lib.oracle_q_good_moves(p, ids.ctypes.data)
+        return ids[:n].copy()
 
     def q_rollout_stream(self, s, stream, policy=0, work=False):
         a, p = self._s(s)

@@ -249,6 +249,44 @@ static int qs_all_moves(qs_t *q, int *ids) {
     return n;
 }
 
+/* generate_good_moves, Quoridor.cpp:518-592 (the alternative actions_to_try, compiled out by TEST_ALL_MOVES in the
+ * shipped build but public): all legal steps, then for every cheap-legal wall in (row, column, h before v) order:
+ * the wall itself when it lengthens the enemy's path by more than ours and closes nobody in; and, when the wall
+ * would hurt US by at least 3 more than the enemy and the enemy still has walls, the walls that pre-empt it — the
+ * crossing wall on the same anchor and the same-orientation walls one square to either side — each at most once
+ * (already_used), fully legal.  A closed-in path counts as length -1 in the differences, as in the reference. */
+static int qs_good_moves(qs_t *q, int *ids) {
+    int n = qs_steps_reversed(q, ids);
+    int p = q->turn, e = 1 - p;
+    if (q->nwalls[p] <= 0) return n;
+    int our_path = qs_sp(q, p), enemy_path = qs_sp(q, e);
+    uint8_t used[8][8][2];
+    memset(used, 0, sizeof used);
+    for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) for (int k = 0; k < 2; k++) {
+        if (!qs_cheap_wall(q, i, j, k == 0)) continue;
+        int enemy_with = qs_sp_wall(q, e, i, j, k == 0), enemy_enc = enemy_with - enemy_path;
+        int our_with = qs_sp_wall(q, p, i, j, k == 0), our_enc = our_with - our_path;
+        if (!used[i][j][k] && enemy_enc > our_enc && enemy_with >= 0 && our_with >= 0) {
+            used[i][j][k] = 1;
+            ids[n++] = k == 0 ? MCTSB_Q_MOVE_HWALL(i, j) : MCTSB_Q_MOVE_VWALL(i, j);
+        }
+        if (q->nwalls[e] > 0 && our_enc - enemy_enc >= 3) {
+            if (!used[i][j][1 - k] && qs_legal_wall(q, i, j, k != 0)) {          /* same anchor, crossing orientation */
+                used[i][j][1 - k] = 1;
+                ids[n++] = k == 0 ? MCTSB_Q_MOVE_VWALL(i, j) : MCTSB_Q_MOVE_HWALL(i, j);
+            }
+            if (k == 0) {
+                if (j - 1 >= 0 && !used[i][j - 1][k] && qs_legal_wall(q, i, j - 1, 1)) { used[i][j - 1][k] = 1; ids[n++] = MCTSB_Q_MOVE_HWALL(i, j - 1); }
+                if (j + 1 < 8 && !used[i][j + 1][k] && qs_legal_wall(q, i, j + 1, 1)) { used[i][j + 1][k] = 1; ids[n++] = MCTSB_Q_MOVE_HWALL(i, j + 1); }
+            } else {
+                if (i - 1 >= 0 && !used[i - 1][j][k] && qs_legal_wall(q, i - 1, j, 0)) { used[i - 1][j][k] = 1; ids[n++] = MCTSB_Q_MOVE_VWALL(i - 1, j); }
+                if (i + 1 < 8 && !used[i + 1][j][k] && qs_legal_wall(q, i + 1, j, 0)) { used[i + 1][j][k] = 1; ids[n++] = MCTSB_Q_MOVE_VWALL(i + 1, j); }
+            }
+        }
+    }
+    return n;
+}
+
 /* evaluate_position, Quoridor.cpp:629-664 (MAX instead of MIN at :661 kept) */
 static double qs_eval(qs_t *q) {
     int wp = qs_sp(q, 0), bp = qs_sp(q, 1), w = q->nwalls[0], b = q->nwalls[1];
@@ -406,6 +444,14 @@ int oracle_q_primitives(const mctsb_qstate *s, int32_t *info, uint8_t *legal209,
         for (int i = 0; i < 8; i++) for (int j = 0; j < 8; j++) for (int k = 0; k < 2; k++)
             cheap128[2 * (8 * i + j) + k] = (uint8_t)qs_cheap_wall(&q, i, j, k == 0);
     return 0;
+}
+
+/* ids[] needs room for MCTSB_Q_NUM_MOVES entries; returns the count */
+int oracle_q_good_moves(const mctsb_qstate *s, int32_t *ids) {
+    qs_t q; qs_load(&q, s); g_work = NULL;
+    int tmp[MCTSB_Q_NUM_MOVES], n = qs_good_moves(&q, tmp);
+    for (int i = 0; i < n; i++) ids[i] = tmp[i];
+    return n;
 }
 
 int oracle_q_sp_with_wall(const mctsb_qstate *s, int player_is_black, int id) {

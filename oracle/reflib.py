@@ -126,6 +126,7 @@ class RefLib:
         L.ref_q_sp_from.argtypes = [vp, C.c_int, C.c_int, C.c_int]
         L.ref_q_play.argtypes = [vp, C.c_int, vp]
         L.ref_q_best_step.argtypes = [vp]
+        L.ref_q_good_moves.argtypes = [vp, vp]
         L.ref_t_primitives.argtypes = [C.c_uint32, C.c_uint32, vp, vp, vp]
         L.ref_grow_tree.restype = C.c_double
         L.ref_grow_tree.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_int]
@@ -194,6 +195,13 @@ class RefLib:
         raw = np.zeros(153, dtype=np.int32)
         ok = self.lib.ref_q_play(p, int(move_id), raw.ctypes.data)
         return bool(ok), raw
+
+    def q_good_moves(self, s):
+        """the reference's generate_good_moves(): canonical move ids in queue order"""
+        a, p = self._s(s)
+        ids = np.zeros(256, dtype=np.int32)
+        n = self.lib.ref_q_good_moves(p, ids.ctypes.data)
+        return ids[:n].copy()
 
     def q_best_step(self, s):
         a, p = self._s(s)

@@ -108,8 +108,9 @@ def test_opening_rollouts_vs_reference_golden(be):
     assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
 
 
-def test_free_running_scores_vs_reference_golden(be, corpus):
-    g = golden("golden_q_distribution.npz")
+@pytest.mark.parametrize("name", ["golden_q_distribution.npz", "golden_q_distribution64.npz"])
+def test_free_running_scores_vs_reference_golden(be, corpus, name):
+    g = golden(name)
     n = int(g["n"])
     states = np.array([m.quoridor_opening() if i < 0 else corpus[i] for i in g["index"]], dtype=m.QSTATE_DTYPE)
     # leaf j, rollout k uses id first + j*n + k; the golden used first_id for every state, so run one leaf at a time
@@ -130,6 +131,39 @@ def test_three_sigma_agreement_on_disjoint_streams(be, corpus):
         ref = g["scores"][j]
         se = np.sqrt(ref.var(ddof=1) / len(ref) + sc[j].var(ddof=1) / R)
         assert abs(ref.mean() - sc[j].mean()) <= 3.0 * se + 1e-12, (j, ref.mean(), sc[j].mean(), se)
+
+
+def test_sixty_four_state_distribution_on_disjoint_streams(be, corpus):
+    """64 states (opening + 63 mid-game), 20 000 rollouts each on streams the reference never
+    saw.  Every state's mean within 3.5 sigma of the reference's, and the 64 deviations together chi-square
+    plausible (sum of z^2 below the 99.9 % quantile of chi2(64) = 112.3)."""
+    g = golden("golden_q_distribution64.npz")
+    states = np.array([m.quoridor_opening() if i < 0 else corpus[i] for i in g["index"]], dtype=m.QSTATE_DTYPE)
+    R = 20000
+    out, _ = be.rollout_outcomes(G, m.POLICY_REF, states, R, 1 << 41, finals=False)
+    sc = out["score"].reshape(len(states), R)
+    z = []
+    for j in range(len(states)):
+        ref = g["scores"][j]
+        se = np.sqrt(ref.var(ddof=1) / len(ref) + sc[j].var(ddof=1) / R)
+        if se == 0:                                  # decided positions: every rollout returns the same value
+            assert ref.mean() == sc[j].mean(), j
+            continue
+        z.append((ref.mean() - sc[j].mean()) / se)
+    z = np.array(z)
+    assert np.abs(z).max() <= 3.5, z
+    assert (z ** 2).sum() <= 112.3 * len(z) / 64 + 1e-9, (z ** 2).sum()
+
+
+def test_good_moves_vs_reference_golden(be, corpus):
+    """mctsb_q_goodmoves (one warp per position, one lane per candidate wall) against the reference's public
+    generate_good_moves() on the opening and the whole corpus: same moves, same queue order."""
+    g = golden("golden_q_goodmoves.npz")
+    states = np.array([m.quoridor_opening() if i < 0 else corpus[i] for i in g["index"]], dtype=m.QSTATE_DTYPE)
+    got = be.q_goodmoves(states)
+    for j in range(len(states)):
+        n = int(g["count"][j])
+        assert len(got[j]) == n and (got[j] == g["ids"][j, :n]).all(), j
 
 
 def test_uniform_policy_vs_golden(be, corpus):
@@ -336,8 +370,8 @@ def test_submit_x_returns_the_movegen_masks_next_to_the_sums(be, corpus):
     assert (legal == legal_ref).all() and (sums0 == sums1).all() and (score0 == score1).all()
     be.submit(G, 0, st[:4], 8, 0)                    # masks were not asked for: asking for them at wait time is an error
     out = np.zeros((4, 4), dtype=np.uint64)
-    assert be.lib.mctsb_wait_x(be.handle, None, None, out.ctypes.data) != 0
-    be.rollout_batch(G, 0, st[:4], 8, 0)
+    assert be.lib.mctsb_wait_x(be.handle, None, None, out.ctypes.data) == 3     # MCTSB_ERR_BAD_ARG, the batch stays pending
+    be.wait()
     with pytest.raises(m.BackendError):              # Tic-Tac-Toe has no move-generation kernel
         be.submit_x(T, 0, np.zeros(1, dtype=m.TSTATE_DTYPE), 8, 0, flags=m.SUBMIT_LEGAL)
 

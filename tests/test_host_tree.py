@@ -54,6 +54,28 @@ def test_actions_order_and_info_vs_reference_golden(host, corpus):
         assert best == g["best_step"][j]
 
 
+def test_good_moves_of_the_host_class_vs_reference_golden(host, corpus):
+    """Quoridor_state::generate_good_moves (the selectable actions_to_try, Quoridor.cpp:518-592,618-627)"""
+    g = golden("golden_q_goodmoves.npz")
+    ids = np.zeros(256, dtype=np.int32)
+    for j, i in enumerate(g["index"]):
+        s = np.ascontiguousarray(m.quoridor_opening() if i < 0 else corpus[i])
+        n = host.mcts_host_q_good_actions(s.ctypes.data, ids.ctypes.data, 256)
+        assert n == g["count"][j] and (ids[:n] == g["ids"][j, :n]).all(), i
+
+
+def test_tree_over_good_moves_only(host, port):
+    """the tree expands generate_good_moves() when asked to: root children = that list, in that order"""
+    g = golden("golden_q_goodmoves.npz")
+    t = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=1, callback=oracle_backend(port))
+    t.set_good_moves_only(True)
+    t.grow(12)
+    r = t.root_stats()
+    n = int(g["count"][0])
+    assert len(r["children"]) == n and (r["children"][:, 0] == g["ids"][0, :n]).all()
+    t.close()
+
+
 def test_next_state_vs_oracle(host, port, corpus):
     rng = np.random.default_rng(21)
     out = np.zeros((), dtype=m.QSTATE_DTYPE)

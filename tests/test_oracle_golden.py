@@ -104,6 +104,24 @@ def test_free_running_scores_match_reference(port, corpus):
         assert (out["score"] == g["scores"][j]).all()
 
 
+def test_free_running_scores_match_reference_64_states(port, corpus):
+    g = golden("golden_q_distribution64.npz")
+    for j, i in enumerate(g["index"]):
+        s = opening_state() if i < 0 else corpus[i]
+        out, _, _ = port.q_rollout_philox(s, int(g["seed"]), int(g["first_id"]), 60)
+        assert (out["score"] == g["scores"][j, :60]).all(), j
+
+
+def test_good_moves_match_reference(port, corpus):
+    """generate_good_moves (Quoridor.cpp:518-592) restated in C against the reference's own, whole corpus"""
+    g = golden("golden_q_goodmoves.npz")
+    for j, i in enumerate(g["index"]):
+        s = opening_state() if i < 0 else corpus[i]
+        n = int(g["count"][j])
+        got = port.q_good_moves(s)
+        assert len(got) == n and (got == g["ids"][j, :n]).all(), i
+
+
 def test_tictactoe_matches_reference(port):
     g = golden("golden_t.npz")
     for j, (x, o, winner, terminal, p1, amask) in enumerate(g["states"]):
