@@ -350,12 +350,13 @@ def main():
     e2e_s = 0.0
     for k in range(args.steps):
         be.flush_l2()
-        barrier()
         t0 = time.perf_counter()
         _, sums = be.rollout_batch(G, P, states_host, per_leaf, first_id(2000 + k))    # host buffers in, H2D, kernel, D2H, host sums out
         merged(sums)                                                                   # ... and the job-wide sums on every rank
         e2e_s += time.perf_counter() - t0
+    t0 = time.perf_counter()
     barrier()
+    e2e_s += time.perf_counter() - t0                  # as for value: the closing barrier belongs to the job
     (e2e_s,) = max_over_ranks([e2e_s])
     e2e_value = total_rollouts / e2e_s
 

@@ -86,6 +86,22 @@ def test_replay_vs_oracle_random_streams(be, port, corpus):
     assert out.tobytes() == exp.tobytes() and fin.tobytes() == efin.tobytes()
 
 
+def test_forced_rare_branches(be, port, corpus):
+    """Replay streams that force what free-running playouts meet only by chance (tests/util.py forced_branch_cases):
+    96 first-legal picks whose shuffled head is an ILLEGAL wall (the rest of the pool follows in key order,
+    Quoridor.cpp:773-788) and best-wall / guided searches over 80 unpruned candidates — more than one batch of the
+    warp's task queue takes per lane.  108 distinct leaves in one launch: every warp mixes leaves and branches."""
+    from tests.util import forced_branch_cases
+    states, streams, notes = forced_branch_cases(port, corpus)
+    exp, efin = port.q_rollout_streams(states, streams)
+    for j, (kind, k) in enumerate(notes):                # the oracle did take the branch: a wall other than the head
+        if kind == "head_miss":
+            first = int(port.q_rollout_stream(states[j], streams[j])["moves"][0])
+            assert first >= 81 and first != (145 if k & 1 else 81) + (k >> 1)
+    out, fin = be.rollout_replay(G, m.POLICY_REF, states, streams)
+    assert out.tobytes() == exp.tobytes() and fin.tobytes() == efin.tobytes()
+
+
 def test_known_answer_streams(be):
     g = golden("golden_kat.npz")
     streams = np.stack([

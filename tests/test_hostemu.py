@@ -185,3 +185,16 @@ def test_lockstep_warp32_long_paths(emu32, port):
     exp, efin, _ = port.q_rollout_philox(s, 5, 0, 96, finals=True)
     out, fin, _, _ = emu32.lockstep(s, 96, 5, 0, blocks=1)
     assert exp.tobytes() == out.tobytes() and efin.tobytes() == fin.tobytes()
+
+
+def test_lockstep_warp32_forced_rare_branches(emu32, port, corpus):
+    """The branches a free-running playout only meets by chance, forced by replay streams (tests/util.py
+    forced_branch_cases): first-legal walls whose shuffled head is ILLEGAL (the rest of the pool follows in key
+    order, Quoridor.cpp:773-788) and best-wall / guided searches with more candidates than one batch of the task
+    queue takes per lane.  108 different leaves, one rollout each, so every warp mixes leaves and branches."""
+    from tests.util import forced_branch_cases
+    states, streams, notes = forced_branch_cases(port, corpus)
+    assert sum(1 for n in notes if n[0] == "head_miss") >= 33 and any(n[0] == "many_candidates" and n[1] > 64 for n in notes)
+    exp, efin = port.q_rollout_streams(states, streams)
+    out, fin, _, _ = emu32.lockstep(states, 1, 0, 0, streams=streams, blocks=2)
+    assert out.tobytes() == exp.tobytes() and fin.tobytes() == efin.tobytes()
