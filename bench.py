@@ -45,6 +45,8 @@ UNIT = "rollouts/s"
 ALG_SAMPLES = {
     "opening": {"rollouts": 4000, "flood_steps": 52533142, "cheap_wall_tests": 18130320, "plies": 196382},
     "corpus": {"rollouts": 12800, "flood_steps": 34874581, "cheap_wall_tests": 12006688, "plies": 381357},
+    # UNI policy from the opening, 1 000 rollouts, ids 0..999: the reference's generate_all_moves + play_move loop
+    "opening_uni": {"rollouts": 1000, "flood_steps": 24789089, "cheap_wall_tests": 5238252, "plies": 375626},
 }
 OPS_PER_FLOOD_STEP, OPS_PER_CHEAP_TEST, OPS_PER_PLY = 24, 12, 200
 
@@ -60,14 +62,17 @@ def recount(workload):
     from oracle.portlib import PortLib
     port = PortLib()
     tot = {"flood_steps": 0, "cheap_wall_tests": 0, "plies": 0}
+    policy = 0
     if workload == "opening":
         runs = [(m.quoridor_opening(), 0, 4000)]
+    elif workload == "opening_uni":
+        runs, policy = [(m.quoridor_opening(), 0, 1000)], 1
     else:
         corpus = np.load(os.path.join(ROOT, "tests", "golden", "corpus_q.npy"))
         runs = [(corpus[i], 200 * i, 200) for i in range(0, 4096, 64)]
     n = 0
     for state, first, count in runs:
-        _, _, w = port.q_rollout_philox(state, m.DEFAULT_SEED, first, count, work=True)
+        _, _, w = port.q_rollout_philox(state, m.DEFAULT_SEED, first, count, policy=policy, work=True)
         for k in tot:
             tot[k] += int(w[k])
         n += count
@@ -225,7 +230,7 @@ def main():
 
     if args.recount:
         out = {}
-        for w in ("opening", "corpus"):
+        for w in ("opening", "corpus", "opening_uni"):
             got = recount(w)
             out[w] = {"counted": got, "literal": ALG_SAMPLES[w], "equal": got == ALG_SAMPLES[w], "alg_ops_per_rollout": alg_ops_per_rollout(w)}
         print(json.dumps(out))
@@ -275,6 +280,8 @@ def main():
     G = m.GAME_QUORIDOR if args.game == "quoridor" else m.GAME_TICTACTOE
     P = m.POLICY_UNI if (args.policy == "uni" and args.game == "quoridor") else m.POLICY_REF
     secondary = args.game != "quoridor" or args.policy != "ref"
+    uni = args.game == "quoridor" and args.policy == "uni"
+    rooflined = not secondary or (uni and args.workload == "opening")       # workloads with a counted numerator
 
     def barrier():
         if dist is not None:
@@ -400,6 +407,21 @@ def main():
 
     # ---- CPU baseline on this box's host cores (bounded sample) ------------------------------------------
     cpu = None
+    if not args.no_cpu_baseline and uni and args.workload == "opening":
+        try:
+            from oracle.reflib import RefLib
+            threads = host_threads()
+            ref = RefLib("native")
+            secs, _, _ = ref.uniform_bench(threads, 50 * threads)
+            jobs = max(50 * threads, int(50 * threads / secs * args.cpu_seconds))
+            secs, mean, plies_mean = ref.uniform_bench(threads, jobs)
+            cpu = {"value": jobs / secs, "unit": UNIT, "cores": threads, "kind": "reference",
+                   "sample": "%d uniformly random playouts from the opening position driven through the reference's public API "
+                             "(actions_to_try = generate_all_moves, play_move) on %d threads, %.1f s; the reference ships no such loop, "
+                             "this is the one the UNI oracle restates" % (jobs, threads, secs),
+                   "mean_score": mean, "mean_plies": plies_mean}
+        except Exception as e:
+            cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
     if not args.no_cpu_baseline and not secondary:
         try:
             threads = host_threads()
@@ -429,7 +451,7 @@ def main():
             cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "unavailable: %s" % e}
 
     per_gpu_rate = (n * args.steps) / (dev_ms * 1e-3)
-    alg_ops = alg_ops_per_rollout(args.workload)
+    alg_ops = alg_ops_per_rollout("opening_uni" if uni else args.workload)
     achieved = per_gpu_rate * alg_ops
     d_roll = max(1, c1["rollouts"] - c0["rollouts"])
     exec_steps_per_rollout = (c1["flood_steps"] - c0["flood_steps"]) / d_roll
@@ -446,9 +468,9 @@ def main():
                    "rollouts_per_step_per_gpu": n, "leaves": n_leaves, "seed": hex(m.DEFAULT_SEED),
                    "l2": "flushed between timed steps (256 MiB memset, outside the timed kernel); inputs are 32 B per leaf and rollout ids differ every step",
                    "merge": None if world == 1 else "every step: mctsb_allreduce_leaf_sums (NCCL behind the C ABI) of the exact per-leaf sums, inside the timed region of value and e2e"},
-        "roofline": {"bound": "sm_int_issue", "achieved": None if secondary else achieved / 1e12, "peak": int_peak / 1e12, "unit": "Tint-op/s",
-                     "frac": None if secondary else achieved / int_peak,
-                     "frac_algorithmic": None if secondary else achieved / int_peak,
+        "roofline": {"bound": "sm_int_issue", "achieved": achieved / 1e12 if rooflined else None, "peak": int_peak / 1e12, "unit": "Tint-op/s",
+                     "frac": achieved / int_peak if rooflined else None,
+                     "frac_algorithmic": achieved / int_peak if rooflined else None,
                      "frac_executed_flood_arithmetic": exec_flood_ops / int_peak if args.game == "quoridor" else None,
                      "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
                      "traffic_note": "1.3 MB per 28 ms launch = 48 MB/s of stack / counter write-back against 32 B in + 24 B out per leaf algorithmic: HBM is idle, the bound is integer issue",

@@ -73,6 +73,14 @@ int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const R
     cudaError_t e;
     if (game == MCTSB_GAME_QUORIDOR && policy == MCTSB_POLICY_REF && !b->use_simple_kernel)
         e = launch_quoridor_lockstep(p, replay, b->d_counters + 7, b->stream);
+    else if (game == MCTSB_GAME_QUORIDOR && policy == MCTSB_POLICY_UNI && !b->use_simple_kernel) {
+        // the two phases of the UNI path talk through one hand-over record per rollout
+        TRY(grow_bytes(b, &b->d_walk, &b->cap_walk, (size_t)p.n_rollouts * MCTSB_UNI_WALK_BYTES));
+        RolloutParams q = p;
+        q.walk = b->d_walk;
+        e = launch_quoridor_uni_lockstep(q, replay, b->d_counters + 7, b->stream);
+        b->launches++;                             // two kernels
+    }
     else if (game == MCTSB_GAME_QUORIDOR) e = launch_quoridor_rollouts(p, policy, replay, b->stream);
     else e = launch_ttt_rollouts(p, replay, b->stream);
     if (e != cudaSuccess) return fail_cuda(b, e, "rollout kernel launch");
@@ -154,7 +162,7 @@ int mctsb_destroy(mctsb_backend *b) {
     if (b->stream) cudaStreamSynchronize(b->stream);
     cudaFree(b->d_states); cudaFree(b->d_sums); cudaFree(b->d_outcomes); cudaFree(b->d_finals);
     mctsb_comm_destroy(b);
-    cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink); cudaFree(b->d_flush); if (b->h_legal) cudaFreeHost(b->h_legal);
+    cudaFree(b->d_walk); cudaFree(b->d_streams); cudaFree(b->d_aux); cudaFree(b->d_counters); cudaFree(b->d_sink); cudaFree(b->d_flush); if (b->h_legal) cudaFreeHost(b->h_legal);
     if (b->h_in) cudaFreeHost(b->h_in);
     if (b->h_out) cudaFreeHost(b->h_out);
     if (b->ev0) cudaEventDestroy(b->ev0);

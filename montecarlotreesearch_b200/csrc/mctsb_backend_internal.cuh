@@ -18,6 +18,7 @@ struct mctsb_backend {
     void *d_finals; size_t cap_finals;               // bytes
     uint32_t *d_streams; size_t cap_streams;         // elements
     void *d_aux; size_t cap_aux;                     // bytes (movegen / play outputs)
+    void *d_walk; size_t cap_walk;                   // bytes (UNI policy: hand-over records between the two kernels)
     unsigned long long *d_counters;                  // [8]: 0-3 rollouts, plies, flood steps, flood queries; 7 = work counter of the lockstep kernel
     uint32_t *d_sink;                                // int-peak microbenchmark
     void *d_flush; size_t flush_bytes;                // L2 flush scratch (bench hygiene)

@@ -46,6 +46,13 @@ MC_HD int popc32(uint32_t v) {
     return __builtin_popcount(v);
 #endif
 }
+MC_HD int hibit32(uint32_t v) {   // v != 0: index of the highest set bit
+#if defined(__CUDA_ARCH__)
+    return 31 - __clz((int)v);
+#else
+    return 31 - __builtin_clz(v);
+#endif
+}
 MC_HD int popc64(uint64_t v) { return popc32((uint32_t)v) + popc32((uint32_t)(v >> 32)); }
 MC_HD int ctz32(uint32_t v) {   // v != 0
 #if defined(__CUDA_ARCH__)
@@ -786,9 +793,11 @@ MC_HD int q_nth_move(const QState &s, uint32_t steps, uint64_t legal_h, uint64_t
 
 // UNI policy (no reference function; oracle = loop over the reference's public API): uniformly
 // random legal move per ply, idx = mulhi(draw, |L|), ply cap MCTSB_UNI_MAX_PLIES scoring 0.5.
+// `plies` comes in as the number of plies already played (the lockstep kernel hands a rollout over once nobody has a
+// wall left; 0 for a whole playout) and goes out as the length of the playout.
 template <class Draws, class Layers>
-MC_HD double q_rollout_uni(QState &s, Draws &d, Layers &ls, int &plies, int &kind, QWork *wk) {
-    plies = 0; kind = 4;
+MC_HD double q_rollout_uni_from(QState &s, Draws &d, Layers &ls, int &plies, int &kind, QWork *wk) {
+    kind = 4;
     for (;;) {
         int w = q_winner(s);
         if (w) { kind = w == 1 ? 0 : 1; return w == 1 ? 1.0 : 0.0; }
@@ -799,6 +808,31 @@ MC_HD double q_rollout_uni(QState &s, Draws &d, Layers &ls, int &plies, int &kin
         if (n == 0) { kind = 3; return 0.5; }
         int mv = q_nth_move(s, steps, lh, lv, (int)mulhi_u32(d.next(), (uint32_t)n));
         if (mv < 81) q_play_step(s, mv); else q_play_wall(s, mv - 128);
+        plies++;
+    }
+}
+
+template <class Draws, class Layers>
+MC_HD double q_rollout_uni(QState &s, Draws &d, Layers &ls, int &plies, int &kind, QWork *wk) {
+    plies = 0;
+    return q_rollout_uni_from(s, d, ls, plies, kind, wk);
+}
+
+// The tail of a UNI playout once neither player has a wall left: the legal set is the step mask alone, so
+// q_rollout_uni_from reduces to this loop (same draws, same order: reversed candidate order, Quoridor.cpp:442-453).
+template <class Draws>
+MC_HD double q_walk_uni(QState &s, Draws &d, int &plies, int &kind) {
+    kind = 4;
+    for (;;) {
+        int w = q_winner(s);
+        if (w) { kind = w == 1 ? 0 : 1; return w == 1 ? 1.0 : 0.0; }
+        if (plies >= MCTSB_UNI_MAX_PLIES) return 0.5;
+        uint32_t m = q_step_mask(s);
+        int n = popc32(m);
+        if (n == 0) { kind = 3; return 0.5; }
+        int idx = (int)mulhi_u32(d.next(), (uint32_t)n);
+        for (; idx > 0; idx--) m &= ~(1u << hibit32(m));
+        q_play_step(s, s.cell[s.turn] + q_step_delta(hibit32(m)));
         plies++;
     }
 }

@@ -65,7 +65,7 @@ static inline unsigned long long ls_emu_bits(double x) { unsigned long long b; m
 #define LS_UNROLL2
 #else
 #define LS_DEV __device__ __forceinline__
-#define LS_NOINLINE __device__ __noinline__
+#define LS_NOINLINE static __device__ __noinline__
 #define LS_ANY(x) __any_sync(0xffffffffu, (x))
 #define LS_BALLOT(x) __ballot_sync(0xffffffffu, (x))
 #define LS_SHFL(v, l) __shfl_sync(0xffffffffu, (v), (l))

@@ -120,6 +120,54 @@ __global__ void __launch_bounds__(kThreads) quoridor_rollout_kernel(RolloutParam
     accumulate_counters(p.counters, active, wk, plies);
 }
 
+// UNI policy, phase B (quoridor_uni_lockstep_body.cuh): the rollouts the lockstep kernel handed over have no wall
+// left on either side — what remains is q_rollout_uni's loop with an empty wall set, a random walk of the two pawns
+// until one reaches its goal row (or the ply cap).  One thread per rollout; record r = {position, plies so far,
+// pending}.  The draw stream continues where phase A stopped: one draw per ply, so position = plies.
+template <bool REPLAY>
+__global__ void __launch_bounds__(kThreads) quoridor_uni_walk_kernel(RolloutParams p) {
+    const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool active = r < p.n_rollouts;
+    const uint32_t leaf = active ? (REPLAY ? (uint32_t)r : (uint32_t)(r / p.rollouts_per_leaf)) : 0u;
+    double score = 0.0; int plies = 0, kind = 0;
+    QWork wk = {0u, 0u, 0u};
+    if (active) {
+        const uint4 *rec = reinterpret_cast<const uint4 *>(p.walk) + 3ull * r;
+        const uint4 tail = rec[2];
+        active = tail.y != 0u;
+        if (active) {
+            const uint4 lo = rec[0], hi = rec[1];
+            mctsb_qstate packed;
+            packed.h_anchor = (uint64_t)lo.x | ((uint64_t)lo.y << 32); packed.v_anchor = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+            packed.wx = hi.x & 0xff; packed.wy = (hi.x >> 8) & 0xff; packed.bx = (hi.x >> 16) & 0xff; packed.by = hi.x >> 24;
+            packed.wwalls = hi.y & 0xff; packed.bwalls = (hi.y >> 8) & 0xff; packed.turn = (hi.y >> 16) & 0xff; packed.flags = hi.y >> 24;
+            packed.move_counter = hi.z; packed.reserved = 0;
+            QState s; q_unpack(s, packed);
+            plies = (int)tail.x;
+            uint32_t draws;
+            if (REPLAY) {
+                StreamDraws d; d.init(p.streams + (size_t)r * p.stream_stride, p.stream_len); d.pos = tail.x;
+                score = q_walk_uni(s, d, plies, kind); draws = d.consumed();
+            } else {
+                PhiloxDraws d; d.init(p.seed, p.first_rollout_id + r); d.pos = tail.x;
+                score = q_walk_uni(s, d, plies, kind); draws = d.consumed();
+            }
+            if (p.outcomes) store_outcome(p.outcomes, r, score, plies, kind, draws);
+            if (p.finals) { mctsb_qstate f; q_pack(s, f); store_qstate(p.finals, r, f); }
+        }
+    }
+    if (p.sums) accumulate_leaf(p.sums, leaf, active, score);
+    accumulate_counters(p.counters, active, wk, plies);
+}
+
+cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, cudaStream_t st) {
+    if (p.n_rollouts == 0) return cudaSuccess;
+    unsigned blocks = (unsigned)((p.n_rollouts + kThreads - 1) / kThreads);
+    if (replay) quoridor_uni_walk_kernel<true><<<blocks, kThreads, 0, st>>>(p);
+    else        quoridor_uni_walk_kernel<false><<<blocks, kThreads, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_quoridor_rollouts(const RolloutParams &p, int policy, bool replay, cudaStream_t st) {
     if (p.n_rollouts == 0) return cudaSuccess;
     unsigned blocks = (unsigned)((p.n_rollouts + kThreads - 1) / kThreads);

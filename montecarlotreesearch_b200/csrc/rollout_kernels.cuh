@@ -24,13 +24,20 @@ struct RolloutParams {
     void *finals;                  // mctsb_qstate[n_rollouts]
     unsigned long long *counters;  // [4]: rollouts, plies, flood_steps, flood_queries
     uint32_t lanes_per_batch;      // lockstep kernel: rollouts a warp takes per batch (1..32; set by the launch)
+    void *walk;                    // UNI lockstep: hand-over records between the two phases, 48 B per rollout (device)
 };
+#define MCTSB_UNI_WALK_BYTES 48
 
 // REF policy, production kernel (quoridor_lockstep.cu): one thread = one rollout, the 32 rollouts of a
 // warp advance ply-synchronously; `work_counter` is a device u64 the launch resets
 cudaError_t launch_quoridor_lockstep(const RolloutParams &p, bool replay, unsigned long long *work_counter, cudaStream_t st);
 
-// one thread = one rollout, natural control flow (UNI policy; REF kept as a cross-check)
+// UNI policy, production path (quoridor_uni_lockstep.cu): phase A = the wall phase on the lockstep machinery, phase
+// B = one thread per rollout walking the pawns once nobody has a wall left.  p.walk must hold n_rollouts records.
+cudaError_t launch_quoridor_uni_lockstep(const RolloutParams &p, bool replay, unsigned long long *work_counter, cudaStream_t st);
+cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, cudaStream_t st);
+
+// one thread = one rollout, natural control flow (cross-check of both policies: MCTSB_SIMPLE_KERNEL=1)
 cudaError_t launch_quoridor_rollouts(const RolloutParams &p, int policy, bool replay, cudaStream_t st);
 cudaError_t launch_ttt_rollouts(const RolloutParams &p, bool replay, cudaStream_t st);
 

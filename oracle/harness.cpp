@@ -13,6 +13,8 @@
 #include "mcts/include/mcts.h"
 #include <chrono>
 #include <atomic>
+#include <thread>
+#include <random>
 
 /* friend functions of Quoridor_state (Quoridor.h:78-80) re-declared at namespace scope */
 bool force_playwall(Quoridor_state &s);
@@ -431,6 +433,55 @@ double ref_jobscheduler_bench2(int game, const mctsb_qstate *qs, int n_states, u
     if (mean_score) *mean_score = sum / n_jobs;
     if (mean_square) *mean_square = sq / n_jobs;
     for (MCTS_state *s : states) delete s;
+    return secs;
+}
+
+/* CPU baseline of the UNI policy: uniformly random legal playouts driven through the reference's PUBLIC API
+ * (actions_to_try -> generate_all_moves, play_move; Quoridor.cpp:594-616,344-392) on n_threads std::threads, each
+ * with its own std::mt19937_64.  The reference has no such function — this is the loop the UNI oracle restates —
+ * so it is timed as "the reference's rules doing the UNI work".  Returns wall seconds. */
+double ref_uniform_bench(const mctsb_qstate *qs, int n_states, int n_threads, int n_playouts, int max_plies,
+                         double *mean_score, double *mean_plies) {
+    Silence q_;
+    std::vector<double> score((size_t)n_playouts, 0.0);
+    std::vector<int> plies((size_t)n_playouts, 0);
+    std::atomic<int> next(0);
+    auto worker = [&](int tid) {
+        std::mt19937_64 gen(0x9E3779B97F4A7C15ull * (uint64_t)(tid + 1));
+        for (;;) {
+            int i = next.fetch_add(1);
+            if (i >= n_playouts) break;
+            Quoridor_state s; load_q(s, qs + (i % n_states));
+            int n = 0; double result = 0.5;
+            while (true) {
+                if (s.is_terminal()) { result = s.check_winner() == 'W' ? 1.0 : 0.0; break; }
+                if (n >= max_plies) break;
+                queue<MCTS_move *> *Q = s.actions_to_try();
+                size_t L = Q->size();
+                if (L == 0) { delete Q; break; }
+                size_t idx = (size_t)(gen() % L);
+                Quoridor_move *chosen = NULL;
+                for (size_t k = 0; !Q->empty(); k++) {
+                    Quoridor_move *m = (Quoridor_move *)Q->front(); Q->pop();
+                    if (k == idx) chosen = m; else delete m;
+                }
+                delete Q;
+                s.play_move(chosen);
+                delete chosen;
+                n++;
+            }
+            score[(size_t)i] = result; plies[(size_t)i] = n;
+        }
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    std::vector<std::thread> th;
+    for (int t = 0; t < n_threads; t++) th.emplace_back(worker, t);
+    for (auto &t : th) t.join();
+    double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    double ss = 0, sp = 0;
+    for (int i = 0; i < n_playouts; i++) { ss += score[(size_t)i]; sp += plies[(size_t)i]; }
+    if (mean_score) *mean_score = ss / n_playouts;
+    if (mean_plies) *mean_plies = sp / n_playouts;
     return secs;
 }
 

@@ -132,6 +132,8 @@ class RefLib:
         L.ref_grow_tree.argtypes = [C.c_int, vp, C.c_uint32, C.c_uint32, C.c_int, vp, vp, C.c_int]
         L.ref_jobscheduler_bench.restype = C.c_double
         L.ref_jobscheduler_bench.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp]
+        L.ref_uniform_bench.restype = C.c_double
+        L.ref_uniform_bench.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
         L.ref_jobscheduler_bench2.restype = C.c_double
         L.ref_jobscheduler_bench2.argtypes = [C.c_int, vp, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, vp, vp]
         if kind == "gpu_dropin":
@@ -322,6 +324,13 @@ class RefLib:
         secs = self.lib.ref_jobscheduler_bench(game, qs.ctypes.data, qs.size, x_mask, o_mask, n_threads,
                                                n_jobs, C.addressof(mean))
         return secs, mean.value
+
+    def uniform_bench(self, n_threads, n_playouts, qstates=None, max_plies=4096):
+        """UNI playouts through the reference's public API on n_threads threads -> (seconds, mean score, mean plies)"""
+        qs = np.ascontiguousarray(qstates if qstates is not None else opening_state(), dtype=QSTATE_DTYPE).reshape(-1)
+        mean, plies = C.c_double(0), C.c_double(0)
+        secs = self.lib.ref_uniform_bench(qs.ctypes.data, qs.size, n_threads, n_playouts, max_plies, C.addressof(mean), C.addressof(plies))
+        return secs, mean.value, plies.value
 
     def jobscheduler_bench2(self, game, n_threads, n_jobs, qstates=None, x_mask=0, o_mask=0):
         """-> (wall seconds, mean result, standard deviation of one result)"""

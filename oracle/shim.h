@@ -34,6 +34,8 @@
 #include <stdexcept>
 #include <chrono>
 #include <atomic>
+#include <thread>
+#include <mutex>
 #include <utility>
 #include <iterator>
 #include <pthread.h>

@@ -25,6 +25,7 @@ class EmuLib:
         L.emu_t_rollout_streams.argtypes = [vp, C.c_int, vp, C.c_uint32, C.c_uint32, vp]
         L.emu_t_winner.argtypes = [C.c_uint32, C.c_uint32]
         L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int]
+        L.emu_uni_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp]
 
     def q_primitives(self, s):
         a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
@@ -122,3 +123,26 @@ class EmuLib:
         self.lib.emu_lockstep(a.ctypes.data, a.size, R, seed, first_id, sp, sl, ss, out.ctypes.data, fin.ctypes.data,
                               sums.ctypes.data, ctr.ctypes.data, blocks, lanes)
         return out, fin, sums, ctr
+
+    def uni_lockstep(self, states, R, seed, first_id, streams=None, blocks=1, lanes=32):
+        """The UNI path on the host: phase A (uni_lockstep_body) + phase B (q_walk_uni over the hand-over records).
+        -> (outcomes, finals, sums, counters, rollouts handed over to phase B)"""
+        import ctypes as C
+        from oracle.reflib import LEAFSUM_DTYPE
+        a = np.ascontiguousarray(states, dtype=QSTATE_DTYPE).reshape(-1)
+        if streams is not None:
+            st = np.ascontiguousarray(streams, dtype=np.uint32)
+            assert R == 1 and st.shape[0] == a.size
+            sp, sl, ss = st.ctypes.data, st.shape[1], st.shape[1]
+        else:
+            sp, sl, ss = None, 0, 0
+        n = a.size * R
+        out = np.zeros(n, dtype=OUTCOME_DTYPE)
+        fin = np.zeros(n, dtype=QSTATE_DTYPE)
+        sums = np.zeros(a.size, dtype=LEAFSUM_DTYPE)
+        ctr = np.zeros(4, dtype=np.uint64)
+        handed = C.c_uint64(0)
+        rc = self.lib.emu_uni_lockstep(a.ctypes.data, a.size, R, seed, first_id, sp, sl, ss, out.ctypes.data, fin.ctypes.data,
+                                       sums.ctypes.data, ctr.ctypes.data, blocks, lanes, C.byref(handed))
+        assert rc == 0
+        return out, fin, sums, ctr, handed.value

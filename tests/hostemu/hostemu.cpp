@@ -8,6 +8,7 @@
 #include "../../montecarlotreesearch_b200/csrc/qcore.cuh"
 #include "../../montecarlotreesearch_b200/csrc/ttt_core.cuh"
 #include "../../montecarlotreesearch_b200/csrc/quoridor_lockstep_body.cuh"
+#include "../../montecarlotreesearch_b200/csrc/quoridor_uni_lockstep_body.cuh"
 #include <vector>
 #include <string.h>
 using namespace mctsb;
@@ -147,6 +148,67 @@ int emu_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t 
     if (streams) lockstep_body<true>(p, &work, smem.data());
     else lockstep_body<false>(p, &work, smem.data());
 #endif
+    if (counters4) for (int i = 0; i < 4; i++) counters4[i] = ctr[i];
+    return 0;
+}
+
+// The UNI path on the host: phase A = uni_lockstep_body (one-lane warp, or emulated 32-lane warps), then phase B as
+// quoridor_uni_walk_kernel does it — q_walk_uni over the hand-over records.  handed_over = rollouts that reached phase B.
+#if defined(MCTSB_EMU_WARP32)
+struct EmuUniLaunch { RolloutParams p; UniWalk *walk; unsigned long long *work; std::vector<std::vector<uint32_t>> *smem; bool replay; };
+static void emu_uni_thread(void *a) {
+    EmuUniLaunch *L = (EmuUniLaunch *)a;
+    uint32_t *sm = (*L->smem)[simt::block()].data();
+    if (L->replay) uni_lockstep_body<true>(L->p, L->walk, L->work, sm); else uni_lockstep_body<false>(L->p, L->walk, L->work, sm);
+}
+#endif
+
+int emu_uni_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint64_t seed, uint64_t first_id,
+                     const uint32_t *streams, uint32_t stream_len, uint32_t stream_stride,
+                     mctsb_outcome *out, mctsb_qstate *finals, mctsb_leaf_sum *sums, uint64_t *counters4, int blocks, int lanes,
+                     uint64_t *handed_over) {
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = states; p.n_leaves = (uint32_t)n_leaves; p.rollouts_per_leaf = R; p.n_rollouts = (uint64_t)n_leaves * R;
+    p.seed = seed; p.first_rollout_id = first_id; p.streams = streams; p.stream_len = stream_len; p.stream_stride = stream_stride;
+    p.sums = sums; p.outcomes = out; p.finals = finals; p.lanes_per_batch = lanes > 0 ? (uint32_t)lanes : 32u;
+    unsigned long long ctr[4] = {0, 0, 0, 0};
+    p.counters = ctr;
+    if (sums) memset(sums, 0, sizeof(mctsb_leaf_sum) * (size_t)n_leaves);
+    std::vector<UniWalk> walk((size_t)p.n_rollouts);
+    memset(walk.data(), 0xff, walk.size() * sizeof(UniWalk));
+    p.walk = walk.data();
+    unsigned long long work = 0;
+#if defined(MCTSB_EMU_WARP32)
+    if (blocks < 1) blocks = 1;
+    std::vector<std::vector<uint32_t>> smem((size_t)blocks, std::vector<uint32_t>(LS_SMEM_WORDS + 64, 0xdeadbeefu));
+    EmuUniLaunch L; L.p = p; L.walk = walk.data(); L.work = &work; L.smem = &smem; L.replay = streams != nullptr;
+    simt::launch(blocks, LS_THREADS, emu_uni_thread, &L);
+#else
+    (void)blocks;
+    std::vector<uint32_t> smem(LS_SMEM_WORDS + 64);
+    if (streams) uni_lockstep_body<true>(p, walk.data(), &work, smem.data());
+    else uni_lockstep_body<false>(p, walk.data(), &work, smem.data());
+#endif
+    uint64_t handed = 0;
+    for (uint64_t r = 0; r < p.n_rollouts; r++) {
+        const UniWalk &w = walk[(size_t)r];
+        if (w.pending == 0u) continue;
+        if (w.pending != 1u) return -1;                       // a rollout phase A never wrote
+        handed++;
+        QState s; q_unpack(s, w.state);
+        int plies = (int)w.plies, kind = 0; double score; uint32_t draws;
+        if (streams) { StreamDraws d; d.init(streams + (size_t)r * stream_stride, stream_len); d.pos = w.plies; score = q_walk_uni(s, d, plies, kind); draws = d.consumed(); }
+        else { PhiloxDraws d; d.init(seed, first_id + r); d.pos = w.plies; score = q_walk_uni(s, d, plies, kind); draws = d.consumed(); }
+        if (out) { memset(out + r, 0, sizeof *out); out[r].score = score; out[r].plies = (uint16_t)plies; out[r].kind = (uint8_t)kind; out[r].draws = draws; }
+        if (finals) q_pack(s, finals[r]);
+        if (sums) {
+            size_t leaf = streams ? (size_t)r : (size_t)(r / R);
+            unsigned long long fx = (unsigned long long)(score * 144115188075855872.0);
+            sums[leaf].lo += fx & ((1ull << 29) - 1); sums[leaf].hi += fx >> 29; sums[leaf].n += 1;
+        }
+        ctr[0]++; ctr[1] += (unsigned long long)plies;
+    }
+    if (handed_over) *handed_over = handed;
     if (counters4) for (int i = 0; i < 4; i++) counters4[i] = ctr[i];
     return 0;
 }

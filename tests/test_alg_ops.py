@@ -5,7 +5,7 @@ import pytest
 import bench
 
 
-@pytest.mark.parametrize("workload", ["opening", "corpus"])
+@pytest.mark.parametrize("workload", ["opening", "corpus", "opening_uni"])
 def test_algorithmic_work_literals_are_what_the_oracle_counts(workload):
     assert bench.recount(workload) == bench.ALG_SAMPLES[workload]
 

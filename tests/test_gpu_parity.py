@@ -200,6 +200,37 @@ def test_uniform_policy_vs_oracle(be, port, corpus):
 
 
 # ---- Tic-Tac-Toe ---------------------------------------------------------------------------------------
+def test_uniform_policy_lockstep_path_vs_simple_kernel_and_oracle(be, port, corpus):
+    """The production UNI path (lockstep wall phase + walk kernel) against the one-thread-per-rollout kernel
+    (MCTSB_SIMPLE_KERNEL=1) on 256 mid-game leaves x 8 playouts, and against the oracle on ragged special leaves
+    (terminal, nobody has walls, one side has walls, a maze that overflows the stored layers); exact leaf sums too."""
+    import os
+    from tests.util import serpentine_state
+    os.environ["MCTSB_SIMPLE_KERNEL"] = "1"
+    try:
+        simple = m.RolloutBackend(0, m.DEFAULT_SEED)
+    finally:
+        del os.environ["MCTSB_SIMPLE_KERNEL"]
+    rng = np.random.default_rng(35)
+    states = corpus[rng.choice(len(corpus), 256, replace=False)]
+    a, fa = be.rollout_outcomes(G, m.POLICY_UNI, states, 8, 4711)
+    b, fb = simple.rollout_outcomes(G, m.POLICY_UNI, states, 8, 4711)
+    simple.close()
+    assert a.tobytes() == b.tobytes() and fa.tobytes() == fb.tobytes()
+    st = corpus[rng.choice(len(corpus), 40, replace=False)].copy()
+    st[3]["bx"] = 0
+    st[7]["wwalls"] = 0; st[7]["bwalls"] = 0
+    st[11]["wwalls"] = 0
+    st[13] = serpentine_state(turn=0, wwalls=3, bwalls=3)
+    out, fin = be.rollout_outcomes(G, m.POLICY_UNI, st, 5, 99)
+    _, sums = be.rollout_batch(G, m.POLICY_UNI, st, 5, 99)
+    for j in range(len(st)):
+        exp, efin, _ = port.q_rollout_philox(st[j], m.DEFAULT_SEED, 99 + 5 * j, 5, policy=1, finals=True)
+        assert exp.tobytes() == out[5 * j: 5 * j + 5].tobytes() and efin.tobytes() == fin[5 * j: 5 * j + 5].tobytes(), j
+        acc, _ = port.leaf_sum(exp["score"])
+        assert (int(acc["lo"]), int(acc["hi"]), int(acc["n"])) == (int(sums["lo"][j]), int(sums["hi"][j]), int(sums["n"][j]))
+
+
 def test_tictactoe_vs_golden(be):
     g = golden("golden_t.npz")
     out, _ = be.rollout_outcomes(T, 0, np.zeros(1, dtype=m.TSTATE_DTYPE), 20000, 0)

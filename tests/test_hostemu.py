@@ -198,3 +198,38 @@ def test_lockstep_warp32_forced_rare_branches(emu32, port, corpus):
     exp, efin = port.q_rollout_streams(states, streams)
     out, fin, _, _ = emu32.lockstep(states, 1, 0, 0, streams=streams, blocks=2)
     assert out.tobytes() == exp.tobytes() and fin.tobytes() == efin.tobytes()
+
+
+# ---- the UNI policy on the lockstep machinery (quoridor_uni_lockstep_body.cuh + the walk of phase B) ----------
+@pytest.mark.parametrize("warp32", [False, True])
+def test_uni_lockstep_vs_reference_golden_and_oracle(warp32, port, corpus):
+    from tests.hostemu.emulib import EmuLib
+    e = EmuLib(warp32=warp32)
+    g = golden("golden_q_uniform.npz")
+    streams = np.stack([philox_stream(int(g["seed"]), int(i), 8192) for i in g["id"]])
+    out, _, _, _, _ = e.uni_lockstep(corpus[g["index"]], 1, 0, 0, streams=streams, blocks=2)
+    assert (out["score"] == g["score"]).all() and (out["draws"] == g["draws"]).all()
+    assert (out["kind"] == g["kind"]).all() and (out["plies"] == g["plies"]).all()
+    # ragged mixed leaves: 5 rollouts per leaf, leaves change inside a warp; terminal, wall-less and one-sided leaves
+    rng = np.random.default_rng(5)
+    st = corpus[rng.choice(len(corpus), 60, replace=False)].copy()
+    st[3]["bx"] = 0                                   # Black has already won
+    st[7]["wwalls"] = 0; st[7]["bwalls"] = 0          # nobody has a wall: handed over at once
+    st[11]["wwalls"] = 0                              # only Black may place walls
+    out, fin, sums, _, handed = e.uni_lockstep(st, 5, 4242, 17, blocks=2)
+    assert handed > 200
+    for j in range(len(st)):
+        exp, efin, _ = port.q_rollout_philox(st[j], 4242, 17 + 5 * j, 5, policy=1, finals=True)
+        assert exp.tobytes() == out[5 * j: 5 * j + 5].tobytes() and efin.tobytes() == fin[5 * j: 5 * j + 5].tobytes(), j
+        acc, _ = port.leaf_sum(exp["score"])
+        assert (int(acc["lo"]), int(acc["hi"]), int(acc["n"])) == (int(sums["lo"][j]), int(sums["hi"][j]), int(sums["n"][j]))
+
+
+def test_uni_lockstep_warp32_long_paths_and_small_batches(emu32, port):
+    """mazes whose paths overflow the stored layers (nothing is pruned: 80 candidates per ply, several queue batches),
+    and a launch shape with fewer than 32 lanes per batch"""
+    from tests.util import serpentine_state
+    for s in (serpentine_state(turn=0, wwalls=3, bwalls=3), serpentine_state(rows=(0, 2, 4, 7), turn=1, wwalls=2, bwalls=4)):
+        exp, efin, _ = port.q_rollout_philox(s, 5, 0, 40, policy=1, finals=True)
+        out, fin, _, _, _ = emu32.uni_lockstep(s, 40, 5, 0, blocks=1, lanes=11)
+        assert exp.tobytes() == out.tobytes() and efin.tobytes() == fin.tobytes()
