@@ -78,7 +78,7 @@ int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const R
         TRY(grow_bytes(b, &b->d_walk, &b->cap_walk, (size_t)p.n_rollouts * MCTSB_UNI_WALK_BYTES));
         RolloutParams q = p;
         q.walk = b->d_walk;
-        e = launch_quoridor_uni_lockstep(q, replay, b->d_counters + 7, b->stream);
+        e = launch_quoridor_uni_lockstep(q, replay, b->d_counters + 6, b->stream);   // slots 6 and 7: the work counters of the two phases
         b->launches++;                             // two kernels
     }
     else if (game == MCTSB_GAME_QUORIDOR) e = launch_quoridor_rollouts(p, policy, replay, b->stream);

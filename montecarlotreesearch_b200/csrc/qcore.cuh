@@ -524,6 +524,35 @@ MC_HD void q_trace_to_anchors(const QTrace &t, uint64_t &may_h, uint64_t &may_v)
     may_h = ch; may_v = cv;
 }
 
+// Cell board (bit 9x+y) -> anchor mask (bit 8x+y): rows 0..7, columns 0..7.
+MC_HD uint64_t b81_to_anchors(B81 v) {
+    uint64_t a = 0;
+#pragma unroll
+    for (int x = 0; x < 8; x++) a |= (uint64_t)(b81_row(v, x) & 0xffu) << (8 * x);
+    return a;
+}
+
+// Walls that cannot close anybody in, found without a search.  A wall removes two parallel neighbouring edges, say
+// A|A' and B|B'.  If a three-step detour around one END of the wall is open (A -> the cell beside it -> across ->
+// A') and the two cells on either side of the wall are joined along it (A-B and A'-B' open), then A~A' and B~B'
+// still hold, every path that used a removed edge has a replacement, and the connectivity of the whole board is
+// what it was: both pawns keep their paths (legal_wall's blocking test, Quoridor.cpp:305-326, must say "legal").
+// On an open board this covers nearly every wall; the others go to the flood fill as before.
+//   horizontal wall under cells c, c+1:  oE[c] & oE[c+9] & ( oE[c-1] & oS[c-1] & oE[c+8]  |  oE[c+1] & oS[c+2] & oE[c+10] )
+//   vertical wall right of cells c, c+9: oS[c] & oS[c+1] & ( oS[c-9] & oE[c-9] & oS[c-8]  |  oS[c+9] & oE[c+18] & oS[c+10] )
+// (openE is 0 on column 8 and openS on row 8, so terms that would wrap around a board edge vanish by themselves.)
+MC_HD void q_detour_safe_masks(const QState &s, uint64_t &safe_h, uint64_t &safe_v) {
+    const B81 oS = s.openS, oE = s.openE;
+    const B81 e9 = shr<9>(oE), s1 = shr<1>(oS);
+    const B81 h_left = shl<1>(oE & oS & shr<9>(oE));                     // bit c: oE[c-1] & oS[c-1] & oE[c+8]
+    const B81 h_right = shr<1>(oE) & shr<2>(oS) & shr<10>(oE);           // bit c: oE[c+1] & oS[c+2] & oE[c+10]
+    const B81 sh = oE & e9 & (h_left | h_right);
+    const B81 v_top = shl<9>(oS & oE & s1);                              // bit c: oS[c-9] & oE[c-9] & oS[c-8]
+    const B81 v_bottom = shr<9>(oS) & shr<18>(oE) & shr<10>(oS);         // bit c: oS[c+9] & oE[c+18] & oS[c+10]
+    const B81 sv = oS & s1 & (v_top | v_bottom);
+    safe_h = b81_to_anchors(sh); safe_v = b81_to_anchors(sv);
+}
+
 struct QCut { uint64_t h, v; int sp; };    // anchors whose wall may change sp(q) (must be measured), and sp(q)
     // anchors whose wall cuts a shortest-path edge, and sp(q)
 
@@ -749,8 +778,11 @@ MC_HD void q_legal_parts(const QState &s, uint32_t &steps, uint64_t &legal_h, ui
     q_cheap_wall_masks(s, lh, lv);
     legal_h = lh; legal_v = lv;
     if ((lh | lv) == 0ull) return;
+    uint64_t safe_h, safe_v;
+    q_detour_safe_masks(s, safe_h, safe_v);
+    if (((lh & ~safe_h) | (lv & ~safe_v)) == 0ull) return;      // every candidate has its detour: nothing to search
     const QCut cw = q_cut_masks(s, 0, ls, wk), cb = q_cut_masks(s, 1, ls, wk);
-    uint64_t th = lh & (cw.h | cb.h), tv = lv & (cw.v | cb.v);
+    uint64_t th = lh & (cw.h | cb.h) & ~safe_h, tv = lv & (cw.v | cb.v) & ~safe_v;
     for (int k = q_mask_first(th, tv); k >= 0; q_mask_clear(th, tv, k), k = q_mask_first(th, tv)) {
         bool ok = true;
         if (q_mask_has(cw.h, cw.v, k)) ok = q_sp_with_wall(s, 0, k, wk) >= 0;

@@ -63,7 +63,7 @@ cudaError_t launch_quoridor_uni_lockstep(const RolloutParams &params, bool repla
     if (replay) quoridor_uni_lockstep_kernel<true><<<blocks, LS_THREADS, UNI_SMEM, st>>>(p, work_counter);
     else        quoridor_uni_lockstep_kernel<false><<<blocks, LS_THREADS, UNI_SMEM, st>>>(p, work_counter);
     if ((e = cudaGetLastError()) != cudaSuccess) return e;
-    return launch_quoridor_uni_walk(p, replay, st);
+    return launch_quoridor_uni_walk(p, replay, work_counter + 1, c.sms, st);     // the walk's own counter: the slot after phase A's
 }
 
 }  // namespace mctsb

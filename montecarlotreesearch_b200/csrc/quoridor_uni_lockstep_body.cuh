@@ -9,8 +9,9 @@
 // of a dozen instructions each, with a length that varies by a factor of thirty between playouts.
 //
 //   phase A (this file): one thread = one rollout, the 32 rollouts of a warp advance ply-synchronously, exactly as
-//     in the REF kernel.  Per ply: goal-rooted layers + trace for BOTH players give the walls that can change a
-//     shortest path at all (q_trace_*, exact: every other wall leaves both distances finite), the survivors go
+//     in the REF kernel.  Per ply: walls with an open three-step detour around one end are legal without a search
+//     (q_detour_safe_masks); for the rest, goal-rooted layers + trace for BOTH players give the walls that can change
+//     a shortest path at all (q_trace_*, exact: every other wall leaves both distances finite), the survivors go
 //     to the warp's shared task queue, all 32 lanes flood-fill them, and a wall that closes a pawn in is struck
 //     from its owner's legal set with one shared-memory atomicOr.  Then one draw picks the idx-th legal move.
 //     A rollout whose two players have no wall left is handed over: its position and ply count go to a record
@@ -111,7 +112,14 @@ LS_DEV void uni_lockstep_body(const RolloutParams &p, UniWalk *walk, unsigned lo
 
         uint64_t cheap_h = 0, cheap_v = 0;
         if (playing) q_cheap_wall_masks(s, cheap_h, cheap_v);
-        const bool need = playing && (cheap_h | cheap_v) != 0ull;
+        // walls with an open detour around one end cannot close anybody in (q_detour_safe_masks): no search for them
+        uint64_t risky_h = 0, risky_v = 0;
+        if (playing && (cheap_h | cheap_v) != 0ull) {
+            uint64_t safe_h, safe_v;
+            q_detour_safe_masks(s, safe_h, safe_v);
+            risky_h = cheap_h & ~safe_h; risky_v = cheap_v & ~safe_v;
+        }
+        const bool need = (risky_h | risky_v) != 0ull;
         const uint32_t steps = playing ? q_step_mask(s) : 0u;
 
         // ---- P2: per player, goal-rooted layers until the pawn is reached, then the trace -> walls that may change
@@ -160,7 +168,7 @@ LS_DEV void uni_lockstep_body(const RolloutParams &p, UniWalk *walk, unsigned lo
         {
             uint32_t pend0 = 0, pend1 = 0, pend2 = 0, pend3 = 0;
             if (need) {
-                const uint64_t ph = cheap_h & (cut_h0 | cut_h1), pv = cheap_v & (cut_v0 | cut_v1);
+                const uint64_t ph = risky_h & (cut_h0 | cut_h1), pv = risky_v & (cut_v0 | cut_v1);
                 pend0 = (uint32_t)ph; pend1 = (uint32_t)(ph >> 32); pend2 = (uint32_t)pv; pend3 = (uint32_t)(pv >> 32);
             }
             // which player a pending wall has to be measured for: bit set = the wall may change that player's distance

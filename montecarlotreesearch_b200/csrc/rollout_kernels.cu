@@ -121,50 +121,202 @@ __global__ void __launch_bounds__(kThreads) quoridor_rollout_kernel(RolloutParam
 }
 
 // UNI policy, phase B (quoridor_uni_lockstep_body.cuh): the rollouts the lockstep kernel handed over have no wall
-// left on either side — what remains is q_rollout_uni's loop with an empty wall set, a random walk of the two pawns
-// until one reaches its goal row (or the ply cap).  One thread per rollout; record r = {position, plies so far,
-// pending}.  The draw stream continues where phase A stopped: one draw per ply, so position = plies.
-template <bool REPLAY>
-__global__ void __launch_bounds__(kThreads) quoridor_uni_walk_kernel(RolloutParams p) {
-    const uint64_t r = (uint64_t)blockIdx.x * kThreads + threadIdx.x;
-    bool active = r < p.n_rollouts;
-    const uint32_t leaf = active ? (REPLAY ? (uint32_t)r : (uint32_t)(r / p.rollouts_per_leaf)) : 0u;
-    double score = 0.0; int plies = 0, kind = 0;
-    QWork wk = {0u, 0u, 0u};
-    if (active) {
-        const uint4 *rec = reinterpret_cast<const uint4 *>(p.walk) + 3ull * r;
-        const uint4 tail = rec[2];
-        active = tail.y != 0u;
-        if (active) {
-            const uint4 lo = rec[0], hi = rec[1];
-            mctsb_qstate packed;
-            packed.h_anchor = (uint64_t)lo.x | ((uint64_t)lo.y << 32); packed.v_anchor = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
-            packed.wx = hi.x & 0xff; packed.wy = (hi.x >> 8) & 0xff; packed.bx = (hi.x >> 16) & 0xff; packed.by = hi.x >> 24;
-            packed.wwalls = hi.y & 0xff; packed.bwalls = (hi.y >> 8) & 0xff; packed.turn = (hi.y >> 16) & 0xff; packed.flags = hi.y >> 24;
-            packed.move_counter = hi.z; packed.reserved = 0;
-            QState s; q_unpack(s, packed);
-            plies = (int)tail.x;
-            uint32_t draws;
-            if (REPLAY) {
-                StreamDraws d; d.init(p.streams + (size_t)r * p.stream_stride, p.stream_len); d.pos = tail.x;
-                score = q_walk_uni(s, d, plies, kind); draws = d.consumed();
-            } else {
-                PhiloxDraws d; d.init(p.seed, p.first_rollout_id + r); d.pos = tail.x;
-                score = q_walk_uni(s, d, plies, kind); draws = d.consumed();
+// left on either side — what remains is q_rollout_uni's loop with an empty wall set (q_walk_uni, qcore.cuh): a random
+// walk of the two pawns until one reaches its goal row (or the ply cap), 20 to 3 000 plies.  Record r = {position,
+// plies so far, pending}; the draw stream continues where phase A stopped (one draw per ply: position = plies).
+// Persistent threads: every trip of the loop plays ONE ply of every lane's rollout, and a lane whose rollout has
+// ended takes the next record from a global counter in the same trip (one atomic per warp and trip), so the ragged
+// lengths never leave lanes idle — a thread-per-rollout launch waits for the longest of 32 walks, four times the mean.
+// (The position lives in scalars here — two boards, two cells, the side to move — not in a QState: its small arrays
+// would be indexed by the side to move and end up in local memory.)  Philox blocks are only computed on every fourth
+// trip of the loop, for all lanes at once: a lane that runs out of draws between two such trips skips a trip or two
+// (once per rollout, then it stays in step), instead of the whole warp paying the generator on every trip.
+// The maze no longer changes in phase B, so the four "may step N/S/W/E" bits of every cell are computed once per
+// rollout into a table in shared memory (81 nibbles = 11 words per thread, one column of the block's array per
+// thread: conflict-free) and a ply reads two nibbles instead of testing eight board bits.
+static constexpr int kWalkWords = 11;
+__device__ __forceinline__ void walk_build_table(uint32_t *col, B81 oS, B81 oE) {
+    // nibble of cell c: bit 0 north (cell c-9 has its south edge open), 1 south, 2 west (cell c-1 has its east edge open), 3 east
+    const B81 n = shl<9>(oS), w = shl<1>(oE);
+#pragma unroll
+    for (int j = 0; j < kWalkWords; j++) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const int c = 8 * j + i;
+            if (c < 81) {
+                const uint32_t nib = (b81_test(n, c) ? 1u : 0u) | (b81_test(oS, c) ? 2u : 0u) | (b81_test(w, c) ? 4u : 0u) | (b81_test(oE, c) ? 8u : 0u);
+                word |= nib << (4 * i);
             }
-            if (p.outcomes) store_outcome(p.outcomes, r, score, plies, kind, draws);
-            if (p.finals) { mctsb_qstate f; q_pack(s, f); store_qstate(p.finals, r, f); }
         }
+        col[j * kThreads] = word;
     }
-    if (p.sums) accumulate_leaf(p.sums, leaf, active, score);
-    accumulate_counters(p.counters, active, wk, plies);
+}
+__device__ __forceinline__ uint32_t walk_moves_from(const uint32_t *col, int c) {
+    return (col[(c >> 3) * kThreads] >> (4 * (c & 7))) & 15u;
 }
 
-cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, cudaStream_t st) {
+// A finished rollout is not written out, and its lane not refilled, at once: both are branches the whole warp
+// would walk through for one lane (unpack + table: several hundred instructions, a fifth of a rollout's own walk
+// when paid per lane).  Finished lanes wait until kWalkBatch of them can be served together.
+static constexpr int kWalkBatch = 8;
+
+template <bool REPLAY>
+__global__ void __launch_bounds__(kThreads) quoridor_uni_walk_kernel(RolloutParams p, unsigned long long *work_counter) {
+    __shared__ uint32_t table[kWalkWords * kThreads];
+    uint32_t *col = table + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    uint64_t hanc = 0, vanc = 0; uint32_t move_counter = 0;
+    int cw = 4, cb = 76, turn = 0;
+    const uint32_t k0 = (uint32_t)p.seed, k1 = (uint32_t)(p.seed >> 32);
+    uint32_t id_lo = 0, id_hi = 0, pos = 0;
+    Philox4 buf = {0u, 0u, 0u, 0u};
+    bool block_valid = false;                                  // buf holds Philox block pos >> 2
+    const uint32_t *stream = nullptr;
+    bool have = false, done = false, exhausted = false;        // walking / finished and waiting to be written out / no records left
+    int fin_kind = -1; double fin_score = 0.5;
+    uint64_t r = 0; uint32_t leaf = 0; int plies = 0;
+    unsigned long long acc_lo = 0, acc_hi = 0, acc_n = 0; uint32_t acc_leaf = 0xffffffffu;
+    uint32_t done_rollouts = 0, done_plies = 0;
+#pragma unroll 1
+    for (uint32_t trip = 0;; trip++) {
+        // ---- service: write out finished rollouts and hand their lanes the next records, kWalkBatch lanes at a time
+        const unsigned idle = __ballot_sync(0xffffffffu, !have && !exhausted);
+        const unsigned walking = __ballot_sync(0xffffffffu, have);
+        if (idle && (__popc(idle) >= kWalkBatch || walking == 0u)) {
+            if (done) {
+                if (p.outcomes) store_outcome(p.outcomes, r, fin_score, plies, fin_kind, pos);
+                if (p.finals) {
+                    mctsb_qstate f;
+                    f.h_anchor = hanc; f.v_anchor = vanc;
+                    f.wx = (uint8_t)(cw / 9); f.wy = (uint8_t)(cw % 9); f.bx = (uint8_t)(cb / 9); f.by = (uint8_t)(cb % 9);
+                    f.wwalls = 0; f.bwalls = 0; f.turn = (uint8_t)turn; f.flags = 0; f.move_counter = move_counter; f.reserved = 0;
+                    store_qstate(p.finals, r, f);
+                }
+                if (p.sums) {
+                    if (acc_leaf != leaf) {
+                        if (acc_n) {
+                            atomicAdd((unsigned long long *)&p.sums[acc_leaf].lo, acc_lo);
+                            atomicAdd((unsigned long long *)&p.sums[acc_leaf].hi, acc_hi);
+                            atomicAdd((unsigned long long *)&p.sums[acc_leaf].n, acc_n);
+                        }
+                        acc_lo = acc_hi = acc_n = 0; acc_leaf = leaf;
+                    }
+                    const unsigned long long fx = __double2ull_rz(fin_score * 144115188075855872.0);
+                    acc_lo += fx & ((1ull << 29) - 1); acc_hi += fx >> 29; acc_n += 1;
+                }
+                done_rollouts++; done_plies += (uint32_t)plies;
+                done = false;
+            }
+            unsigned long long base = 0;
+            const int leader = __ffs((int)idle) - 1;
+            if (lane == leader) base = atomicAdd(work_counter, (unsigned long long)__popc(idle));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if ((idle >> lane) & 1u) {
+                r = base + (unsigned long long)__popc(idle & ((1u << lane) - 1u));
+                if (r >= p.n_rollouts) exhausted = true;
+                else {
+                    const uint4 *rec = reinterpret_cast<const uint4 *>(p.walk) + 3ull * r;
+                    const uint4 tail = rec[2];
+                    if (tail.y != 0u) {                       // pending: phase A handed it over (else it ended there)
+                        const uint4 lo = rec[0], hi = rec[1];
+                        mctsb_qstate packed;
+                        packed.h_anchor = (uint64_t)lo.x | ((uint64_t)lo.y << 32); packed.v_anchor = (uint64_t)lo.z | ((uint64_t)lo.w << 32);
+                        packed.wx = hi.x & 0xff; packed.wy = (hi.x >> 8) & 0xff; packed.bx = (hi.x >> 16) & 0xff; packed.by = hi.x >> 24;
+                        packed.wwalls = hi.y & 0xff; packed.bwalls = (hi.y >> 8) & 0xff; packed.turn = (hi.y >> 16) & 0xff; packed.flags = hi.y >> 24;
+                        packed.move_counter = hi.z; packed.reserved = 0;
+                        QState s; q_unpack(s, packed);
+                        walk_build_table(col, s.openS, s.openE);
+                        hanc = s.hanc; vanc = s.vanc; move_counter = s.move_counter;
+                        cw = s.cell[0]; cb = s.cell[1]; turn = s.turn;
+                        plies = (int)tail.x; pos = tail.x;
+                        leaf = REPLAY ? (uint32_t)r : (uint32_t)(r / p.rollouts_per_leaf);
+                        if (REPLAY) stream = p.streams + (size_t)r * p.stream_stride;
+                        else { const uint64_t id = p.first_rollout_id + r; id_lo = (uint32_t)id; id_hi = (uint32_t)(id >> 32); }
+                        have = true;
+                        block_valid = false;
+                        if (!REPLAY && (pos & 3u) != 0u) { buf = philox4x32_10(pos >> 2, id_lo, id_hi, 0u, k0, k1); block_valid = true; }   // mid-block start
+                    }
+                }
+            }
+        }
+        if (!__any_sync(0xffffffffu, have || done || !exhausted)) break;
+        if (!REPLAY && (trip & 3u) == 0u) {                    // the generator's turn: every lane that is out of draws
+            const bool need = have && !block_valid;
+            if (__any_sync(0xffffffffu, need)) {
+                const Philox4 fresh = philox4x32_10(pos >> 2, id_lo, id_hi, 0u, k0, k1);
+                if (need) { buf = fresh; block_valid = true; }
+            }
+        }
+        // ---- one ply of q_walk_uni (qcore.cuh): winner, ply cap, step mask, pick, play
+        if (have) {
+            if (cw >= 72) { fin_kind = 0; fin_score = 1.0; have = false; done = true; }
+            else if (cb < 9) { fin_kind = 1; fin_score = 0.0; have = false; done = true; }
+            else if (plies >= MCTSB_UNI_MAX_PLIES) { fin_kind = 4; fin_score = 0.5; have = false; done = true; }
+        }
+        const int me = turn ? cb : cw, en = turn ? cw : cb;
+        uint32_t m = 0;
+        if (have) {                                             // q_step_mask (qcore.cuh) from the table
+            const uint32_t mm = walk_moves_from(col, me);
+            const int dist = me - en;
+            const bool adjacent = dist == 9 || dist == -9 || dist == 1 || dist == -1;
+            if (!adjacent) m = (mm & 1u) | ((mm & 2u) << 1) | ((mm & 4u) << 2) | ((mm & 8u) << 3);   // plain steps: candidates 0, 2, 4, 6
+            else {                                              // the pawns touch: jumps and side steps (rare)
+                const uint32_t em = walk_moves_from(col, en);
+                const bool aN = (mm & 1u) && en == me - 9, aS = (mm & 2u) && en == me + 9;
+                const bool aW = (mm & 4u) && en == me - 1, aE = (mm & 8u) && en == me + 1;
+                const bool eN = em & 1u, eS = em & 2u, eW = em & 4u, eE = em & 8u;
+                if ((mm & 1u) && !aN) m |= 1u << 0;
+                if (aN && eN)         m |= 1u << 1;
+                if ((mm & 2u) && !aS) m |= 1u << 2;
+                if (aS && eS)         m |= 1u << 3;
+                if ((mm & 4u) && !aW) m |= 1u << 4;
+                if (aW && eW)         m |= 1u << 5;
+                if ((mm & 8u) && !aE) m |= 1u << 6;
+                if (aE && eE)         m |= 1u << 7;
+                if ((aN && !eN && eW) || (aW && !eW && eN)) m |= 1u << 8;
+                if ((aN && !eN && eE) || (aE && !eE && eN)) m |= 1u << 9;
+                if ((aS && !eS && eW) || (aW && !eW && eS)) m |= 1u << 10;
+                if ((aS && !eS && eE) || (aE && !eE && eS)) m |= 1u << 11;
+            }
+            if (m == 0u) { fin_kind = 3; fin_score = 0.5; have = false; done = true; }      // no legal move at all
+        }
+        const int n = __popc(m);
+        if (have && (REPLAY || block_valid)) {                  // a lane out of draws waits for the generator's trip
+            uint32_t u;
+            if (REPLAY) u = stream[pos % p.stream_len];
+            else { const uint32_t sh = pos & 3u; u = sh == 0 ? buf.x : sh == 1 ? buf.y : sh == 2 ? buf.z : buf.w; }
+            pos++;
+            if ((pos & 3u) == 0u) block_valid = false;
+            int idx = (int)__umulhi(u, (uint32_t)n);
+#pragma unroll 1
+            for (; idx > 0; idx--) m &= ~(1u << (31 - __clz((int)m)));
+            const int target = me + q_step_delta(31 - __clz((int)m));
+            if (turn) cb = target; else cw = target;
+            turn ^= 1; move_counter++;
+            plies++;
+        }
+    }
+    if (p.sums && acc_n) {
+        atomicAdd((unsigned long long *)&p.sums[acc_leaf].lo, acc_lo);
+        atomicAdd((unsigned long long *)&p.sums[acc_leaf].hi, acc_hi);
+        atomicAdd((unsigned long long *)&p.sums[acc_leaf].n, acc_n);
+    }
+    if (p.counters) {
+        const uint32_t a = __reduce_add_sync(0xffffffffu, done_rollouts), b = __reduce_add_sync(0xffffffffu, done_plies);
+        if (lane == 0 && a) { atomicAdd(p.counters + 0, (unsigned long long)a); atomicAdd(p.counters + 1, (unsigned long long)b); }
+    }
+}
+
+cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, unsigned long long *work_counter, int sms, cudaStream_t st) {
     if (p.n_rollouts == 0) return cudaSuccess;
-    unsigned blocks = (unsigned)((p.n_rollouts + kThreads - 1) / kThreads);
-    if (replay) quoridor_uni_walk_kernel<true><<<blocks, kThreads, 0, st>>>(p);
-    else        quoridor_uni_walk_kernel<false><<<blocks, kThreads, 0, st>>>(p);
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
+    if (e != cudaSuccess) return e;
+    // persistent grid: up to 16 blocks of 128 threads per SM, never more threads than rollouts
+    unsigned long long want = (p.n_rollouts + kThreads - 1) / kThreads, cap = (unsigned long long)sms * 16ull;
+    unsigned blocks = (unsigned)(want < cap ? want : cap);
+    if (replay) quoridor_uni_walk_kernel<true><<<blocks, kThreads, 0, st>>>(p, work_counter);
+    else        quoridor_uni_walk_kernel<false><<<blocks, kThreads, 0, st>>>(p, work_counter);
     return cudaGetLastError();
 }
 
@@ -227,14 +379,15 @@ __global__ void __launch_bounds__(kThreads) quoridor_movegen_kernel(const mctsb_
     if (warp >= n) return;
     QState s;
     q_unpack(s, load_qstate(states, warp));
-    uint64_t ch, cv;
+    uint64_t ch, cv, safe_h, safe_v;
     q_cheap_wall_masks(s, ch, cv);
+    q_detour_safe_masks(s, safe_h, safe_v);                 // an open detour around one end: legal without a search
     uint32_t bal[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         int a = 32 * (j >> 1) + lane, vertical = j & 1;
         bool ok = ((vertical ? cv : ch) >> a) & 1ull;
-        if (ok) ok = q_wall_keeps_paths(s, 2 * a + vertical, nullptr);
+        if (ok && !(((vertical ? safe_v : safe_h) >> a) & 1ull)) ok = q_wall_keeps_paths(s, 2 * a + vertical, nullptr);
         bal[j] = __ballot_sync(0xffffffffu, ok);
     }
     if (lane == 0) {

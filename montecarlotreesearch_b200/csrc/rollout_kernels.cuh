@@ -35,7 +35,7 @@ cudaError_t launch_quoridor_lockstep(const RolloutParams &p, bool replay, unsign
 // UNI policy, production path (quoridor_uni_lockstep.cu): phase A = the wall phase on the lockstep machinery, phase
 // B = one thread per rollout walking the pawns once nobody has a wall left.  p.walk must hold n_rollouts records.
 cudaError_t launch_quoridor_uni_lockstep(const RolloutParams &p, bool replay, unsigned long long *work_counter, cudaStream_t st);
-cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, cudaStream_t st);
+cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, unsigned long long *work_counter, int sms, cudaStream_t st);
 
 // one thread = one rollout, natural control flow (cross-check of both policies: MCTSB_SIMPLE_KERNEL=1)
 cudaError_t launch_quoridor_rollouts(const RolloutParams &p, int policy, bool replay, cudaStream_t st);

@@ -218,7 +218,7 @@ def test_uniform_policy_lockstep_path_vs_simple_kernel_and_oracle(be, port, corp
     simple.close()
     assert a.tobytes() == b.tobytes() and fa.tobytes() == fb.tobytes()
     st = corpus[rng.choice(len(corpus), 40, replace=False)].copy()
-    st[3]["bx"] = 0
+    st[3]["bx"] = 0; st[3]["by"] = (int(st[3]["wy"]) + 1) % 9      # Black has already won (and does not stand on White)
     st[7]["wwalls"] = 0; st[7]["bwalls"] = 0
     st[11]["wwalls"] = 0
     st[13] = serpentine_state(turn=0, wwalls=3, bwalls=3)

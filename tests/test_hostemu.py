@@ -213,7 +213,7 @@ def test_uni_lockstep_vs_reference_golden_and_oracle(warp32, port, corpus):
     # ragged mixed leaves: 5 rollouts per leaf, leaves change inside a warp; terminal, wall-less and one-sided leaves
     rng = np.random.default_rng(5)
     st = corpus[rng.choice(len(corpus), 60, replace=False)].copy()
-    st[3]["bx"] = 0                                   # Black has already won
+    st[3]["bx"] = 0; st[3]["by"] = (int(st[3]["wy"]) + 1) % 9      # Black has already won (and does not stand on White)
     st[7]["wwalls"] = 0; st[7]["bwalls"] = 0          # nobody has a wall: handed over at once
     st[11]["wwalls"] = 0                              # only Black may place walls
     out, fin, sums, _, handed = e.uni_lockstep(st, 5, 4242, 17, blocks=2)
