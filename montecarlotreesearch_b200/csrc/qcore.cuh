@@ -553,6 +553,19 @@ MC_HD void q_detour_safe_masks(const QState &s, uint64_t &safe_h, uint64_t &safe
     safe_h = b81_to_anchors(sh); safe_v = b81_to_anchors(sv);
 }
 
+// the same test for ONE wall k = 2 * anchor + orientation (branch-free apart from the orientation select)
+MC_HD bool q_detour_safe_one(B81 oS, B81 oE, int k) {
+    const int a = k >> 1, c = 9 * (a >> 3) + (a & 7);
+    if (k & 1) {
+        const bool top = c >= 9 && b81_test(oS, c - 9) && b81_test(oE, c - 9) && b81_test(oS, c - 8);
+        const bool bottom = b81_test(oS, c + 9) && b81_test(oE, c + 18) && b81_test(oS, c + 10);
+        return b81_test(oS, c) && b81_test(oS, c + 1) && (top || bottom);
+    }
+    const bool left = c >= 1 && b81_test(oE, c - 1) && b81_test(oS, c - 1) && b81_test(oE, c + 8);
+    const bool right = b81_test(oE, c + 1) && b81_test(oS, c + 2) && b81_test(oE, c + 10);
+    return b81_test(oE, c) && b81_test(oE, c + 9) && (left || right);
+}
+
 struct QCut { uint64_t h, v; int sp; };    // anchors whose wall may change sp(q) (must be measured), and sp(q)
     // anchors whose wall cuts a shortest-path edge, and sp(q)
 
@@ -715,7 +728,7 @@ MC_HD int q_pick_semirandom(QState &s, Draws &d, Layers &ls, QWork *wk) {
             }
         } else if (n > 0) {                                    // first fully legal in shuffled order (:773-788)
             int k = q_pool_select(cheap_h, cheap_v, j0);       // the head of the shuffle: one draw
-            if (q_wall_keeps_paths(s, k, wk)) return 128 + k;
+            if (q_detour_safe_one(s.openS, s.openE, k) || q_wall_keeps_paths(s, k, wk)) return 128 + k;
             uint64_t th = cheap_h, tv = cheap_v;
             q_mask_clear(th, tv, k);
             while (th | tv) {                                  // rare: walk on in key order
