@@ -272,3 +272,23 @@ def test_config4_quoridor_selfplay_flush_on_gpu(host, in_flight):
     assert 0 <= mv < 209
     t.advance(mv)
     t.close()
+
+
+@pytest.mark.gpu
+def test_cpp_root_parallel_selfplay_program(tmp_path):
+    """integration/selfplay_root_parallel.cpp: configs[3]/[4] as a plain C++ program over libmcts_host.so — one tree
+    and one host thread per GPU of the box, NCCL merge of the root statistics behind the C ABI, no Python in the loop."""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "montecarlotreesearch_b200")
+    exe = str(tmp_path / "selfplay_cpp")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "include"), "-I", os.path.join(pkg, "host"),
+                           os.path.join(root, "integration", "selfplay_root_parallel.cpp"), "-L", pkg, "-lmcts_host", "-lmctsb",
+                           "-Wl,-rpath," + pkg, "-o", exe])
+    r = subprocess.run([exe, "0", "96", "16", "256", "8"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["n_gpus"] == m.device_count() and line["moves"] == 8 and line["same_move_on_every_gpu"]
+    assert line["rollouts_total"] == line["n_gpus"] * 8 * 96 * 256
