@@ -85,7 +85,7 @@ ALG_OPS_PER_ROLLOUT = alg_ops_per_rollout("opening")
 EXEC_OPS_PER_FLOOD_STEP = 30
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of 2^20 rollouts (ncu --set full, profiles/): the
 # algorithmic HBM traffic is 32 B in + 24 B out per LEAF; what is measured is stack/L2 write-back noise
-NCU_DRAM_BYTES_PER_LAUNCH = 818944 + 520704   # profiles/r02_lockstep.md (ncu --set full, one launch of 2^20 rollouts)
+NCU_DRAM_BYTES_PER_LAUNCH = 433664 + 1706752   # profiles/r02_lockstep.md (ncu --set full, one launch of 2^20 rollouts: read + write)
 
 
 class ClockSampler:
@@ -472,8 +472,9 @@ def main():
                      "frac": achieved / int_peak if rooflined else None,
                      "frac_algorithmic": achieved / int_peak if rooflined else None,
                      "frac_executed_flood_arithmetic": exec_flood_ops / int_peak if args.game == "quoridor" else None,
-                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
-                     "traffic_note": "1.3 MB per 28 ms launch = 48 MB/s of stack / counter write-back against 32 B in + 24 B out per leaf algorithmic: HBM is idle, the bound is integer issue",
+                     "traffic": NCU_DRAM_BYTES_PER_LAUNCH if not secondary else None,
+                     "traffic_note": "REF policy, 2^20 rollouts: 2.1 MB per 28 ms launch = 76 MB/s of spill / counter write-back against 32 B in + 24 B out per leaf algorithmic: HBM is idle, the bound is integer issue"
+                                     if not secondary else "UNI policy: 48 B hand-over record written by the wall phase and read by the walk kernel per rollout (profiles/r02_uni.md)" if uni else None,
                      "alu_pipe_lop3_peak": lop3_peak / 1e12, "alg_ops_per_rollout": alg_ops, "executed_flood_steps_per_rollout": exec_steps_per_rollout,
                      "note": "thread-level integer ops; peak measured live by mctsb_int_issue_peak (LOP3 + integer-add chains on all SMs, both pipes; alu_pipe_lop3_peak = LOP3 only). "
                              "frac (= frac_algorithmic) = rollouts/s x the REFERENCE algorithm's integer work per rollout (oracle work counters, recounted by tests/test_alg_ops.py) / peak: "
