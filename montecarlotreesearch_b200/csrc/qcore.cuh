@@ -537,6 +537,7 @@ MC_HD uint64_t b81_to_anchors(B81 v) {
 // A') and the two cells on either side of the wall are joined along it (A-B and A'-B' open), then A~A' and B~B'
 // still hold, every path that used a removed edge has a replacement, and the connectivity of the whole board is
 // what it was: both pawns keep their paths (legal_wall's blocking test, Quoridor.cpp:305-326, must say "legal").
+// The same holds when BOTH ends have their detour (A~A' around one end, B~B' around the other), joined or not.
 // On an open board this covers nearly every wall; the others go to the flood fill as before.
 //   horizontal wall under cells c, c+1:  oE[c] & oE[c+9] & ( oE[c-1] & oS[c-1] & oE[c+8]  |  oE[c+1] & oS[c+2] & oE[c+10] )
 //   vertical wall right of cells c, c+9: oS[c] & oS[c+1] & ( oS[c-9] & oE[c-9] & oS[c-8]  |  oS[c+9] & oE[c+18] & oS[c+10] )
@@ -546,10 +547,10 @@ MC_HD void q_detour_safe_masks(const QState &s, uint64_t &safe_h, uint64_t &safe
     const B81 e9 = shr<9>(oE), s1 = shr<1>(oS);
     const B81 h_left = shl<1>(oE & oS & shr<9>(oE));                     // bit c: oE[c-1] & oS[c-1] & oE[c+8]
     const B81 h_right = shr<1>(oE) & shr<2>(oS) & shr<10>(oE);           // bit c: oE[c+1] & oS[c+2] & oE[c+10]
-    const B81 sh = oE & e9 & (h_left | h_right);
+    const B81 sh = (oE & e9 & (h_left | h_right)) | (h_left & h_right);   // one detour + joined sides, or a detour at either end
     const B81 v_top = shl<9>(oS & oE & s1);                              // bit c: oS[c-9] & oE[c-9] & oS[c-8]
     const B81 v_bottom = shr<9>(oS) & shr<18>(oE) & shr<10>(oS);         // bit c: oS[c+9] & oE[c+18] & oS[c+10]
-    const B81 sv = oS & s1 & (v_top | v_bottom);
+    const B81 sv = (oS & s1 & (v_top | v_bottom)) | (v_top & v_bottom);
     safe_h = b81_to_anchors(sh); safe_v = b81_to_anchors(sv);
 }
 
@@ -559,11 +560,11 @@ MC_HD bool q_detour_safe_one(B81 oS, B81 oE, int k) {
     if (k & 1) {
         const bool top = c >= 9 && b81_test(oS, c - 9) && b81_test(oE, c - 9) && b81_test(oS, c - 8);
         const bool bottom = b81_test(oS, c + 9) && b81_test(oE, c + 18) && b81_test(oS, c + 10);
-        return b81_test(oS, c) && b81_test(oS, c + 1) && (top || bottom);
+        return (b81_test(oS, c) && b81_test(oS, c + 1) && (top || bottom)) || (top && bottom);
     }
     const bool left = c >= 1 && b81_test(oE, c - 1) && b81_test(oS, c - 1) && b81_test(oE, c + 8);
     const bool right = b81_test(oE, c + 1) && b81_test(oS, c + 2) && b81_test(oE, c + 10);
-    return b81_test(oE, c) && b81_test(oE, c + 9) && (left || right);
+    return (b81_test(oE, c) && b81_test(oE, c + 9) && (left || right)) || (left && right);
 }
 
 struct QCut { uint64_t h, v; int sp; };    // anchors whose wall may change sp(q) (must be measured), and sp(q)

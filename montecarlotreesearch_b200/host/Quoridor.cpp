@@ -105,9 +105,9 @@ Quoridor_move *Quoridor_state::get_best_step_move(char player) const {
     return new Quoridor_move((short)(t / 9), (short)(t % 9), player, ' ');
 }
 
-queue<MCTS_move *> *Quoridor_state::generate_all_moves() const {
-    queue<MCTS_move *> *Q = new queue<MCTS_move *>();
-    char p = whose_turn();
+// generate_all_moves as canonical ids (Quoridor.cpp:594-616): steps in reversed candidate order, then anchors row-major
+// with the horizontal wall before the vertical one
+int Quoridor_state::all_move_ids(uint8_t *ids) const {
     uint32_t steps; uint64_t lh, lv;
     if (have_legal_mask) {
         // the move-generation kernel already answered (gpu_set_legal): ids 81..144 = horizontal anchors,
@@ -116,16 +116,34 @@ queue<MCTS_move *> *Quoridor_state::generate_all_moves() const {
         lh = (legal_mask[1] >> 17) | (legal_mask[2] << 47);
         lv = (legal_mask[2] >> 17) | (legal_mask[3] << 47);
     } else q_legal_parts(s, steps, lh, lv, nullptr);
-    // generate_all_moves order (Quoridor.cpp:594-616): steps in reversed candidate order, then anchors
-    // row-major with the horizontal wall before the vertical one
+    int n = 0;
     for (int i = 11; i >= 0; i--)
-        if ((steps >> i) & 1u) Q->push(Quoridor_move::from_canonical_id(q_move_to_id(s.cell[s.turn] + q_step_delta(i)), p));
-    for (int a = 0; a < 64; a++) {
-        if ((lh >> a) & 1ull) Q->push(Quoridor_move::from_canonical_id(q_move_to_id(128 + 2 * a), p));
-        if ((lv >> a) & 1ull) Q->push(Quoridor_move::from_canonical_id(q_move_to_id(128 + 2 * a + 1), p));
+        if ((steps >> i) & 1u) ids[n++] = (uint8_t)(s.cell[s.turn] + q_step_delta(i));
+    for (uint64_t any = lh | lv; any; any &= any - 1) {              // anchors that have at least one legal wall, ascending
+        const int a = __builtin_ctzll(any);
+        if ((lh >> a) & 1ull) ids[n++] = (uint8_t)(81 + a);
+        if ((lv >> a) & 1ull) ids[n++] = (uint8_t)(145 + a);
     }
+    return n;
+}
+
+queue<MCTS_move *> *Quoridor_state::generate_all_moves() const {
+    queue<MCTS_move *> *Q = new queue<MCTS_move *>();
+    uint8_t ids[MCTSB_Q_NUM_MOVES];
+    const int n = all_move_ids(ids);
+    const char p = whose_turn();
+    for (int i = 0; i < n; i++) Q->push(Quoridor_move::from_canonical_id(ids[i], p));
     return Q;
 }
+
+bool Quoridor_state::actions_to_try_ids(std::vector<uint8_t> &ids) const {
+    ids.resize(MCTSB_Q_NUM_MOVES);
+    const int n = good_moves_only ? q_good_moves(s, ids.data(), nullptr) : all_move_ids(ids.data());
+    ids.resize((size_t)n);
+    return true;
+}
+
+MCTS_move *Quoridor_state::move_of_id(int id) const { return Quoridor_move::from_canonical_id(id, whose_turn()); }
 
 // generate_good_moves, Quoridor.cpp:518-592: the shared rule code does the work (q_good_moves)
 queue<MCTS_move *> *Quoridor_state::generate_good_moves() const {

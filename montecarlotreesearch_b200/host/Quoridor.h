@@ -45,6 +45,7 @@ public:
     vector<MCTS_move *> get_legal_step_moves2(char p) const;        // forward candidate order  (Quoridor.cpp:457-474)
     Quoridor_move *get_best_step_move(char player) const;           // Quoridor.cpp:476-497
     queue<MCTS_move *> *generate_all_moves() const;                 // Quoridor.cpp:594-616
+    int all_move_ids(uint8_t *ids) const;                           // the same list as canonical ids (room for 209)
     queue<MCTS_move *> *generate_good_moves() const;                // Quoridor.cpp:518-592
     // which of the two actions_to_try() returns; inherited by every next_state (the reference chooses at compile time)
     void set_good_moves_only(bool on) { good_moves_only = on; have_legal_mask = false; }
@@ -64,6 +65,8 @@ public:
     int gpu_policy_id() const override { return rollout_policy; }
     bool gpu_pack(void *dst) const override;
     void gpu_set_legal(const uint64_t *mask4) override;
+    bool actions_to_try_ids(std::vector<uint8_t> &ids) const override;      // canonical move ids, actions_to_try() order
+    MCTS_move *move_of_id(int id) const override;
     MCTS_state *next_state_of_listed_move(const MCTS_move *move) const override;
 };
 

@@ -20,17 +20,25 @@ void mcts_set_verbose(bool on) { g_verbose = on; }
 // nodes: they are played out once and never selected again) never pays for move generation.
 MCTS_node::MCTS_node(MCTS_node *parent, MCTS_state *state, const MCTS_move *move, MCTS_tree *tree)
     : terminal(false), size(0), number_of_simulations(0), score(0.0), state(state), move(move),
-      children(new vector<MCTS_node *>()), index_in_parent(0), parent(parent), untried_actions(NULL), tree(tree), virtual_visits(0) {
+      children(new vector<MCTS_node *>()), index_in_parent(0), parent(parent), untried_actions(NULL), next_untried_id(0), listed(false), listed_as_ids(false), tree(tree), virtual_visits(0) {
     terminal = state->is_terminal();
+    p1_to_move = state->player1_turn();
 }
 
-queue<MCTS_move *> *MCTS_node::actions() const {
-    if (untried_actions == NULL) {
-        untried_actions = state->actions_to_try();
-        children->reserve(STARTING_NUMBER_OF_CHILDREN);
-        const_cast<MCTS_node *>(this)->child_stats.reserve(STARTING_NUMBER_OF_CHILDREN);
-    }
-    return untried_actions;
+void MCTS_node::list_actions() const {
+    if (listed) return;
+    listed = true;
+    listed_as_ids = state->actions_to_try_ids(untried_ids);
+    if (!listed_as_ids) untried_actions = state->actions_to_try();
+    children->reserve(STARTING_NUMBER_OF_CHILDREN);
+    MCTS_node *self = const_cast<MCTS_node *>(this);
+    self->child_stats.reserve(STARTING_NUMBER_OF_CHILDREN);
+    self->rank_exploit.reserve(STARTING_NUMBER_OF_CHILDREN); self->rank_inv_sqrt.reserve(STARTING_NUMBER_OF_CHILDREN);
+}
+
+bool MCTS_node::no_untried_action() const {
+    list_actions();
+    return listed_as_ids ? next_untried_id >= untried_ids.size() : untried_actions->empty();
 }
 
 MCTS_node::~MCTS_node() {
@@ -44,7 +52,7 @@ MCTS_node::~MCTS_node() {
     }
 }
 
-bool MCTS_node::is_fully_expanded() const { return terminal || actions()->empty(); }   // mcts.cpp:92-94
+bool MCTS_node::is_fully_expanded() const { return terminal || no_untried_action(); }   // mcts.cpp:92-94
 bool MCTS_node::is_terminal() const { return terminal; }
 unsigned int MCTS_node::get_size() const { return size; }
 const MCTS_move *MCTS_node::get_move() const { return move; }
@@ -52,14 +60,16 @@ const MCTS_state *MCTS_node::get_current_state() const { return state; }
 
 // Expansion only: pop the FRONT of the FIFO (children appear in actions_to_try order, mcts.cpp:46-54)
 MCTS_node *MCTS_node::expand_no_rollout() {
-    if (terminal || actions()->empty()) return NULL;
-    MCTS_move *next_move = untried_actions->front();
-    untried_actions->pop();
+    if (terminal || no_untried_action()) return NULL;
+    MCTS_move *next_move;
+    if (listed_as_ids) next_move = state->move_of_id(untried_ids[next_untried_id++]);
+    else { next_move = untried_actions->front(); untried_actions->pop(); }
     MCTS_state *next = state->next_state_of_listed_move(next_move);    // the move comes from this state's own list
     MCTS_node *child = new MCTS_node(this, next, next_move, tree);
     child->index_in_parent = (uint32_t)children->size();
     children->push_back(child);
     child_stats.push_back(MCTS_child_stat{0.0, 0.0, 0.0});
+    rank_exploit.push_back(0.0f); rank_inv_sqrt.push_back(0.0f);
     return child;
 }
 
@@ -97,18 +107,29 @@ void MCTS_node::rollout() {
     backpropagate(sum, R);
 }
 
+// the two numbers the ranking pass of select_best_child keeps per child (float: the pass only has to find the
+// children that CAN be the maximum)
+static inline void rank_terms(const MCTS_child_stat &c, bool p1, float &exploit, float &inv_sqrt) {
+    const double s = c.score + (p1 ? 0.0 : 1.0) * c.virtual_visits;
+    exploit = (float)((p1 ? 0.0 : 1.0) + (p1 ? 1.0 : -1.0) * (s / c.visits));
+    inv_sqrt = (float)(1.0 / sqrt(c.visits));
+}
+
 void MCTS_node::mirror_to_parent() {
     if (parent == NULL) return;
     MCTS_child_stat &c = parent->child_stats[index_in_parent];
     c.score = score; c.visits = (double)(number_of_simulations + virtual_visits); c.virtual_visits = (double)virtual_visits;
+    rank_terms(c, parent->p1_to_move, parent->rank_exploit[index_in_parent], parent->rank_inv_sqrt[index_in_parent]);
 }
 
 void MCTS_node::rebuild_child_stats() {
     child_stats.resize(children->size());
+    rank_exploit.resize(children->size()); rank_inv_sqrt.resize(children->size());
     for (size_t i = 0; i < children->size(); i++) {
         MCTS_node *c = children->at(i);
         c->index_in_parent = (uint32_t)i;
         child_stats[i] = MCTS_child_stat{c->score, (double)(c->number_of_simulations + c->virtual_visits), (double)c->virtual_visits};
+        rank_terms(child_stats[i], p1_to_move, rank_exploit[i], rank_inv_sqrt[i]);
     }
 }
 
@@ -133,39 +154,44 @@ void MCTS_node::add_virtual(int64_t n) {
 // maximum wins; c <= 0 means pure win rate.  Simulations still in flight (virtual_visits) count as
 // losses for the side choosing here — zero unless leaves_per_flush > 1.  Reads the parent's own array of
 // child statistics, never the children.
+//
+// The reference's expression costs two divisions and a square root per child; a Quoridor node has ~131 children and
+// a selection passes three such nodes, each with its statistics in a different corner of memory.  Here a first pass
+// ranks the children with one multiply-add each over two dense float arrays (exploit + c*sqrt(log N) * n^-1/2: the
+// reference's value up to ~1e-6), and only the children within 1e-5 of the best — almost always one — are
+// evaluated with the reference's own double-precision expression, in index order.  Every child whose exact value
+// could be the maximum is in that set, so the first strict maximum is the reference's.
 __attribute__((target_clones("avx2", "default")))
 MCTS_node *MCTS_node::select_best_child(double c) const {
     if (children->empty()) return NULL;
     if (children->size() == 1) return children->at(0);
-    double best = -1;
-    size_t argmax = children->size();
-    const bool p1 = state->player1_turn();
+    const bool p1 = p1_to_move;
     const double n_parent = (double)(number_of_simulations + virtual_visits);
     const double log_parent = c > 0 ? log(n_parent) : 0.0;      // the same value for every child (mcts.cpp:121 computes it per child)
     const MCTS_child_stat *cs = child_stats.data();
     const size_t e = children->size();
-    // pass 1: every child's value, the reference's expression term by term (IEEE division and square root give
-    // the same bits in vector and scalar form, so the compiler may run this loop four children at a time)
-    static thread_local vector<double> value;
-    value.resize(e);
-    double *v = value.data();
     const double virt_as_loss = p1 ? 0.0 : 1.0, sign = p1 ? 1.0 : -1.0, base = p1 ? 0.0 : 1.0;
-    if (c > 0) {
-        for (size_t i = 0; i < e; i++) {
-            const double n = cs[i].visits;
-            const double s = cs[i].score + virt_as_loss * cs[i].virtual_visits;
-            v[i] = (base + sign * (s / n)) + c * sqrt(log_parent / n);
-        }
-    } else {
-        for (size_t i = 0; i < e; i++) {
-            const double n = cs[i].visits;
-            const double s = cs[i].score + virt_as_loss * cs[i].virtual_visits;
-            v[i] = base + sign * (s / n);
-        }
+    // pass 1: the maximum of the approximate values
+    const float coef = c > 0 ? (float)(c * sqrt(log_parent)) : 0.0f;
+    const float *re = rank_exploit.data(), *ri = rank_inv_sqrt.data();
+    float amax = -1.0f;
+    for (size_t i = 0; i < e; i++) {
+        const float a = re[i] + coef * ri[i];
+        amax = a > amax ? a : amax;
     }
-    // pass 2: first strict maximum (mcts.cpp:123)
-    for (size_t i = 0; i < e; i++) if (v[i] > best) { best = v[i]; argmax = i; }
-    return argmax < children->size() ? children->at(argmax) : NULL;
+    double best = -1;
+    size_t argmax = e;
+    const bool finite = amax - amax == 0.0f;                     // false when a child has no visit yet (n = 0): evaluate everybody
+    const float threshold = finite ? amax - 1e-5f * (1.0f + fabsf(amax)) : 0.0f;
+    // pass 2: the reference's expression, term by term, for the children that can be the maximum
+    for (size_t i = 0; i < e; i++) {
+        if (finite && !(re[i] + coef * ri[i] >= threshold)) continue;
+        const double n = cs[i].visits;
+        const double s = cs[i].score + virt_as_loss * cs[i].virtual_visits;
+        const double exact = c > 0 ? (base + sign * (s / n)) + c * sqrt(log_parent / n) : base + sign * (s / n);
+        if (exact > best) { best = exact; argmax = i; }
+    }
+    return argmax < e ? children->at(argmax) : NULL;
 }
 
 // reference mcts.cpp:132-157
@@ -176,7 +202,7 @@ MCTS_node *MCTS_node::advance_tree(const MCTS_move *m) {
         else delete child;
     }
     children->clear();
-    child_stats.clear();
+    child_stats.clear(); rank_exploit.clear(); rank_inv_sqrt.clear();
     if (next == NULL) {
         if (g_verbose) cout << "INFO: Didn't find child node. Had to start over." << endl;
         next = new MCTS_node(NULL, state->next_state(m), NULL, tree);
@@ -255,7 +281,7 @@ void MCTS_tree::apply_legal_masks(const vector<MCTS_node *> &leaves, size_t firs
     if (legal == NULL) return;
     for (size_t k = 0; k < count; k++) {
         MCTS_node *leaf = leaves[first + k];
-        if (leaf->untried_actions == NULL && !leaf->terminal) leaf->state->gpu_set_legal(legal + 4 * k);
+        if (!leaf->listed && !leaf->terminal) leaf->state->gpu_set_legal(legal + 4 * k);
     }
 }
 

@@ -60,13 +60,22 @@ class MCTS_node {
     const MCTS_move *move;
     vector<MCTS_node *> *children;
     vector<MCTS_child_stat> child_stats;   // child_stats[i] mirrors children->at(i)
+    // what the ranking pass of select_best_child reads, 8 bytes per child in two dense float arrays (a Quoridor node
+    // has ~131 children: 1 KB instead of the 5 KB of pointers + statistics): the exploitation term as the side
+    // choosing here sees it, and n^-1/2; refreshed whenever the child's statistics change
+    vector<float> rank_exploit, rank_inv_sqrt;
+    bool p1_to_move;                       // state->player1_turn(), asked once
     uint32_t index_in_parent;
     MCTS_node *parent;
-    mutable queue<MCTS_move *> *untried_actions;   // generated on first use (actions())
+    // the moves not tried yet, generated on first use: as the reference's queue of moves, or — when the game offers
+    // actions_to_try_ids — as one byte per move with a cursor (a move object is then only made for the move expanded)
+    mutable queue<MCTS_move *> *untried_actions;
+    mutable vector<uint8_t> untried_ids; mutable uint32_t next_untried_id; mutable bool listed, listed_as_ids;
     MCTS_tree *tree;                       // owner (batching parameters, backend, rollout ids); may be NULL
     uint64_t virtual_visits;               // pending simulations counted as losses while a flush is in flight
     void backpropagate(double w, uint64_t n);
-    queue<MCTS_move *> *actions() const;
+    void list_actions() const;
+    bool no_untried_action() const;
     void add_virtual(int64_t n);
     void mirror_to_parent();
     void rebuild_child_stats();

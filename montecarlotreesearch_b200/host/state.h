@@ -9,6 +9,7 @@
 #include <iostream>
 #include <queue>
 #include <stdexcept>
+#include <vector>
 #include <string>
 
 using namespace std;   // the reference header does this and game code written against it relies on it
@@ -39,6 +40,11 @@ public:
     virtual int gpu_game_id() const { return -1; }
     virtual int gpu_policy_id() const { return 0; }
     virtual bool gpu_pack(void *dst) const { (void)dst; return false; }
+    // Optional compact form of actions_to_try(): the same moves in the same order as small integers of the game's own
+    // choosing.  A node then keeps ~130 bytes instead of ~130 heap-allocated moves, and materialises a move
+    // (move_of_id) only when it expands it.  Return false if the game does not offer it.
+    virtual bool actions_to_try_ids(std::vector<uint8_t> &ids) const { (void)ids; return false; }
+    virtual MCTS_move *move_of_id(int id) const { (void)id; return NULL; }
     // The legal-move mask of this position as the backend's move-generation kernel computed it (4 words,
     // canonical move ids): a state that keeps it answers its next actions_to_try() from the mask instead of
     // generating the moves on the CPU.  Same list, same order.
