@@ -159,7 +159,13 @@ __device__ __forceinline__ uint32_t walk_moves_from(const uint32_t *col, int c) 
 // A finished rollout is not written out, and its lane not refilled, at once: both are branches the whole warp
 // would walk through for one lane (unpack + table: several hundred instructions, a fifth of a rollout's own walk
 // when paid per lane).  Finished lanes wait until kWalkBatch of them can be served together.
-static constexpr int kWalkBatch = 8;
+#ifndef MCTSB_WALK_BATCH
+#define MCTSB_WALK_BATCH 8
+#endif
+#ifndef MCTSB_WALK_BLOCKS_PER_SM
+#define MCTSB_WALK_BLOCKS_PER_SM 16
+#endif
+static constexpr int kWalkBatch = MCTSB_WALK_BATCH;
 
 template <bool REPLAY>
 __global__ void __launch_bounds__(kThreads) quoridor_uni_walk_kernel(RolloutParams p, unsigned long long *work_counter) {
@@ -312,8 +318,8 @@ cudaError_t launch_quoridor_uni_walk(const RolloutParams &p, bool replay, unsign
     if (p.n_rollouts == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned long long), st);
     if (e != cudaSuccess) return e;
-    // persistent grid: up to 16 blocks of 128 threads per SM, never more threads than rollouts
-    unsigned long long want = (p.n_rollouts + kThreads - 1) / kThreads, cap = (unsigned long long)sms * 16ull;
+    // persistent grid: up to MCTSB_WALK_BLOCKS_PER_SM blocks of 128 threads per SM, never more threads than rollouts
+    unsigned long long want = (p.n_rollouts + kThreads - 1) / kThreads, cap = (unsigned long long)sms * (unsigned long long)MCTSB_WALK_BLOCKS_PER_SM;
     unsigned blocks = (unsigned)(want < cap ? want : cap);
     if (replay) quoridor_uni_walk_kernel<true><<<blocks, kThreads, 0, st>>>(p, work_counter);
     else        quoridor_uni_walk_kernel<false><<<blocks, kThreads, 0, st>>>(p, work_counter);

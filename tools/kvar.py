@@ -3,7 +3,8 @@
 the lockstep kernel of each on the GPU box in one gpurun call.
 
   python tools/kvar.py build name1:-DX=1,-DY name2: ...     (here: nvcc cross-compiles into tools/_var/<name>/)
-  python tools/kvar.py run [rollouts] [workload]             (on the GPU box: every built variant, 4 timed launches)
+  python tools/kvar.py run [rollouts] [workload]             (on the GPU box: every built variant, 4 timed launches;
+                                                              KVAR_POLICY=1 times the UNI path instead of the REF kernel)
 """
 import os, subprocess, sys, json, shutil
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -36,7 +37,7 @@ def run_one(lib, rollouts, workload):
     be.upload_states(m.GAME_QUORIDOR, state)
     ms = []
     for k in range(6):
-        t = be.run_resident(m.GAME_QUORIDOR, m.POLICY_REF, per_leaf, k * rollouts, timed=True)
+        t = be.run_resident(m.GAME_QUORIDOR, int(os.environ.get("KVAR_POLICY", "0")), per_leaf, k * rollouts, timed=True)
         score, sums = be.wait()
         ms.append(t)
     c = be.counters()
