@@ -19,6 +19,7 @@ class EmuLib:
         L.emu_q_best_step.argtypes = [vp]
         L.emu_q_play.argtypes = [vp, C.c_int, vp]
         L.emu_q_cut_check.argtypes = [vp, C.c_int, vp]
+        L.emu_q_detour_check.argtypes = [vp, vp]
         L.emu_q_rollout_streams.argtypes = [vp, C.c_int, C.c_int, vp, C.c_uint32, C.c_uint32, vp, vp, vp]
         L.emu_q_rollout_philox.argtypes = [vp, C.c_int, C.c_uint64, C.c_uint64, C.c_int, vp, vp, vp]
         L.emu_t_rollout_philox.argtypes = [C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint64, C.c_int, vp]
@@ -49,6 +50,15 @@ class EmuLib:
         a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
         k = 2 * (wall_id - 81) if wall_id < 145 else 2 * (wall_id - 145) + 1
         return self.lib.emu_q_sp_with_wall(a.ctypes.data, int(black), k)
+
+    def q_detour_check(self, states):
+        """(violations, cheap-legal walls, walls settled without a search, cheap-legal but illegal walls) over `states`"""
+        a = np.ascontiguousarray(states, dtype=QSTATE_DTYPE).reshape(-1)
+        out = np.zeros(3, dtype=np.int64)
+        bad = 0
+        for i in range(a.size):
+            bad += self.lib.emu_q_detour_check(a[i:i + 1].ctypes.data, out.ctypes.data)
+        return bad, int(out[0]), int(out[1]), int(out[2])
 
     def q_cut_check(self, states, player):
         """(violations, candidates, candidates the pruning masks keep) summed over `states`"""

@@ -57,6 +57,25 @@ int emu_q_cut_check(const mctsb_qstate *p, int player, int64_t *out2) {
     return bad;
 }
 
+// The search-free legality rule: every cheap-legal wall inside q_detour_safe_masks must keep both paths (and the
+// one-wall form must agree with the mask form).  Returns the number of violations; out3 = {cheap-legal walls, walls
+// the rule settles, cheap-legal walls that are in fact illegal}.
+int emu_q_detour_check(const mctsb_qstate *p, int64_t *out3) {
+    QState s; q_unpack(s, *p);
+    uint64_t ch, cv, sh, sv; q_cheap_wall_masks(s, ch, cv); q_detour_safe_masks(s, sh, sv);
+    int bad = 0;
+    for (int k = 0; k < 128; k++) {
+        const bool safe = q_mask_has(sh, sv, k);
+        if (safe != q_detour_safe_one(s.openS, s.openE, k)) bad++;
+        if (!q_mask_has(ch, cv, k)) continue;
+        out3[0]++;
+        const bool legal = q_wall_keeps_paths(s, k, nullptr);
+        if (!legal) out3[2]++;
+        if (safe) { out3[1]++; if (!legal) bad++; }
+    }
+    return bad;
+}
+
 int emu_q_rollout_streams(const mctsb_qstate *states, int policy, int n, const uint32_t *streams, uint32_t len,
                           uint32_t stride, mctsb_outcome *out, mctsb_qstate *finals, uint64_t *work3) {
     LocalLayers pool;

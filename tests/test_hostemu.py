@@ -54,6 +54,18 @@ def test_pruning_masks_are_exact_on_corpus(emu, corpus):
         assert n > 100000 and kept < 0.45 * n        # the masks prune: most walls need no search
 
 
+def test_detour_rule_never_passes_an_illegal_wall(emu, corpus):
+    """q_detour_safe_masks (legal without a search: at most one of the wall's three lattice points touches anything):
+    on the whole corpus plus dense late-game positions every wall it settles keeps both paths, the one-wall form agrees
+    with the mask form, and it settles most candidates."""
+    from tests.util import serpentine_state
+    bad, cheap, settled, illegal = emu.q_detour_check(corpus)
+    assert bad == 0 and illegal > 0
+    assert settled > 0.6 * cheap, (settled, cheap)
+    bad, cheap, settled, illegal = emu.q_detour_check(np.array([serpentine_state(turn=0), serpentine_state(rows=(0, 2, 4, 7), turn=1)]))
+    assert bad == 0 and illegal > 0 and settled < cheap
+
+
 def test_core_replay_vs_golden(emu, corpus):
     g = golden("golden_q_replay.npz")
     seed = int(g["seed"])
