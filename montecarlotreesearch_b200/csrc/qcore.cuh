@@ -567,6 +567,38 @@ MC_HD bool q_detour_safe_one(B81 oS, B81 oE, int k) {
     return (b81_test(oE, c) && b81_test(oE, c + 9) && (left || right)) || (left && right);
 }
 
+// ------------------------------------------------------------------------------------------------
+// Connectivity only (legality of a wall, not its effect on the distance): ONE path is enough.  A wall that covers no
+// edge of some fixed pawn-to-goal path leaves that path, hence the pawn's connection, intact.  The walk picks one
+// predecessor per layer (south, north, east, west in that order) — a single bit moves down the layers, ~40
+// instructions per layer instead of the ~170 of q_trace_step's all-shortest-paths bookkeeping — and the walls over
+// its sp edges (two anchors per edge) are the only ones that can close this pawn in.
+// ------------------------------------------------------------------------------------------------
+struct QPathWalk { B81 cur, es, ee; };       // the walker, the south-type and east-type edges it used (stored at the upper / left cell)
+
+MC_HD void q_path_init(QPathWalk &w, B81 pawn) { w.cur = pawn; w.es = w.ee = b81(0u, 0u, 0u); }
+
+MC_HD void q_path_step(QPathWalk &w, B81 L, B81 oS, B81 oE) {
+    const B81 sS = w.cur & oS & shr<9>(L);           // step south: edge stored at cur
+    const B81 tN = shr<9>(w.cur) & oS & L;           // step north to cur-9: edge stored there
+    const B81 sE = w.cur & oE & shr<1>(L);
+    const B81 tW = shr<1>(w.cur) & oE & L;
+    const uint32_t hS = b81_any(sS) ? 0xffffffffu : 0u, hN = b81_any(tN) ? ~hS : 0u;
+    const uint32_t vert = hS | hN, hE = b81_any(sE) ? ~vert : 0u, hW = ~(vert | hE);
+    const B81 s9 = shl<9>(sS), e1 = shl<1>(sE);
+    w.es = b81(w.es.a | (sS.a & hS) | (tN.a & hN), w.es.b | (sS.b & hS) | (tN.b & hN), w.es.c | (sS.c & hS) | (tN.c & hN));
+    w.ee = b81(w.ee.a | (sE.a & hE) | (tW.a & hW), w.ee.b | (sE.b & hE) | (tW.b & hW), w.ee.c | (sE.c & hE) | (tW.c & hW));
+    w.cur = b81((s9.a & hS) | (tN.a & hN) | (e1.a & hE) | (tW.a & hW), (s9.b & hS) | (tN.b & hN) | (e1.b & hE) | (tW.b & hW),
+                (s9.c & hS) | (tN.c & hN) | (e1.c & hE) | (tW.c & hW));
+}
+
+// anchors whose wall covers an edge of the walked path: an edge stored at cell c lies under the horizontal (right of the
+// vertical) walls anchored at c and at c-1 (c-9)
+MC_HD void q_path_to_anchors(const QPathWalk &w, uint64_t &cut_h, uint64_t &cut_v) {
+    cut_h = b81_to_anchors(w.es | shr<1>(w.es));
+    cut_v = b81_to_anchors(w.ee | shr<9>(w.ee));
+}
+
 struct QCut { uint64_t h, v; int sp; };    // anchors whose wall may change sp(q) (must be measured), and sp(q)
     // anchors whose wall cuts a shortest-path edge, and sp(q)
 
@@ -606,6 +638,39 @@ MC_HD QCut q_cut_masks(const QState &s, int player, Layers &ls, QWork *wk) {
     }
     // 3. edges -> wall anchors
     q_trace_to_anchors(t, out.h, out.v);
+    return out;
+}
+
+// the same with the one-path walk: anchors whose wall may close `player` in (every other wall leaves the walked path)
+template <class Layers>
+MC_HD QCut q_block_masks(const QState &s, int player, Layers &ls, QWork *wk) {
+    QCut out;
+    const B81 goal = player ? b81(MCTSB_GOAL_B_A, 0u, 0u) : b81(0u, 0u, MCTSB_GOAL_W_C);
+    const B81 pawn = b81_bit(s.cell[player]);
+    const B81 oS = s.openS, oE = s.openE;
+    if (wk) wk->flood_queries++;
+    const QFloodMasks fm = q_flood_masks(oS, oE);
+    B81 reached = goal;
+    int d = 0;
+    bool found = b81_any(pawn & goal), dead = false;
+    while (!found && !dead) {
+        B81 grown = q_flood_step(reached, fm);
+        B81 layer = andn(grown, reached);
+        if (wk) wk->flood_steps++;
+        d++;
+        if (!b81_any(layer) || d >= MCTSB_MAX_LAYERS) { dead = true; break; }
+        ls.put(d, layer);
+        reached = grown;
+        found = b81_any(layer & pawn);
+    }
+    if (dead) { out.h = out.v = ~0ull; out.sp = -1; return out; }      // walled off or too deep to store: every wall is measured
+    out.sp = d;
+    QPathWalk w; q_path_init(w, pawn);
+    for (int k = d - 1; k >= 0; k--) {
+        q_path_step(w, k == 0 ? goal : ls.get(k), oS, oE);
+        if (wk) wk->flood_steps++;
+    }
+    q_path_to_anchors(w, out.h, out.v);
     return out;
 }
 
@@ -795,7 +860,7 @@ MC_HD void q_legal_parts(const QState &s, uint32_t &steps, uint64_t &legal_h, ui
     uint64_t safe_h, safe_v;
     q_detour_safe_masks(s, safe_h, safe_v);
     if (((lh & ~safe_h) | (lv & ~safe_v)) == 0ull) return;      // every candidate has its detour: nothing to search
-    const QCut cw = q_cut_masks(s, 0, ls, wk), cb = q_cut_masks(s, 1, ls, wk);
+    const QCut cw = q_block_masks(s, 0, ls, wk), cb = q_block_masks(s, 1, ls, wk);
     uint64_t th = lh & (cw.h | cb.h) & ~safe_h, tv = lv & (cw.v | cb.v) & ~safe_v;
     for (int k = q_mask_first(th, tv); k >= 0; q_mask_clear(th, tv, k), k = q_mask_first(th, tv)) {
         bool ok = true;

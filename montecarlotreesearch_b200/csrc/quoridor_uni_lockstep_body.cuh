@@ -10,8 +10,8 @@
 //
 //   phase A (this file): one thread = one rollout, the 32 rollouts of a warp advance ply-synchronously, exactly as
 //     in the REF kernel.  Per ply: walls with an open three-step detour around one end are legal without a search
-//     (q_detour_safe_masks); for the rest, goal-rooted layers + trace for BOTH players give the walls that can change
-//     a shortest path at all (q_trace_*, exact: every other wall leaves both distances finite), the survivors go
+//     (q_detour_safe_masks); for the rest, goal-rooted layers + one path walked back for BOTH players give the walls
+//     that lie over an edge of that path (q_path_*: every other wall leaves the path, hence the connection), the survivors go
 //     to the warp's shared task queue, all 32 lanes flood-fill them, and a wall that closes a pawn in is struck
 //     from its owner's legal set with one shared-memory atomicOr.  Then one draw picks the idx-th legal move.
 //     A rollout whose two players have no wall left is handed over: its position and ply count go to a record
@@ -122,8 +122,8 @@ LS_DEV void uni_lockstep_body(const RolloutParams &p, UniWalk *walk, unsigned lo
         const bool need = (risky_h | risky_v) != 0ull;
         const uint32_t steps = playing ? q_step_mask(s) : 0u;
 
-        // ---- P2: per player, goal-rooted layers until the pawn is reached, then the trace -> walls that may change
-        //      that player's distance.  Every other wall leaves the distance as it is, hence finite.
+        // ---- P2: per player, goal-rooted layers until the pawn is reached, then ONE path walked back down the layers ->
+        //      the walls over its edges.  Every other wall leaves that path, hence the pawn's connection, intact.
         uint64_t cut_h0 = ~0ull, cut_v0 = ~0ull, cut_h1 = ~0ull, cut_v1 = ~0ull;
         {
             const QFloodMasks fm = q_flood_masks(s.openS, s.openE);
@@ -147,18 +147,30 @@ LS_DEV void uni_lockstep_body(const RolloutParams &p, UniWalk *walk, unsigned lo
                 const int sp = need ? (int)da : -1;                // -1: walled off (never in a legal position)
                 if (sp > 0) wk.flood_steps += (uint32_t)sp;
                 const bool tracing = need && sp >= 0 && sp < MCTSB_MAX_LAYERS;
+#if defined(MCTSB_UNI_FULL_TRACE)                            // A/B switch: the REF kernel's all-shortest-paths trace (fewer candidates, 4x the cost per layer)
                 QTrace t; q_trace_init(t, pawn);
+#else
+                QPathWalk t; q_path_init(t, pawn);                  // one path down the layers: only walls over its edges can close this pawn in
+#endif
                 int k = tracing ? sp - 1 : -1;
                 LS_UNROLL1
                 while (LS_ANY(k >= 0)) {
                     if (k >= 0) {
+#if defined(MCTSB_UNI_FULL_TRACE)
                         q_trace_step(t, k == 0 ? goal : ls.get(k), s.openS, s.openE);
+#else
+                        q_path_step(t, k == 0 ? goal : ls.get(k), s.openS, s.openE);
+#endif
                         wk.flood_steps++;
                         k--;
                     }
                 }
                 uint64_t ch = ~0ull, cv = ~0ull;
+#if defined(MCTSB_UNI_FULL_TRACE)
                 if (tracing) q_trace_to_anchors(t, ch, cv);
+#else
+                if (tracing) q_path_to_anchors(t, ch, cv);
+#endif
                 if (pl == 0) { cut_h0 = ch; cut_v0 = cv; } else { cut_h1 = ch; cut_v1 = cv; }
             }
         }

@@ -294,10 +294,16 @@ __global__ void __launch_bounds__(kThreads) quoridor_uni_walk_kernel(RolloutPara
             else { const uint32_t sh = pos & 3u; u = sh == 0 ? buf.x : sh == 1 ? buf.y : sh == 2 ? buf.z : buf.w; }
             pos++;
             if ((pos & 3u) == 0u) block_valid = false;
-            int idx = (int)__umulhi(u, (uint32_t)n);
+            // the idx-th legal step in reversed candidate order = the idx-th HIGHEST set bit = the (n-1-idx)-th lowest:
+            // a pawn never has more than five legal steps, so four predicated "clear the lowest bit" do it without a loop
+            const int skip = n - 1 - (int)__umulhi(u, (uint32_t)n);
+            m = skip > 0 ? m & (m - 1u) : m;
+            m = skip > 1 ? m & (m - 1u) : m;
+            m = skip > 2 ? m & (m - 1u) : m;
+            m = skip > 3 ? m & (m - 1u) : m;
 #pragma unroll 1
-            for (; idx > 0; idx--) m &= ~(1u << (31 - __clz((int)m)));
-            const int target = me + q_step_delta(31 - __clz((int)m));
+            for (int extra = skip - 4; extra > 0; extra--) m &= m - 1u;      // never entered on a 9x9 board; kept for exactness
+            const int target = me + q_step_delta(__ffs((int)m) - 1);
             if (turn) cb = target; else cw = target;
             turn ^= 1; move_counter++;
             plies++;
