@@ -34,7 +34,8 @@ typedef enum {
     MCTSB_ERR_NOT_SUBMITTED = 5, /* wait without a pending submit                                 */
     MCTSB_ERR_BUSY = 6,        /* submit while a previous submit has not been waited for          */
     MCTSB_ERR_OOM = 7,
-    MCTSB_ERR_COMM = 8         /* an NCCL call failed / libnccl.so.2 is not present: multi-GPU exchange only       */
+    MCTSB_ERR_COMM = 8,        /* an NCCL call failed / libnccl.so.2 is not present: multi-GPU exchange only       */
+    MCTSB_ERR_TREE_FULL = 9    /* device-resident tree: node pool exhausted or a selection path deeper than the level buffers */
 } mctsb_status;
 
 /* ---- games and rollout policies ------------------------------------------------------- */
@@ -246,6 +247,51 @@ int mctsb_comm_info(const mctsb_backend *b, int *world, int *rank);
 int mctsb_allreduce_root_stats(mctsb_backend *b, double *stats /* in/out */, int n);
 int mctsb_allreduce_leaf_sums(mctsb_backend *b, mctsb_leaf_sum *sums /* in/out */, int n_leaves);
 int mctsb_allreduce_root_stats_group(mctsb_backend **handles, double **stats, int n_handles, int n);
+
+/* ---- the search tree resident in HBM (tree-parallel selection, virtual loss, batched backprop) ----
+ * Replaces the loop of MCTS_tree::grow_tree (mcts.cpp:182-210) — select (mcts.cpp:161-171), select_best_child
+ * (mcts.cpp:104-130), expand (mcts.cpp:37-55, children in generate_all_moves order, Quoridor.cpp:594-616), rollout
+ * (mcts.cpp:57-81) and backpropagate (mcts.cpp:83-90) — for Quoridor trees whose Simulation phase is batched as
+ * `leaves_per_flush` leaves x `rollouts_per_leaf` playouts: the nodes live in device memory, one launch selects and
+ * expands a whole flush, the rollout kernel reads the leaf positions where they lie, one launch back-propagates.
+ * The host queues launches and never sees a node.  The tree is the host tree's (host/mcts.cpp, same batching) node
+ * for node and double for double: selections are made in the same order with the same virtual losses, UCT ties are
+ * settled by the reference's double expression (ln N from the host's libm), scores are summed in selection order.
+ * Leaf d of a flush draws from Philox streams first_rollout_id + d*rollouts_per_leaf + r, as mctsb_submit numbers them.
+ *   max_nodes: node pool (86 bytes per node; a node reserves ids for all its children when it is first expanded).
+ * Not thread-safe; uses the stream of `b`, which must outlive the tree and must not have a submit pending. */
+typedef struct mctsb_tree mctsb_tree;
+typedef struct mctsb_tree_info {
+    uint64_t root_sims;            /* MCTS_node::number_of_simulations of the root                                */
+    double   root_score;           /* its score                                                                   */
+    uint32_t root_size;            /* MCTS_tree::get_size()                                                       */
+    uint32_t root_children;        /* children expanded so far                                                    */
+    uint32_t nodes_used;           /* node ids handed out (pool fill)                                             */
+    uint32_t deepest_level;        /* deepest selection path of any flush so far                                  */
+    uint32_t exact_evals;          /* selections settled by the double-precision expression                       */
+    uint32_t flags;                /* bit 3: some ln N came from the device's log() instead of the host's table   */
+    uint64_t flushes, rollouts;    /* flushes played, playouts played                                             */
+    float    ms_select, ms_rollout, ms_backprop;   /* CUDA-event time of the three phases, summed over the last mctsb_tree_grow */
+    uint32_t reserved;
+} mctsb_tree_info;
+int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *root, int policy,
+                      uint32_t rollouts_per_leaf, uint32_t max_leaves_per_flush, uint64_t max_nodes, double uct_c);
+int mctsb_tree_destroy(mctsb_tree *t);
+/* `iterations` Selection+Expansion+Simulation+Backpropagation rounds in flushes of `leaves_per_flush` (the last one
+ * may be shorter); returns after the last flush has been back-propagated. */
+int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flush, uint64_t first_rollout_id);
+int mctsb_tree_get_info(mctsb_tree *t, mctsb_tree_info *info);
+/* root children in creation (= actions_to_try) order: canonical move id, simulations, score; returns the count in *n */
+int mctsb_tree_root_children(mctsb_tree *t, int32_t *move_ids, uint64_t *sims, double *scores, int max_children, int *n);
+/* the reference's final choice: select_best_child with c = 0 (mcts.cpp:268-270); -1 when the root has no child */
+int mctsb_tree_best_move(mctsb_tree *t, int32_t *move_id);
+/* advance_tree (mcts.cpp:132-157,260-264): the child that carries the move becomes the root (its subtree is kept);
+ * a move without a child starts a fresh root.  MCTSB_ERR_BAD_ARG for an illegal move. */
+int mctsb_tree_advance(mctsb_tree *t, int32_t move_id);
+int mctsb_tree_root_state(mctsb_tree *t, mctsb_qstate *out);
+/* the whole tree in pre-order (children in creation order), one row per node, at most `cap` rows written; *n = nodes */
+int mctsb_tree_dump(mctsb_tree *t, uint64_t cap, int32_t *depth, int32_t *move_id, uint64_t *sims, double *score,
+                    uint32_t *size, uint32_t *n_children, uint64_t *n);
 
 #ifdef __cplusplus
 }

@@ -39,7 +39,13 @@ EXPORTS = [
     "mctsb_submit_x", "mctsb_wait_x", "mctsb_q_goodmoves",
     "mctsb_comm_unique_id", "mctsb_comm_init_rank", "mctsb_comm_init_all", "mctsb_comm_destroy", "mctsb_comm_info",
     "mctsb_allreduce_root_stats", "mctsb_allreduce_leaf_sums", "mctsb_allreduce_root_stats_group",
+    "mctsb_tree_create", "mctsb_tree_destroy", "mctsb_tree_grow", "mctsb_tree_get_info", "mctsb_tree_root_children",
+    "mctsb_tree_best_move", "mctsb_tree_advance", "mctsb_tree_root_state", "mctsb_tree_dump",
 ]
+TREE_INFO_DTYPE = np.dtype([("root_sims", "<u8"), ("root_score", "<f8"), ("root_size", "<u4"), ("root_children", "<u4"),
+                            ("nodes_used", "<u4"), ("deepest_level", "<u4"), ("exact_evals", "<u4"), ("flags", "<u4"),
+                            ("flushes", "<u8"), ("rollouts", "<u8"), ("ms_select", "<f4"), ("ms_rollout", "<f4"),
+                            ("ms_backprop", "<f4"), ("reserved", "<u4")])
 SUBMIT_LEGAL = 1
 Q_GOOD_MAX = 144
 COMM_ID_BYTES = 128
@@ -105,6 +111,15 @@ def load_library():
     L.mctsb_get_counters.argtypes = [vp, vp]
     L.mctsb_leaf_sum_to_double.restype = C.c_double
     L.mctsb_leaf_sum_to_double.argtypes = [vp]
+    L.mctsb_tree_create.argtypes = [vp, C.POINTER(vp), vp, i32, u32, u32, u64, C.c_double]
+    L.mctsb_tree_destroy.argtypes = [vp]
+    L.mctsb_tree_grow.argtypes = [vp, u32, u32, u64]
+    L.mctsb_tree_get_info.argtypes = [vp, vp]
+    L.mctsb_tree_root_children.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
+    L.mctsb_tree_best_move.argtypes = [vp, C.POINTER(C.c_int32)]
+    L.mctsb_tree_advance.argtypes = [vp, C.c_int32]
+    L.mctsb_tree_root_state.argtypes = [vp, vp]
+    L.mctsb_tree_dump.argtypes = [vp, u64, vp, vp, vp, vp, vp, vp, C.POINTER(u64)]
     return L
 
 
@@ -141,7 +156,7 @@ class RolloutBackend:
     def _ck(self, st):
         if st != 0:
             msg = self.lib.mctsb_strerror(st).decode()
-            if st in (2, 8):
+            if st in (2, 8, 9):
                 msg += " / " + self.lib.mctsb_last_cuda_error(self.handle).decode()
             raise BackendError(st, msg)
 
@@ -303,3 +318,57 @@ def unpack_legal(mask4):
     m = np.asarray(mask4, dtype=np.uint64).reshape(-1, 4)
     bits = np.unpackbits(m.view(np.uint8).reshape(m.shape[0], 32), axis=1, bitorder="little")
     return bits[:, :NUM_MOVES]
+
+
+class DeviceTree:
+    """The search tree resident in HBM (mctsb_tree_*): Selection, Expansion, Simulation and Backpropagation of a
+    Quoridor tree on the device, `leaves_per_flush` leaves x `rollouts_per_leaf` playouts per flush."""
+
+    def __init__(self, backend, root, rollouts_per_leaf, leaves_per_flush, policy=POLICY_REF, max_nodes=1 << 22, c=1.41):
+        self.be, self.lib = backend, backend.lib
+        self.R, self.K = rollouts_per_leaf, leaves_per_flush
+        r = np.ascontiguousarray(root, dtype=QSTATE_DTYPE)
+        self.h = C.c_void_p()
+        backend._ck(self.lib.mctsb_tree_create(backend.handle, C.byref(self.h), r.ctypes.data, policy, rollouts_per_leaf,
+                                               leaves_per_flush, max_nodes, c))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mctsb_tree_destroy(self.h)
+            self.h = None
+
+    def grow(self, iterations, first_rollout_id, leaves_per_flush=None):
+        self.be._ck(self.lib.mctsb_tree_grow(self.h, iterations, leaves_per_flush or self.K, first_rollout_id))
+
+    def info(self):
+        o = np.zeros((), dtype=TREE_INFO_DTYPE)
+        self.be._ck(self.lib.mctsb_tree_get_info(self.h, o.ctypes.data))
+        return {k: o[k].item() for k in TREE_INFO_DTYPE.names}
+
+    def root_children(self, max_children=256):
+        mv, sims, sc = np.zeros(max_children, np.int32), np.zeros(max_children, np.uint64), np.zeros(max_children, np.float64)
+        n = C.c_int(0)
+        self.be._ck(self.lib.mctsb_tree_root_children(self.h, mv.ctypes.data, sims.ctypes.data, sc.ctypes.data, max_children, C.byref(n)))
+        k = min(n.value, max_children)
+        return mv[:k].copy(), sims[:k].copy(), sc[:k].copy()
+
+    def best_move(self):
+        mv = C.c_int32(-1)
+        self.be._ck(self.lib.mctsb_tree_best_move(self.h, C.byref(mv)))
+        return mv.value
+
+    def advance(self, move_id):
+        self.be._ck(self.lib.mctsb_tree_advance(self.h, int(move_id)))
+
+    def root_state(self):
+        s = np.zeros((), dtype=QSTATE_DTYPE)
+        self.be._ck(self.lib.mctsb_tree_root_state(self.h, s.ctypes.data))
+        return s
+
+    def dump(self, cap=1 << 20):
+        a = {"depth": np.zeros(cap, np.int32), "move": np.zeros(cap, np.int32), "sims": np.zeros(cap, np.uint64),
+             "score": np.zeros(cap, np.float64), "size": np.zeros(cap, np.uint32), "n_children": np.zeros(cap, np.uint32)}
+        n = C.c_uint64(0)
+        self.be._ck(self.lib.mctsb_tree_dump(self.h, cap, *[a[k].ctypes.data for k in ("depth", "move", "sims", "score", "size", "n_children")], C.byref(n)))
+        assert n.value <= cap, "tree larger than the dump buffer"
+        return {k: v[:n.value].copy() for k, v in a.items()}

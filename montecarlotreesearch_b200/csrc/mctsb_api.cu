@@ -69,7 +69,10 @@ bool valid_qstates(const mctsb_qstate *s, int n) {
     return true;
 }
 
-int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const RolloutParams &p) {
+}  // namespace
+
+// shared with mctsb_tree.cu (the device-resident tree plays its flushes through the same kernels)
+int mctsb_internal_launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const mctsb::RolloutParams &p) {
     cudaError_t e;
     if (game == MCTSB_GAME_QUORIDOR && policy == MCTSB_POLICY_REF && !b->use_simple_kernel)
         e = launch_quoridor_lockstep(p, replay, b->d_counters + 7, b->stream);
@@ -86,6 +89,12 @@ int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const R
     if (e != cudaSuccess) return fail_cuda(b, e, "rollout kernel launch");
     b->launches++;
     return MCTSB_OK;
+}
+
+namespace {
+
+int launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const RolloutParams &p) {
+    return mctsb_internal_launch_rollouts(b, game, policy, replay, p);
 }
 
 int upload_states(mctsb_backend *b, int game, const void *states, int n) {
@@ -117,6 +126,7 @@ const char *mctsb_strerror(int status) {
         case MCTSB_ERR_BUSY: return "a submitted batch has not been waited for";
         case MCTSB_ERR_COMM: return "multi-GPU exchange failed (NCCL), see mctsb_last_cuda_error";
         case MCTSB_ERR_OOM: return "out of device or pinned memory";
+        case MCTSB_ERR_TREE_FULL: return "device-resident tree: node pool exhausted or selection path too deep (see mctsb_last_cuda_error)";
         default: return "unknown status";
     }
 }

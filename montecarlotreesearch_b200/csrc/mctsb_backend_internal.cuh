@@ -38,3 +38,7 @@ struct mctsb_backend {
     char cuda_err[256];
 };
 
+
+namespace mctsb { struct RolloutParams; }
+// mctsb_api.cu: picks the kernel(s) of (game, policy) and launches them on the handle's stream
+int mctsb_internal_launch_rollouts(mctsb_backend *b, int game, int policy, bool replay, const mctsb::RolloutParams &p);

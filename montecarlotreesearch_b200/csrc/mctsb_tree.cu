@@ -1,0 +1,439 @@
+// mctsb_tree.cu — the search tree resident in HBM behind the C ABI (include/mctsb.h, mctsb_tree_*): kernels around
+// the warp-level code of tree_body.cuh and the host side that queues them.  Replaces the loop of
+// MCTS_tree::grow_tree (reference mcts/src/mcts.cpp:182-210) for Quoridor trees with batched Simulation.
+//
+// One flush = four launches on the backend's stream, no host synchronisation in between:
+//   tree_select_kernel    cooperative, one CTA per SM: the flush's descents level by level (grid barrier between
+//                         levels), then the leaf positions gathered into the rollout kernel's input
+//   rollout kernel(s)     the production REF / UNI path (mctsb_internal_launch_rollouts)
+//   tree_results_kernel   exact leaf sums -> doubles; leaves created by the flush take their first result
+//   tree_backprop_kernel  one warp per item: results added along the paths in selection order
+#include "tree_body.cuh"
+#include "mctsb_backend_internal.cuh"
+#include <cooperative_groups.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace cg = cooperative_groups;
+using namespace mctsb;
+
+namespace {
+
+constexpr int TREE_THREADS = 128;                  // 4 warps per CTA
+constexpr int TREE_WARPS = TREE_THREADS / 32;
+
+__global__ void __launch_bounds__(TREE_THREADS) tree_select_kernel(TreeCtx t, uint32_t n, mctsb_qstate *leaf_states) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ TreeWarpSmem wsm[TREE_WARPS];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const uint32_t gtid = blockIdx.x * TREE_THREADS + threadIdx.x, gthreads = gridDim.x * TREE_THREADS;
+    const uint32_t warp = blockIdx.x * TREE_WARPS + wib, nwarps = gridDim.x * TREE_WARPS;
+    for (uint32_t d = gtid; d < n; d += gthreads) t.idx[d] = d;               // level 0: every descent starts at the root
+    if (gtid == 0) {
+        TreeItem r; r.node = t.ctl->root; r.start = 0; r.count = n; r.level = 0;
+        t.items[0] = r; t.ctl->n_items = 1;
+    }
+    grid.sync();
+    uint32_t begin = 0, end = 1, level = 0;
+    unsigned long long t0 = 0;
+    if (gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    while (begin < end) {
+        for (uint32_t i = begin + warp; i < end; i += nwarps) tree_select_item(t, t.items[i], lane, wsm[wib]);
+        grid.sync();
+        if (gtid == 0) {
+            unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            t.ctl->level_ns[level < 7 ? level : 7] += t1 - t0; t0 = t1;
+        }
+        begin = end; end = *(volatile uint32_t *)&t.ctl->n_items; level++;
+    }
+    if (gtid == 0 && level > t.ctl->depth_max) t.ctl->depth_max = level;
+    for (uint32_t d = gtid; d < n; d += gthreads)                              // the rollout kernel's input, in selection order
+        ls_store_qstate(leaf_states, d, tr_load_qstate(t.pool.state, (uint32_t)t.leaf_of[d]));
+}
+
+__global__ void __launch_bounds__(TREE_THREADS) tree_results_kernel(TreeCtx t, uint32_t n, const mctsb_leaf_sum *sums, double *w) {
+    const uint32_t d = blockIdx.x * TREE_THREADS + threadIdx.x;
+    if (d >= n) return;
+    w[d] = tr_leaf_sum_to_double(sums[d].lo, sums[d].hi);
+    tree_backprop_created(t, d, w);
+}
+
+__global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, const double *w) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warp = (blockIdx.x * TREE_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * TREE_WARPS;
+    const uint32_t n_items = t.ctl->n_items;
+    for (uint32_t i = warp; i < n_items; i += nwarps) tree_backprop_item(t, t.items[i], lane, w);
+}
+
+int fail(mctsb_backend *b, cudaError_t e, const char *what) {
+    if (b) snprintf(b->cuda_err, sizeof b->cuda_err, "%s: %s", what, cudaGetErrorString(e));
+    return e == cudaErrorMemoryAllocation ? MCTSB_ERR_OOM : MCTSB_ERR_CUDA;
+}
+#define TCK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail(b, e_, #call); } while (0)
+
+}  // namespace
+
+struct mctsb_tree {
+    mctsb_backend *b;
+    int policy;
+    uint32_t R, K; uint64_t pool_cap; double c;
+    TreeCtx ctx;                        // device pointers
+    mctsb_qstate *d_leaf_states; mctsb_leaf_sum *d_sums; double *d_w;
+    double *d_logtab;
+    void *allocs[32]; int n_allocs;
+    int select_blocks;
+    uint64_t flushes, rollouts;
+    float ms[3];
+    cudaEvent_t ev[4];
+};
+
+namespace {
+
+template <class T> int dev_alloc(mctsb_tree *t, T **p, size_t n) {
+    mctsb_backend *b = t->b;
+    TCK(cudaMalloc((void **)p, n * sizeof(T)));
+    t->allocs[t->n_allocs++] = *p;
+    return MCTSB_OK;
+}
+#define TTRY(call) do { int s_ = (call); if (s_ != MCTSB_OK) { mctsb_tree_destroy(t); return s_; } } while (0)
+
+int read_ctl(mctsb_tree *t, TreeCtl *out) {
+    mctsb_backend *b = t->b;
+    TCK(cudaStreamSynchronize(b->stream));
+    TCK(cudaMemcpy(out, t->ctx.ctl, sizeof *out, cudaMemcpyDeviceToHost));
+    return MCTSB_OK;
+}
+
+// a fresh node written from the host (the first root, or a root that advance_tree has to start over)
+int write_node(mctsb_tree *t, uint32_t id, const mctsb_qstate &st) {
+    mctsb_backend *b = t->b;
+    QState s;
+    q_unpack(s, st);
+    const TreePool &P = t->ctx.pool;
+    const double zero = 0.0; const unsigned long long zero64 = 0; const uint32_t zero32 = 0; const int32_t minus1 = -1;
+    const uint16_t zero16 = 0, unlisted = TR_UNLISTED; const uint8_t nomove = 0xff, flags = q_winner(s) ? TR_FLAG_TERMINAL : 0;
+    TCK(cudaMemcpy(P.state + id, &st, sizeof st, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.score + id, &zero, 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.sims + id, &zero64, 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.virt + id, &zero32, 4, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.size + id, &zero32, 4, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.parent + id, &minus1, 4, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.first_child + id, &minus1, 4, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.n_children + id, &zero16, 2, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.n_moves + id, &unlisted, 2, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.move + id, &nomove, 1, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.flags + id, &flags, 1, cudaMemcpyHostToDevice));
+    return MCTSB_OK;
+}
+
+bool valid_root(const mctsb_qstate &p) {
+    if (p.wx > 8 || p.wy > 8 || p.bx > 8 || p.by > 8 || p.wwalls > 10 || p.bwalls > 10 || p.turn > 1 || p.flags != 0) return false;
+    if (p.wx == p.bx && p.wy == p.by) return false;
+    if (p.h_anchor & p.v_anchor) return false;
+    if (p.h_anchor & ((p.h_anchor << 1) & ~0x0101010101010101ull)) return false;
+    if (p.v_anchor & (p.v_anchor << 8)) return false;
+    return true;
+}
+
+struct RootView { TreeCtl ctl; int first, nc; std::vector<uint8_t> move; std::vector<unsigned long long> sims; std::vector<double> score; mctsb_qstate state; };
+
+int read_root(mctsb_tree *t, RootView &v) {
+    mctsb_backend *b = t->b;
+    int s = read_ctl(t, &v.ctl);
+    if (s != MCTSB_OK) return s;
+    const TreePool &P = t->ctx.pool;
+    const int r = v.ctl.root;
+    uint16_t nc = 0;
+    TCK(cudaMemcpy(&v.first, P.first_child + r, 4, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(&nc, P.n_children + r, 2, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(&v.state, P.state + r, sizeof v.state, cudaMemcpyDeviceToHost));
+    v.nc = nc;
+    v.move.resize(nc); v.sims.resize(nc); v.score.resize(nc);
+    if (nc) {
+        TCK(cudaMemcpy(v.move.data(), P.move + v.first, nc, cudaMemcpyDeviceToHost));
+        TCK(cudaMemcpy(v.sims.data(), P.sims + v.first, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+        TCK(cudaMemcpy(v.score.data(), P.score + v.first, (size_t)nc * 8, cudaMemcpyDeviceToHost));
+    }
+    return MCTSB_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *root, int policy,
+                      uint32_t rollouts_per_leaf, uint32_t max_leaves_per_flush, uint64_t max_nodes, double uct_c) {
+    if (!b || !out || !root || rollouts_per_leaf == 0 || max_leaves_per_flush == 0) return MCTSB_ERR_BAD_ARG;
+    *out = nullptr;
+    if (policy != MCTSB_POLICY_REF && policy != MCTSB_POLICY_UNI) return MCTSB_ERR_BAD_ARG;
+    if (max_nodes < 512 || max_nodes > 0x7fffff00ull) return MCTSB_ERR_BAD_ARG;
+    // virtual losses are counted in 32 bits: two flushes' worth of playouts must fit
+    if ((uint64_t)rollouts_per_leaf * max_leaves_per_flush >= (1ull << 30)) return MCTSB_ERR_BAD_ARG;
+    if (!valid_root(*root)) return MCTSB_ERR_BAD_STATE;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    TCK(cudaSetDevice(b->device));
+    mctsb_tree *t = new (std::nothrow) mctsb_tree();
+    if (!t) return MCTSB_ERR_OOM;
+    memset(t, 0, sizeof *t);
+    t->b = b; t->policy = policy; t->R = rollouts_per_leaf; t->K = max_leaves_per_flush; t->pool_cap = max_nodes; t->c = uct_c;
+    TreeCtx &c = t->ctx;
+    const size_t N = (size_t)max_nodes, K = t->K;
+    TTRY(dev_alloc(t, &c.pool.state, N)); TTRY(dev_alloc(t, &c.pool.lh, N)); TTRY(dev_alloc(t, &c.pool.lv, N));
+    TTRY(dev_alloc(t, &c.pool.score, N)); TTRY(dev_alloc(t, &c.pool.sims, N)); TTRY(dev_alloc(t, &c.pool.virt, N));
+    TTRY(dev_alloc(t, &c.pool.size, N)); TTRY(dev_alloc(t, &c.pool.parent, N)); TTRY(dev_alloc(t, &c.pool.first_child, N));
+    TTRY(dev_alloc(t, &c.pool.n_children, N)); TTRY(dev_alloc(t, &c.pool.n_moves, N)); TTRY(dev_alloc(t, &c.pool.move, N));
+    TTRY(dev_alloc(t, &c.pool.flags, N));
+    TTRY(dev_alloc(t, &c.ctl, 1));
+    c.items_cap = (uint32_t)(K * TR_MAX_LEVELS < (1u << 30) ? K * TR_MAX_LEVELS : (1u << 30));
+    TTRY(dev_alloc(t, &c.items, (size_t)c.items_cap));
+    TTRY(dev_alloc(t, &c.idx, K * TR_MAX_LEVELS)); TTRY(dev_alloc(t, &c.choice, K)); TTRY(dev_alloc(t, &c.leaf_of, K)); TTRY(dev_alloc(t, &c.created, K));
+    TTRY(dev_alloc(t, &t->d_leaf_states, K)); TTRY(dev_alloc(t, &t->d_sums, K)); TTRY(dev_alloc(t, &t->d_w, K));
+    c.K = t->K; c.pool_cap = (uint32_t)max_nodes; c.R = t->R; c.c = uct_c;
+    // ln N for every N = m * R a node of this pool can reach, from the host's libm: the exact UCT expression then
+    // sees the doubles the host tree sees.  One entry per iteration the pool can hold.
+    {
+        const size_t n = (size_t)(max_nodes < (1u << 22) ? max_nodes : (1u << 22)) + 2 * K + 16;
+        std::vector<double> tab(n);
+        for (size_t m = 0; m < n; m++) tab[m] = log((double)((unsigned long long)m * t->R));
+        TTRY(dev_alloc(t, &t->d_logtab, n));
+        cudaError_t e = cudaMemcpy(t->d_logtab, tab.data(), n * sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) { int s = fail(b, e, "log table upload"); mctsb_tree_destroy(t); return s; }
+        c.logtab = t->d_logtab; c.logtab_n = (uint32_t)n;
+    }
+    TreeCtl ctl; memset(&ctl, 0, sizeof ctl);
+    ctl.pool_top = 1; ctl.root = 0;
+    cudaError_t e = cudaMemcpy(c.ctl, &ctl, sizeof ctl, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { int s = fail(b, e, "tree control block upload"); mctsb_tree_destroy(t); return s; }
+    TTRY(write_node(t, 0, *root));
+    for (int i = 0; i < 4; i++) {
+        e = cudaEventCreate(&t->ev[i]);
+        if (e != cudaSuccess) { int s = fail(b, e, "cudaEventCreate"); mctsb_tree_destroy(t); return s; }
+    }
+    // the selection kernel synchronises its CTAs between levels: all of them must be resident (cooperative launch)
+    int dev_sms = 0, per_sm = 0, coop = 0;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, b->device);
+    cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_select_kernel, TREE_THREADS, 0);
+    if (!coop || per_sm < 1 || dev_sms < 1) { snprintf(b->cuda_err, sizeof b->cuda_err, "cooperative launch not available"); mctsb_tree_destroy(t); return MCTSB_ERR_CUDA; }
+    t->select_blocks = dev_sms;
+    *out = t;
+    return MCTSB_OK;
+}
+
+int mctsb_tree_destroy(mctsb_tree *t) {
+    if (!t) return MCTSB_OK;
+    cudaSetDevice(t->b->device);
+    cudaStreamSynchronize(t->b->stream);
+    for (int i = 0; i < t->n_allocs; i++) cudaFree(t->allocs[i]);
+    for (int i = 0; i < 4; i++) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    delete t;
+    return MCTSB_OK;
+}
+
+int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flush, uint64_t first_rollout_id) {
+    if (!t || leaves_per_flush == 0 || leaves_per_flush > t->K) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    if (b->pending) return MCTSB_ERR_BUSY;
+    TCK(cudaSetDevice(b->device));
+    b->res_game = -1; b->res_leaves = 0;
+    t->ms[0] = t->ms[1] = t->ms[2] = 0.0f;
+    std::vector<cudaEvent_t> evs;           // per-flush phase marks, read after the last flush
+    const uint32_t n_flushes = (iterations + leaves_per_flush - 1) / leaves_per_flush;
+    const bool timed = n_flushes <= 4096;
+    if (timed) {
+        evs.resize((size_t)n_flushes * 4);
+        for (auto &e : evs) TCK(cudaEventCreate(&e));
+    }
+    uint32_t done = 0, f = 0;
+    int status = MCTSB_OK;
+    while (done < iterations && status == MCTSB_OK) {
+        uint32_t n = iterations - done < leaves_per_flush ? iterations - done : leaves_per_flush;
+        if (timed) cudaEventRecord(evs[4 * f + 0], b->stream);
+        void *args[] = {(void *)&t->ctx, (void *)&n, (void *)&t->d_leaf_states};
+        cudaError_t e = cudaLaunchCooperativeKernel((const void *)tree_select_kernel, dim3(t->select_blocks), dim3(TREE_THREADS), args, 0, b->stream);
+        if (e != cudaSuccess) { status = fail(b, e, "tree select launch"); break; }
+        b->launches++;
+        if (timed) cudaEventRecord(evs[4 * f + 1], b->stream);
+        e = cudaMemsetAsync(t->d_sums, 0, (size_t)n * sizeof(mctsb_leaf_sum), b->stream);
+        if (e != cudaSuccess) { status = fail(b, e, "cudaMemsetAsync"); break; }
+        RolloutParams p; memset(&p, 0, sizeof p);
+        p.states = t->d_leaf_states; p.n_leaves = n; p.rollouts_per_leaf = t->R; p.n_rollouts = (uint64_t)n * t->R;
+        p.seed = b->seed; p.first_rollout_id = first_rollout_id + (uint64_t)done * t->R; p.sums = t->d_sums; p.counters = b->d_counters;
+        status = mctsb_internal_launch_rollouts(b, MCTSB_GAME_QUORIDOR, t->policy, false, p);
+        if (status != MCTSB_OK) break;
+        if (timed) cudaEventRecord(evs[4 * f + 2], b->stream);
+        tree_results_kernel<<<(n + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, b->stream>>>(t->ctx, n, t->d_sums, t->d_w);
+        tree_backprop_kernel<<<t->select_blocks * 2, TREE_THREADS, 0, b->stream>>>(t->ctx, t->d_w);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) { status = fail(b, e, "tree backprop launch"); break; }
+        b->launches += 2;
+        if (timed) cudaEventRecord(evs[4 * f + 3], b->stream);
+        done += n; f++;
+        t->flushes++; t->rollouts += (uint64_t)n * t->R;
+    }
+    cudaError_t e = cudaStreamSynchronize(b->stream);
+    if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
+    if (timed) {
+        if (status == MCTSB_OK)
+            for (uint32_t i = 0; i < f; i++)
+                for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, evs[4 * i + k], evs[4 * i + k + 1]); t->ms[k] += ms; }
+        for (auto &ev : evs) cudaEventDestroy(ev);
+    }
+    if (status != MCTSB_OK) return status;
+    TreeCtl ctl;
+    int s = read_ctl(t, &ctl);
+    if (s != MCTSB_OK) return s;
+    if (ctl.error & (TR_ERR_POOL | TR_ERR_ITEMS | TR_ERR_DEPTH)) {
+        snprintf(b->cuda_err, sizeof b->cuda_err, "device tree: %s%s%s", (ctl.error & TR_ERR_POOL) ? "node pool exhausted " : "",
+                 (ctl.error & TR_ERR_DEPTH) ? "selection path deeper than the level buffers " : "", (ctl.error & TR_ERR_ITEMS) ? "item list full" : "");
+        return MCTSB_ERR_TREE_FULL;
+    }
+    return MCTSB_OK;
+}
+
+int mctsb_tree_get_info(mctsb_tree *t, mctsb_tree_info *info) {
+    if (!t || !info) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    TCK(cudaSetDevice(b->device));
+    TreeCtl ctl;
+    int s = read_ctl(t, &ctl);
+    if (s != MCTSB_OK) return s;
+    memset(info, 0, sizeof *info);
+    const TreePool &P = t->ctx.pool;
+    unsigned long long sims = 0; uint16_t nc = 0;
+    TCK(cudaMemcpy(&sims, P.sims + ctl.root, 8, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(&info->root_score, P.score + ctl.root, 8, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(&info->root_size, P.size + ctl.root, 4, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(&nc, P.n_children + ctl.root, 2, cudaMemcpyDeviceToHost));
+    info->root_sims = sims; info->root_children = nc; info->nodes_used = ctl.pool_top; info->deepest_level = ctl.depth_max;
+    info->exact_evals = ctl.exact_evals; info->flags = ctl.error; info->flushes = t->flushes; info->rollouts = t->rollouts;
+    if (getenv("MCTSB_TREE_DEBUG"))
+        fprintf(stderr, "tree: steps %u (unique or alike %u, same-statistics ties %u, settled by the exact expression %u) | level ms: %.3f %.3f %.3f %.3f %.3f %.3f %.3f %.3f\n", ctl.steps,
+                ctl.steps - ctl.ties_same - ctl.exact_evals, ctl.ties_same, ctl.exact_evals, ctl.level_ns[0] * 1e-6, ctl.level_ns[1] * 1e-6, ctl.level_ns[2] * 1e-6,
+                ctl.level_ns[3] * 1e-6, ctl.level_ns[4] * 1e-6, ctl.level_ns[5] * 1e-6, ctl.level_ns[6] * 1e-6, ctl.level_ns[7] * 1e-6);
+    info->ms_select = t->ms[0]; info->ms_rollout = t->ms[1]; info->ms_backprop = t->ms[2];
+    return MCTSB_OK;
+}
+
+int mctsb_tree_root_children(mctsb_tree *t, int32_t *move_ids, uint64_t *sims, double *scores, int max_children, int *n) {
+    if (!t || !n || max_children < 0) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    TCK(cudaSetDevice(b->device));
+    RootView v;
+    int s = read_root(t, v);
+    if (s != MCTSB_OK) return s;
+    *n = v.nc;
+    for (int i = 0; i < v.nc && i < max_children; i++) {
+        if (move_ids) move_ids[i] = v.move[i];
+        if (sims) sims[i] = v.sims[i];
+        if (scores) scores[i] = v.score[i];
+    }
+    return MCTSB_OK;
+}
+
+int mctsb_tree_best_move(mctsb_tree *t, int32_t *move_id) {
+    if (!t || !move_id) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    TCK(cudaSetDevice(b->device));
+    RootView v;
+    int s = read_root(t, v);
+    if (s != MCTSB_OK) return s;
+    *move_id = -1;
+    if (v.nc == 0) return MCTSB_OK;
+    if (v.nc == 1) { *move_id = v.move[0]; return MCTSB_OK; }
+    // select_best_child(0.0): win rate of the side to move at the root, first strict maximum (mcts.cpp:104-129)
+    const bool p1 = v.state.turn == 0;
+    double best = -1; int arg = -1;
+    for (int i = 0; i < v.nc; i++) {
+        const double exact = d_add(p1 ? 0.0 : 1.0, d_mul(p1 ? 1.0 : -1.0, d_div(v.score[i], (double)v.sims[i])));
+        if (exact > best) { best = exact; arg = i; }
+    }
+    if (arg >= 0) *move_id = v.move[arg];
+    return MCTSB_OK;
+}
+
+int mctsb_tree_advance(mctsb_tree *t, int32_t move_id) {
+    if (!t || move_id < 0 || move_id >= MCTSB_Q_NUM_MOVES) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    TCK(cudaSetDevice(b->device));
+    RootView v;
+    int s = read_root(t, v);
+    if (s != MCTSB_OK) return s;
+    int32_t next = -1;
+    for (int i = 0; i < v.nc; i++) if (v.move[i] == move_id) next = v.first + i;
+    if (next >= 0) {
+        const int32_t minus1 = -1;
+        TCK(cudaMemcpy(t->ctx.pool.parent + next, &minus1, 4, cudaMemcpyHostToDevice));
+    } else {                                              // "Didn't find child node. Had to start over." (mcts.cpp:149-152)
+        QState q;
+        q_unpack(q, v.state);
+        if (!q_legal_move(q, move_id)) return MCTSB_ERR_BAD_ARG;
+        q_play_id(q, move_id);
+        mctsb_qstate st; q_pack(q, st);
+        if ((uint64_t)v.ctl.pool_top + 1 > t->pool_cap) return MCTSB_ERR_TREE_FULL;
+        next = (int32_t)v.ctl.pool_top;
+        s = write_node(t, (uint32_t)next, st);
+        if (s != MCTSB_OK) return s;
+        const uint32_t top = v.ctl.pool_top + 1;
+        TCK(cudaMemcpy(&t->ctx.ctl->pool_top, &top, 4, cudaMemcpyHostToDevice));
+    }
+    TCK(cudaMemcpy(&t->ctx.ctl->root, &next, 4, cudaMemcpyHostToDevice));
+    return MCTSB_OK;
+}
+
+int mctsb_tree_root_state(mctsb_tree *t, mctsb_qstate *out) {
+    if (!t || !out) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    TCK(cudaSetDevice(b->device));
+    TreeCtl ctl;
+    int s = read_ctl(t, &ctl);
+    if (s != MCTSB_OK) return s;
+    TCK(cudaMemcpy(out, t->ctx.pool.state + ctl.root, sizeof *out, cudaMemcpyDeviceToHost));
+    return MCTSB_OK;
+}
+
+int mctsb_tree_dump(mctsb_tree *t, uint64_t cap, int32_t *depth, int32_t *move_id, uint64_t *sims, double *score,
+                    uint32_t *size, uint32_t *n_children, uint64_t *n) {
+    if (!t || !n) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    TCK(cudaSetDevice(b->device));
+    TreeCtl ctl;
+    int s = read_ctl(t, &ctl);
+    if (s != MCTSB_OK) return s;
+    const size_t N = ctl.pool_top;
+    const TreePool &P = t->ctx.pool;
+    std::vector<int32_t> first(N); std::vector<uint16_t> nc(N); std::vector<uint8_t> mv(N);
+    std::vector<unsigned long long> sm(N); std::vector<double> sc(N); std::vector<uint32_t> sz(N);
+    TCK(cudaMemcpy(first.data(), P.first_child, N * 4, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(nc.data(), P.n_children, N * 2, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(mv.data(), P.move, N, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(sm.data(), P.sims, N * 8, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(sc.data(), P.score, N * 8, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(sz.data(), P.size, N * 4, cudaMemcpyDeviceToHost));
+    // iterative pre-order walk, children in creation order
+    struct Frame { int32_t node; int32_t depth; };
+    std::vector<Frame> stack;
+    stack.push_back({ctl.root, 0});
+    uint64_t k = 0;
+    while (!stack.empty()) {
+        const Frame fr = stack.back(); stack.pop_back();
+        if (k < cap) {
+            if (depth) depth[k] = fr.depth;
+            if (move_id) move_id[k] = mv[fr.node] == 0xff ? -1 : mv[fr.node];
+            if (sims) sims[k] = sm[fr.node];
+            if (score) score[k] = sc[fr.node];
+            if (size) size[k] = sz[fr.node];
+            if (n_children) n_children[k] = nc[fr.node];
+        }
+        k++;
+        for (int i = nc[fr.node] - 1; i >= 0; i--) stack.push_back({first[fr.node] + i, fr.depth + 1});
+    }
+    *n = k;
+    return MCTSB_OK;
+}
+
+}  // extern "C"

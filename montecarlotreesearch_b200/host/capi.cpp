@@ -233,6 +233,27 @@ int mcts_host_root_stats(void *hs, double *out4, double *children, int max_child
     return n;
 }
 
+// pre-order walk from the root, children in their current order: one row per node (tests: the device-resident tree
+// of csrc/tree_body.cuh must hold the same nodes with the same statistics)
+static void dump_walk(int game, const MCTS_node *n, int depth, uint64_t cap, uint64_t &k, int32_t *o_depth, int32_t *o_move,
+                      uint64_t *o_sims, double *o_score, uint32_t *o_size, uint32_t *o_nchildren) {
+    if (k < cap) {
+        o_depth[k] = depth; o_move[k] = n->get_move() ? move_index(game, n->get_move()) : -1;
+        o_sims[k] = n->get_number_of_simulations(); o_score[k] = n->get_score(); o_size[k] = n->get_size();
+        o_nchildren[k] = (uint32_t)n->get_children().size();
+    }
+    k++;
+    for (const MCTS_node *c : n->get_children()) dump_walk(game, c, depth + 1, cap, k, o_depth, o_move, o_sims, o_score, o_size, o_nchildren);
+}
+
+uint64_t mcts_host_dump_tree(void *hs, uint64_t cap, int32_t *o_depth, int32_t *o_move, uint64_t *o_sims, double *o_score,
+                             uint32_t *o_size, uint32_t *o_nchildren) {
+    HostSession *h = (HostSession *)hs;
+    uint64_t k = 0;
+    dump_walk(h->game, h->tree->get_root(), 0, cap, k, o_depth, o_move, o_sims, o_score, o_size, o_nchildren);
+    return k;
+}
+
 int mcts_host_best_move(void *hs) {
     HostSession *h = (HostSession *)hs;
     MCTS_node *b = h->tree->select_best_child();

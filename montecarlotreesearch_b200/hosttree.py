@@ -27,6 +27,8 @@ def load():
     L.mcts_host_grow.argtypes = [vp, C.c_int, C.c_double, C.c_char_p, C.c_int]
     L.mcts_host_root_stats.argtypes = [vp, vp, vp, C.c_int]
     L.mcts_host_best_move.argtypes = [vp]
+    L.mcts_host_dump_tree.restype = C.c_uint64
+    L.mcts_host_dump_tree.argtypes = [vp, C.c_uint64, vp, vp, vp, vp, vp, vp]
     L.mcts_host_advance.argtypes = [vp, C.c_int]
     L.mcts_host_current_state.argtypes = [vp, vp]
     L.mcts_host_counters.argtypes = [vp, vp, vp]
@@ -115,6 +117,14 @@ class Session:
 
     def best_move(self):
         return self.lib.mcts_host_best_move(self.h)
+
+    def dump(self, cap=1 << 20):
+        """the whole tree in pre-order: dict of arrays depth, move, sims, score, size, n_children (one row per node)"""
+        a = {"depth": np.zeros(cap, np.int32), "move": np.zeros(cap, np.int32), "sims": np.zeros(cap, np.uint64),
+             "score": np.zeros(cap, np.float64), "size": np.zeros(cap, np.uint32), "n_children": np.zeros(cap, np.uint32)}
+        n = self.lib.mcts_host_dump_tree(self.h, cap, *[a[k].ctypes.data for k in ("depth", "move", "sims", "score", "size", "n_children")])
+        assert n <= cap, "tree larger than the dump buffer"
+        return {k: v[:n].copy() for k, v in a.items()}
 
     def advance(self, move_id):
         return bool(self.lib.mcts_host_advance(self.h, move_id))

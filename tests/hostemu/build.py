@@ -7,7 +7,7 @@ SO = os.path.join(HERE, "_hostemu.so")
 SO32 = os.path.join(HERE, "_hostemu32.so")      # the same with 32-lane warps (simt.h fibers)
 ROOT = os.path.dirname(os.path.dirname(HERE))
 SRC = [os.path.join(HERE, "hostemu.cpp")] + [
-    os.path.join(ROOT, "montecarlotreesearch_b200", "csrc", f) for f in ("qcore.cuh", "ttt_core.cuh", "philox.cuh", "quoridor_lockstep_body.cuh", "quoridor_uni_lockstep_body.cuh", "rollout_kernels.cuh")
+    os.path.join(ROOT, "montecarlotreesearch_b200", "csrc", f) for f in ("qcore.cuh", "ttt_core.cuh", "philox.cuh", "quoridor_lockstep_body.cuh", "quoridor_uni_lockstep_body.cuh", "rollout_kernels.cuh", "tree_body.cuh")
 ] + [os.path.join(ROOT, "include", "mctsb.h")]
 
 

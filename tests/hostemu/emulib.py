@@ -27,6 +27,18 @@ class EmuLib:
         L.emu_t_winner.argtypes = [C.c_uint32, C.c_uint32]
         L.emu_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int]
         L.emu_uni_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp]
+        if warp32:
+            L.emu_tree_create.restype = vp
+            L.emu_tree_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32]
+            L.emu_tree_destroy.argtypes = [vp]
+            L.emu_tree_select.argtypes = [vp, C.c_uint32, vp]
+            L.emu_tree_backprop.argtypes = [vp, vp]
+            L.emu_tree_dump.restype = C.c_uint64
+            L.emu_tree_dump.argtypes = [vp, C.c_uint64] + [vp] * 7
+            L.emu_tree_advance.argtypes = [vp, C.c_int]
+            L.emu_tree_stats.argtypes = [vp, vp]
+            L.emu_leaf_sum_to_double.restype = C.c_double
+            L.emu_leaf_sum_to_double.argtypes = [C.c_uint64, C.c_uint64]
 
     def q_primitives(self, s):
         a = np.ascontiguousarray(s, dtype=QSTATE_DTYPE)
@@ -156,3 +168,45 @@ class EmuLib:
                                        sums.ctypes.data, ctr.ctypes.data, blocks, lanes, C.byref(handed))
         assert rc == 0
         return out, fin, sums, ctr, handed.value
+
+
+class EmuTree:
+    """The device-resident tree (csrc/tree_body.cuh) on emulated 32-lane warps; the playouts of a flush are the caller's."""
+
+    def __init__(self, emu, root, R, K, pool_cap=1 << 18, c=1.41, logtab_n=1 << 16):
+        assert emu.lib.emu_warp_width() == 32
+        self.lib, self.R, self.K = emu.lib, R, K
+        r = np.ascontiguousarray(root, dtype=QSTATE_DTYPE)
+        self.h = self.lib.emu_tree_create(r.ctypes.data, R, K, pool_cap, c, logtab_n)
+
+    def close(self):
+        if self.h:
+            self.lib.emu_tree_destroy(self.h)
+            self.h = None
+
+    def select(self, n):
+        leaves = np.zeros(n, dtype=QSTATE_DTYPE)
+        err = self.lib.emu_tree_select(self.h, n, leaves.ctypes.data)
+        assert err >= 0
+        return leaves, err
+
+    def backprop(self, sums):
+        from oracle.reflib import LEAFSUM_DTYPE
+        s = np.ascontiguousarray(sums, dtype=LEAFSUM_DTYPE)
+        return self.lib.emu_tree_backprop(self.h, s.ctypes.data)
+
+    def advance(self, move_id):
+        return self.lib.emu_tree_advance(self.h, int(move_id)) == 0
+
+    def stats(self):
+        o = np.zeros(4, dtype=np.uint32)
+        self.lib.emu_tree_stats(self.h, o.ctypes.data)
+        return {"pool_top": int(o[0]), "items": int(o[1]), "error": int(o[2]), "exact_evals": int(o[3])}
+
+    def dump(self, cap=1 << 20):
+        a = {"depth": np.zeros(cap, np.int32), "move": np.zeros(cap, np.int32), "sims": np.zeros(cap, np.uint64),
+             "score": np.zeros(cap, np.float64), "size": np.zeros(cap, np.uint32), "n_children": np.zeros(cap, np.uint32),
+             "virt": np.zeros(cap, np.uint32)}
+        n = self.lib.emu_tree_dump(self.h, cap, *[a[k].ctypes.data for k in ("depth", "move", "sims", "score", "size", "n_children", "virt")])
+        assert n <= cap
+        return {k: v[:n].copy() for k, v in a.items()}

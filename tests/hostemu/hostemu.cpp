@@ -9,6 +9,7 @@
 #include "../../montecarlotreesearch_b200/csrc/ttt_core.cuh"
 #include "../../montecarlotreesearch_b200/csrc/quoridor_lockstep_body.cuh"
 #include "../../montecarlotreesearch_b200/csrc/quoridor_uni_lockstep_body.cuh"
+#include "../../montecarlotreesearch_b200/csrc/tree_body.cuh"
 #include <vector>
 #include <string.h>
 using namespace mctsb;
@@ -233,5 +234,119 @@ int emu_uni_lockstep(const mctsb_qstate *states, int n_leaves, uint32_t R, uint6
 }
 
 int emu_warp_width() { return LS_WARP; }
+
+// ---- the device-resident tree (csrc/tree_body.cuh) on emulated 32-lane warps -----------------------------------
+// Selection / Expansion / Backpropagation run exactly as the kernels of csrc/mctsb_tree.cu run them (level by
+// level, one warp per item); the playouts of a flush are the caller's (the test feeds the same results to the
+// host tree and to this one).
+#if defined(MCTSB_EMU_WARP32)
+struct EmuTree {
+    TreeCtx t; TreeCtl ctl;
+    std::vector<mctsb_qstate> state; std::vector<uint64_t> lh, lv; std::vector<double> score; std::vector<unsigned long long> sims;
+    std::vector<uint32_t> virt, size; std::vector<int32_t> parent, first_child; std::vector<uint16_t> n_children, n_moves;
+    std::vector<uint8_t> move, flags;
+    std::vector<TreeItem> items; std::vector<uint32_t> idx; std::vector<uint8_t> choice, created; std::vector<int32_t> leaf_of;
+    std::vector<double> logtab;
+    uint32_t n_last;
+};
+struct EmuTreeLaunch { EmuTree *T; uint32_t begin, end; const double *w; TreeWarpSmem *wsm; };
+static void emu_tree_select_thread(void *a) {
+    EmuTreeLaunch *L = (EmuTreeLaunch *)a;
+    const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
+    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_select_item(L->T->t, L->T->items[i], lane, L->wsm[warp]);
+}
+static void emu_tree_backprop_thread(void *a) {
+    EmuTreeLaunch *L = (EmuTreeLaunch *)a;
+    const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
+    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_backprop_item(L->T->t, L->T->items[i], lane, L->w);
+}
+
+void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t pool_cap, double c, uint32_t logtab_n) {
+    EmuTree *T = new EmuTree();
+    T->state.resize(pool_cap); T->lh.resize(pool_cap); T->lv.resize(pool_cap); T->score.resize(pool_cap); T->sims.resize(pool_cap);
+    T->virt.resize(pool_cap); T->size.resize(pool_cap); T->parent.resize(pool_cap); T->first_child.resize(pool_cap);
+    T->n_children.resize(pool_cap); T->n_moves.resize(pool_cap); T->move.resize(pool_cap); T->flags.resize(pool_cap);
+    T->items.resize((size_t)K * TR_MAX_LEVELS); T->idx.resize((size_t)K * TR_MAX_LEVELS); T->choice.resize(K); T->created.resize(K); T->leaf_of.resize(K);
+    T->logtab.resize(logtab_n);
+    for (uint32_t m = 0; m < logtab_n; m++) T->logtab[m] = log((double)((unsigned long long)m * R));
+    TreeCtx &t = T->t;
+    t.pool.state = T->state.data(); t.pool.lh = T->lh.data(); t.pool.lv = T->lv.data(); t.pool.score = T->score.data(); t.pool.sims = T->sims.data();
+    t.pool.virt = T->virt.data(); t.pool.size = T->size.data(); t.pool.parent = T->parent.data(); t.pool.first_child = T->first_child.data();
+    t.pool.n_children = T->n_children.data(); t.pool.n_moves = T->n_moves.data(); t.pool.move = T->move.data(); t.pool.flags = T->flags.data();
+    t.ctl = &T->ctl; t.items = T->items.data(); t.items_cap = (uint32_t)T->items.size(); t.idx = T->idx.data(); t.choice = T->choice.data();
+    t.leaf_of = T->leaf_of.data(); t.created = T->created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
+    t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
+    memset(&T->ctl, 0, sizeof T->ctl);
+    QState s; q_unpack(s, *root);
+    T->state[0] = *root; T->score[0] = 0; T->sims[0] = 0; T->virt[0] = 0; T->size[0] = 0; T->parent[0] = -1; T->first_child[0] = -1;
+    T->n_children[0] = 0; T->n_moves[0] = TR_UNLISTED; T->move[0] = 0xff; T->flags[0] = q_winner(s) ? TR_FLAG_TERMINAL : 0;
+    T->ctl.pool_top = 1; T->ctl.root = 0; T->n_last = 0;
+    return T;
+}
+void emu_tree_destroy(void *h) { delete (EmuTree *)h; }
+
+// Selection + Expansion of one flush of n descents; leaf_states[d] = position of the leaf descent d ended at
+int emu_tree_select(void *h, uint32_t n, mctsb_qstate *leaf_states) {
+    EmuTree *T = (EmuTree *)h;
+    if (n == 0 || n > T->t.K) return -1;
+    for (uint32_t d = 0; d < n; d++) T->idx[d] = d;
+    TreeItem r; r.node = T->ctl.root; r.start = 0; r.count = n; r.level = 0;
+    T->items[0] = r; T->ctl.n_items = 1;
+    std::vector<TreeWarpSmem> wsm(4);
+    memset(wsm.data(), 0xa5, sizeof(TreeWarpSmem) * 4);
+    uint32_t begin = 0, end = 1;
+    while (begin < end) {
+        EmuTreeLaunch L{T, begin, end, nullptr, wsm.data()};
+        simt::launch(1, 128, emu_tree_select_thread, &L);
+        begin = end; end = T->ctl.n_items;
+    }
+    for (uint32_t d = 0; d < n; d++) leaf_states[d] = T->state[T->leaf_of[d]];
+    T->n_last = n;
+    return (int)T->ctl.error;
+}
+
+// Backpropagation of the flush selected last: sums[d] = exact result of the R playouts of descent d
+int emu_tree_backprop(void *h, const mctsb_leaf_sum *sums) {
+    EmuTree *T = (EmuTree *)h;
+    std::vector<double> w(T->n_last);
+    for (uint32_t d = 0; d < T->n_last; d++) w[d] = tr_leaf_sum_to_double(sums[d].lo, sums[d].hi);
+    for (uint32_t d = 0; d < T->n_last; d++) tree_backprop_created(T->t, d, w.data());
+    EmuTreeLaunch L{T, 0, T->ctl.n_items, w.data(), nullptr};
+    simt::launch(1, 128, emu_tree_backprop_thread, &L);
+    return (int)T->ctl.error;
+}
+
+double emu_leaf_sum_to_double(uint64_t lo, uint64_t hi) { return tr_leaf_sum_to_double(lo, hi); }
+
+// pre-order walk from the root, children in creation order: one row per node
+static void emu_tree_walk(const EmuTree *T, int node, int depth, uint64_t cap, uint64_t &n, int32_t *o_depth, int32_t *o_move, uint64_t *o_sims,
+                          double *o_score, uint32_t *o_size, uint32_t *o_nchildren, uint32_t *o_virt) {
+    if (n < cap) {
+        o_depth[n] = depth; o_move[n] = T->move[node] == 0xff ? -1 : T->move[node]; o_sims[n] = T->sims[node]; o_score[n] = T->score[node];
+        o_size[n] = T->size[node]; o_nchildren[n] = T->n_children[node]; o_virt[n] = T->virt[node];
+    }
+    n++;
+    for (int i = 0; i < T->n_children[node]; i++)
+        emu_tree_walk(T, T->first_child[node] + i, depth + 1, cap, n, o_depth, o_move, o_sims, o_score, o_size, o_nchildren, o_virt);
+}
+uint64_t emu_tree_dump(void *h, uint64_t cap, int32_t *o_depth, int32_t *o_move, uint64_t *o_sims, double *o_score, uint32_t *o_size,
+                       uint32_t *o_nchildren, uint32_t *o_virt) {
+    const EmuTree *T = (const EmuTree *)h;
+    uint64_t n = 0;
+    emu_tree_walk(T, T->ctl.root, 0, cap, n, o_depth, o_move, o_sims, o_score, o_size, o_nchildren, o_virt);
+    return n;
+}
+int emu_tree_advance(void *h, int move_id) {            // the child that carries `move_id` becomes the root; -1 if it was never expanded
+    EmuTree *T = (EmuTree *)h;
+    const int r = T->ctl.root;
+    for (int i = 0; i < T->n_children[r]; i++)
+        if (T->move[T->first_child[r] + i] == move_id) { T->ctl.root = T->first_child[r] + i; T->parent[T->ctl.root] = -1; return 0; }
+    return -1;
+}
+void emu_tree_stats(void *h, uint32_t *out4) {
+    const EmuTree *T = (const EmuTree *)h;
+    out4[0] = T->ctl.pool_top; out4[1] = T->ctl.n_items; out4[2] = T->ctl.error; out4[3] = T->ctl.exact_evals;
+}
+#endif
 
 }  // extern "C"

@@ -104,6 +104,9 @@ template <class T> inline T shfl_up(T x, int delta, int site) {
 }
 inline uint32_t reduce_add(uint32_t x, int site) { const uint64_t *v = exchange(x, site); uint32_t s = 0; for (int l = 0; l < WARP; l++) s += (uint32_t)v[l]; return s; }
 inline void syncwarp(int site) { (void)exchange(0, site); }
+inline int reduce_max(int x, int site) { const uint64_t *v = exchange((uint64_t)(uint32_t)x, site); int m = (int)(uint32_t)v[0]; for (int l = 1; l < WARP; l++) { int y = (int)(uint32_t)v[l]; if (y > m) m = y; } return m; }
+inline uint32_t reduce_maxu(uint32_t x, int site) { const uint64_t *v = exchange(x, site); uint32_t m = 0; for (int l = 0; l < WARP; l++) if ((uint32_t)v[l] > m) m = (uint32_t)v[l]; return m; }
+inline uint32_t match_any(uint32_t x, int site) { const uint64_t *v = exchange(x, site); uint32_t m = 0; for (int l = 0; l < WARP; l++) if ((uint32_t)v[l] == x) m |= 1u << l; return m; }
 
 // run body(arg) on n_blocks x threads_per_block fibers; returns when every fiber has returned
 inline void launch(int n_blocks, int threads_per_block, void (*body)(void *), void *arg) {

@@ -1,0 +1,195 @@
+"""The device-resident tree (csrc/tree_body.cuh, C ABI mctsb_tree_*): Selection / Expansion / Backpropagation on the
+GPU must build the SAME tree as the host tree (host/mcts.cpp) under the same batching — same nodes in the same
+order, same simulation counts, same score doubles.  On CPU the warp-level code runs on emulated 32-lane warps
+(tests/hostemu) and both trees are fed the same playout results; the -m gpu tests run the kernels."""
+import ctypes as C
+import hashlib
+
+import numpy as np
+import pytest
+
+import montecarlotreesearch_b200 as m
+from oracle.reflib import LEAFSUM_DTYPE
+from tests.hostlib import Session, load
+
+
+@pytest.fixture(scope="module")
+def host():
+    return load()
+
+
+@pytest.fixture(scope="module")
+def emu32():
+    from tests.hostemu.emulib import EmuLib
+    return EmuLib(warp32=True)
+
+
+def fake_sum(state_bytes, first_id, R):
+    """a made-up exact playout sum of one leaf, a function of (position, Philox ids): {lo, hi} limbs of sum(score * 2^57)"""
+    h = hashlib.blake2b(state_bytes + int(first_id).to_bytes(8, "little"), digest_size=16).digest()
+    a, b = int.from_bytes(h[:8], "little"), int.from_bytes(h[8:], "little")
+    return a % (R << 29), b % ((R << 28) + 1)
+
+
+def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, c_checks=True):
+    """grow the host tree and the emulated device tree side by side; compare after every flush"""
+    from tests.hostemu.emulib import EmuTree
+    to_double = emu32.lib.emu_leaf_sum_to_double
+    log = []
+
+    def cb(game, policy, states, n_leaves, Rr, first_id, out, user):
+        for i in range(n_leaves):
+            sb = C.string_at(states + 32 * i, 32)
+            if port is None:
+                lo, hi = fake_sum(sb, first_id + i * Rr, Rr)
+            else:
+                s = np.frombuffer(sb, dtype=m.QSTATE_DTYPE)[0]
+                o, _, _ = port.q_rollout_philox(s, m.DEFAULT_SEED, first_id + i * Rr, Rr)
+                acc, _ = port.leaf_sum(o["score"])
+                lo, hi = int(acc["lo"]), int(acc["hi"])
+            out[i] = to_double(lo, hi)
+        log.append((n_leaves, first_id))
+
+    base_id = 1 << 40
+    host.mcts_host_set_next_rollout_id(base_id)
+    ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, callback=cb)
+    dt = EmuTree(emu32, root, R, K)
+    done = 0
+    for f in range(flushes):
+        n = K if not isinstance(flushes, list) else K
+        ht.grow(n)
+        leaves, err = dt.select(n)
+        assert err == 0, err
+        sums = np.zeros(n, dtype=LEAFSUM_DTYPE)
+        for d in range(n):
+            sb = leaves[d].tobytes()
+            if port is None:
+                lo, hi = fake_sum(sb, base_id + (done + d) * R, R)
+            else:
+                o, _, _ = port.q_rollout_philox(leaves[d], m.DEFAULT_SEED, base_id + (done + d) * R, R)
+                acc, _ = port.leaf_sum(o["score"])
+                lo, hi = int(acc["lo"]), int(acc["hi"])
+            sums[d] = (lo, hi, R)
+        assert dt.backprop(sums) == 0
+        done += n
+        a, b = ht.dump(), dt.dump()
+        assert len(a["depth"]) == len(b["depth"]), (f, len(a["depth"]), len(b["depth"]))
+        for k in ("depth", "move", "n_children", "sims", "size"):
+            assert (a[k] == b[k]).all(), (f, k, np.flatnonzero(a[k] != b[k])[:8])
+        assert a["score"].tobytes() == b["score"].tobytes(), (f, "score", np.flatnonzero(a["score"] != b["score"])[:8])
+        assert (b["virt"] == 0).all()
+        if advance_every and (f + 1) % advance_every == 0:
+            mv = ht.best_move()
+            ht.advance(mv)
+            assert dt.advance(mv)
+    st = dt.stats()
+    ht.close(); dt.close()
+    return st, log
+
+
+def test_leaf_sum_conversion_matches_the_abi_helper(emu32, port):
+    """tr_leaf_sum_to_double (device code) = mctsb_leaf_sum_to_double's correctly rounded exact sum"""
+    rng = np.random.default_rng(5)
+    to_double = emu32.lib.emu_leaf_sum_to_double
+    for R in (1, 4, 16, 127, 128, 4096, 1 << 20):
+        for _ in range(200):
+            lo, hi = int(rng.integers(0, R << 29)), int(rng.integers(0, (R << 28) + 1))
+            exact = (hi << 29) + lo
+            # correctly rounded exact / 2^57 with Python integers
+            from fractions import Fraction
+            assert to_double(lo, hi) == float(Fraction(exact, 1 << 57)), (R, lo, hi)
+    assert to_double(0, 0) == 0.0
+
+
+@pytest.mark.parametrize("R,K,flushes", [(4, 1, 40), (4, 16, 12), (16, 256, 6), (1, 1024, 4)])
+def test_emulated_device_tree_equals_host_tree(host, emu32, R, K, flushes):
+    st, _ = drive_both(host, emu32, m.quoridor_opening(), R, K, flushes)
+    assert st["error"] == 0
+
+
+def test_emulated_device_tree_midgame_with_advance(host, emu32):
+    """a mid-game root (few walls left: deeper, narrower trees, terminal nodes inside a flush) and tree reuse across moves"""
+    from tests.util import golden
+    corpus = golden("corpus_q.npy")
+    for i in (7, 1234, 4000):
+        st, _ = drive_both(host, emu32, corpus[i], 2, 128, 8, advance_every=2)
+        assert st["error"] == 0
+
+
+def test_emulated_device_tree_with_oracle_playouts(host, emu32, port):
+    """the same with real playouts (oracle): exact sums through both conversions"""
+    st, _ = drive_both(host, emu32, m.quoridor_opening(), 2, 32, 4, port=port)
+    assert st["error"] == 0
+
+
+# ---- the kernels, on the GPU ---------------------------------------------------------------------------------------
+def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0):
+    """device tree vs host tree (both playing their rollouts on the GPU, same Philox ids): identical after every grow"""
+    be = m.RolloutBackend(0, m.DEFAULT_SEED)
+    base_id = 1 << 41
+    host.mcts_host_set_next_rollout_id(base_id)
+    ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, policy=policy)
+    dt = m.DeviceTree(be, root, R, K, policy=policy)
+    done = 0
+    for f in range(flushes):
+        n = K if not (tail and f == flushes - 1) else tail
+        ht.grow(n)
+        dt.grow(n, base_id + done * R)
+        done += n
+        a, b = ht.dump(), dt.dump()
+        assert len(a["depth"]) == len(b["depth"]), (f, len(a["depth"]), len(b["depth"]))
+        for k in ("depth", "move", "n_children", "sims", "size"):
+            assert (a[k] == b[k]).all(), (f, k, np.flatnonzero(a[k] != b[k])[:8])
+        assert a["score"].tobytes() == b["score"].tobytes(), (f, "score", np.flatnonzero(a["score"] != b["score"])[:8])
+        assert ht.best_move() == dt.best_move()
+        if advance_every and (f + 1) % advance_every == 0:
+            mv = ht.best_move()
+            ht.advance(mv); dt.advance(mv)
+            assert ht.current_state().tobytes() == dt.root_state().tobytes()
+    info = dt.info()
+    r = ht.root_stats()
+    assert info["root_sims"] == r["sims"] and info["root_score"] == r["score"] and info["root_size"] == r["size"]
+    ht.close(); dt.close(); be.close()
+    return info
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,K,flushes", [(4, 1, 30), (4, 16, 20), (16, 256, 10), (16, 4096, 6), (1, 8192, 4)])
+def test_device_tree_equals_host_tree_on_gpu(host, R, K, flushes):
+    info = compare_gpu(host, m.quoridor_opening(), R, K, flushes, tail=max(1, K // 3))
+    assert info["flags"] == 0 and info["flushes"] == flushes
+
+
+@pytest.mark.gpu
+def test_device_tree_midgame_advance_and_uni_policy_on_gpu(host):
+    from tests.util import golden
+    corpus = golden("corpus_q.npy")
+    deepest = 0
+    for i in (7, 1234, 4000):
+        info = compare_gpu(host, corpus[i], 8, 512, 8, advance_every=2)
+        assert info["flags"] == 0
+        deepest = max(deepest, info["deepest_level"])
+    assert deepest >= 2
+    info = compare_gpu(host, m.quoridor_opening(), 4, 256, 4, policy=m.POLICY_UNI)
+    assert info["flags"] == 0
+
+
+@pytest.mark.gpu
+def test_device_tree_full_pool_and_bad_arguments():
+    be = m.RolloutBackend(0, m.DEFAULT_SEED)
+    with pytest.raises(m.BackendError) as e:
+        t = m.DeviceTree(be, m.quoridor_opening(), 4, 64, max_nodes=600)      # root + 131 children, then 4 x 131 do not fit
+        t.grow(64 * 40, 0)
+    assert e.value.status == 9
+    bad = m.quoridor_opening().copy(); bad["wx"] = 9
+    with pytest.raises(m.BackendError) as e:
+        m.DeviceTree(be, bad, 4, 64)
+    assert e.value.status == 4
+    t = m.DeviceTree(be, m.quoridor_opening(), 4, 64)
+    with pytest.raises(m.BackendError):
+        t.grow(10, 0, leaves_per_flush=65)                                     # more than the tree was created for
+    with pytest.raises(m.BackendError):
+        t.advance(0)                                                           # not a legal move of the opening
+    t.advance(13)                                                              # never expanded: fresh root (mcts.cpp:149-152)
+    assert t.info()["root_sims"] == 0 and int(t.root_state()["turn"]) == 1
+    t.close(); be.close()
