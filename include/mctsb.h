@@ -280,6 +280,10 @@ int mctsb_tree_destroy(mctsb_tree *t);
 /* `iterations` Selection+Expansion+Simulation+Backpropagation rounds in flushes of `leaves_per_flush` (the last one
  * may be shorter); returns after the last flush has been back-propagated. */
 int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flush, uint64_t first_rollout_id);
+/* on: flush f+1 is selected while the playouts of flush f run (its leaves keep their virtual losses until the
+ * results arrive) — the order of the host tree with MCTS_batching::overlap, one flush in flight; off (default):
+ * every flush is back-propagated before the next one is selected. */
+int mctsb_tree_set_overlap(mctsb_tree *t, int on);
 int mctsb_tree_get_info(mctsb_tree *t, mctsb_tree_info *info);
 /* root children in creation (= actions_to_try) order: canonical move id, simulations, score; returns the count in *n */
 int mctsb_tree_root_children(mctsb_tree *t, int32_t *move_ids, uint64_t *sims, double *scores, int max_children, int *n);

@@ -23,19 +23,23 @@ using namespace mctsb;
 
 namespace {
 
-constexpr int TREE_THREADS = 128;                  // 4 warps per CTA
+constexpr int TREE_THREADS = 128;                  // results / backprop kernels: 4 warps per CTA
 constexpr int TREE_WARPS = TREE_THREADS / 32;
+// The selection kernel runs one warp per CTA: 32 threads x <= 128 registers and 7 KB of shared memory fit on an SM
+// next to four resident blocks of the rollout kernel's 96-register build, so the next flush can be selected while the
+// playouts of the current one are running (mctsb_tree_set_overlap), and all its CTAs stay resident for the grid barrier.
+constexpr int SELECT_THREADS = 32;
 
-__global__ void __launch_bounds__(TREE_THREADS) tree_select_kernel(TreeCtx t, uint32_t n, mctsb_qstate *leaf_states) {
+__global__ void __launch_bounds__(SELECT_THREADS) tree_select_kernel(TreeCtx t, uint32_t n, mctsb_qstate *leaf_states) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ TreeWarpSmem wsm[TREE_WARPS];
-    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const uint32_t gtid = blockIdx.x * TREE_THREADS + threadIdx.x, gthreads = gridDim.x * TREE_THREADS;
-    const uint32_t warp = blockIdx.x * TREE_WARPS + wib, nwarps = gridDim.x * TREE_WARPS;
+    __shared__ TreeWarpSmem wsm[1];
+    const int lane = threadIdx.x & 31, wib = 0;
+    const uint32_t gtid = blockIdx.x * SELECT_THREADS + threadIdx.x, gthreads = gridDim.x * SELECT_THREADS;
+    const uint32_t warp = blockIdx.x, nwarps = gridDim.x;
     for (uint32_t d = gtid; d < n; d += gthreads) t.idx[d] = d;               // level 0: every descent starts at the root
     if (gtid == 0) {
         TreeItem r; r.node = t.ctl->root; r.start = 0; r.count = n; r.level = 0;
-        t.items[0] = r; t.ctl->n_items = 1;
+        t.items[0] = r; *t.n_items = 1;
     }
     grid.sync();
     uint32_t begin = 0, end = 1, level = 0;
@@ -48,7 +52,7 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_select_kernel(TreeCtx t, ui
             unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             t.ctl->level_ns[level < 7 ? level : 7] += t1 - t0; t0 = t1;
         }
-        begin = end; end = *(volatile uint32_t *)&t.ctl->n_items; level++;
+        begin = end; end = *(volatile uint32_t *)t.n_items; level++;
     }
     if (gtid == 0 && level > t.ctl->depth_max) t.ctl->depth_max = level;
     for (uint32_t d = gtid; d < n; d += gthreads)                              // the rollout kernel's input, in selection order
@@ -65,7 +69,7 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_results_kernel(TreeCtx t, u
 __global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, const double *w) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * TREE_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * TREE_WARPS;
-    const uint32_t n_items = t.ctl->n_items;
+    const uint32_t n_items = *t.n_items;
     for (uint32_t i = warp; i < n_items; i += nwarps) tree_backprop_item(t, t.items[i], lane, w);
 }
 
@@ -81,14 +85,16 @@ struct mctsb_tree {
     mctsb_backend *b;
     int policy;
     uint32_t R, K; uint64_t pool_cap; double c;
-    TreeCtx ctx;                        // device pointers
-    mctsb_qstate *d_leaf_states; mctsb_leaf_sum *d_sums; double *d_w;
+    TreeCtx ctx[2];                     // device pointers; one set of per-flush arrays per flush slot
+    mctsb_qstate *d_leaf_states[2]; mctsb_leaf_sum *d_sums[2]; double *d_w[2];
     double *d_logtab;
-    void *allocs[32]; int n_allocs;
+    void *allocs[64]; int n_allocs;
     int select_blocks;
+    bool overlap;                       // select flush f+1 while the playouts of flush f run (host tree: MCTS_batching::overlap)
+    cudaStream_t tree_stream;           // Selection / Backpropagation kernels in overlap mode (the playouts stay on the backend's stream)
+    cudaEvent_t ev_selected[2], ev_played[2];
     uint64_t flushes, rollouts;
     float ms[3];
-    cudaEvent_t ev[4];
 };
 
 namespace {
@@ -104,7 +110,8 @@ template <class T> int dev_alloc(mctsb_tree *t, T **p, size_t n) {
 int read_ctl(mctsb_tree *t, TreeCtl *out) {
     mctsb_backend *b = t->b;
     TCK(cudaStreamSynchronize(b->stream));
-    TCK(cudaMemcpy(out, t->ctx.ctl, sizeof *out, cudaMemcpyDeviceToHost));
+    if (t->tree_stream) TCK(cudaStreamSynchronize(t->tree_stream));
+    TCK(cudaMemcpy(out, t->ctx[0].ctl, sizeof *out, cudaMemcpyDeviceToHost));
     return MCTSB_OK;
 }
 
@@ -113,7 +120,7 @@ int write_node(mctsb_tree *t, uint32_t id, const mctsb_qstate &st) {
     mctsb_backend *b = t->b;
     QState s;
     q_unpack(s, st);
-    const TreePool &P = t->ctx.pool;
+    const TreePool &P = t->ctx[0].pool;
     const double zero = 0.0; const unsigned long long zero64 = 0; const uint32_t zero32 = 0; const int32_t minus1 = -1;
     const uint16_t zero16 = 0, unlisted = TR_UNLISTED; const uint8_t nomove = 0xff, flags = q_winner(s) ? TR_FLAG_TERMINAL : 0;
     TCK(cudaMemcpy(P.state + id, &st, sizeof st, cudaMemcpyHostToDevice));
@@ -145,7 +152,7 @@ int read_root(mctsb_tree *t, RootView &v) {
     mctsb_backend *b = t->b;
     int s = read_ctl(t, &v.ctl);
     if (s != MCTSB_OK) return s;
-    const TreePool &P = t->ctx.pool;
+    const TreePool &P = t->ctx[0].pool;
     const int r = v.ctl.root;
     uint16_t nc = 0;
     TCK(cudaMemcpy(&v.first, P.first_child + r, 4, cudaMemcpyDeviceToHost));
@@ -180,7 +187,7 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     if (!t) return MCTSB_ERR_OOM;
     memset(t, 0, sizeof *t);
     t->b = b; t->policy = policy; t->R = rollouts_per_leaf; t->K = max_leaves_per_flush; t->pool_cap = max_nodes; t->c = uct_c;
-    TreeCtx &c = t->ctx;
+    TreeCtx &c = t->ctx[0];
     const size_t N = (size_t)max_nodes, K = t->K;
     TTRY(dev_alloc(t, &c.pool.state, N)); TTRY(dev_alloc(t, &c.pool.lh, N)); TTRY(dev_alloc(t, &c.pool.lv, N));
     TTRY(dev_alloc(t, &c.pool.score, N)); TTRY(dev_alloc(t, &c.pool.sims, N)); TTRY(dev_alloc(t, &c.pool.virt, N));
@@ -188,11 +195,15 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     TTRY(dev_alloc(t, &c.pool.n_children, N)); TTRY(dev_alloc(t, &c.pool.n_moves, N)); TTRY(dev_alloc(t, &c.pool.move, N));
     TTRY(dev_alloc(t, &c.pool.flags, N));
     TTRY(dev_alloc(t, &c.ctl, 1));
-    c.items_cap = (uint32_t)(K * TR_MAX_LEVELS < (1u << 30) ? K * TR_MAX_LEVELS : (1u << 30));
-    TTRY(dev_alloc(t, &c.items, (size_t)c.items_cap));
-    TTRY(dev_alloc(t, &c.idx, K * TR_MAX_LEVELS)); TTRY(dev_alloc(t, &c.choice, K)); TTRY(dev_alloc(t, &c.leaf_of, K)); TTRY(dev_alloc(t, &c.created, K));
-    TTRY(dev_alloc(t, &t->d_leaf_states, K)); TTRY(dev_alloc(t, &t->d_sums, K)); TTRY(dev_alloc(t, &t->d_w, K));
     c.K = t->K; c.pool_cap = (uint32_t)max_nodes; c.R = t->R; c.c = uct_c;
+    c.items_cap = (uint32_t)(K * TR_MAX_LEVELS < (1u << 30) ? K * TR_MAX_LEVELS : (1u << 30));
+    t->ctx[1] = c;
+    for (int k = 0; k < 2; k++) {                      // per-flush arrays, one set per slot
+        TreeCtx &f = t->ctx[k];
+        TTRY(dev_alloc(t, &f.n_items, 1)); TTRY(dev_alloc(t, &f.items, (size_t)f.items_cap));
+        TTRY(dev_alloc(t, &f.idx, K * TR_MAX_LEVELS)); TTRY(dev_alloc(t, &f.choice, K)); TTRY(dev_alloc(t, &f.leaf_of, K)); TTRY(dev_alloc(t, &f.created, K));
+        TTRY(dev_alloc(t, &t->d_leaf_states[k], K)); TTRY(dev_alloc(t, &t->d_sums[k], K)); TTRY(dev_alloc(t, &t->d_w[k], K));
+    }
     // ln N for every N = m * R a node of this pool can reach, from the host's libm: the exact UCT expression then
     // sees the doubles the host tree sees.  One entry per iteration the pool can hold.
     {
@@ -202,22 +213,29 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
         TTRY(dev_alloc(t, &t->d_logtab, n));
         cudaError_t e = cudaMemcpy(t->d_logtab, tab.data(), n * sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) { int s = fail(b, e, "log table upload"); mctsb_tree_destroy(t); return s; }
-        c.logtab = t->d_logtab; c.logtab_n = (uint32_t)n;
+        for (int k = 0; k < 2; k++) { t->ctx[k].logtab = t->d_logtab; t->ctx[k].logtab_n = (uint32_t)n; }
     }
     TreeCtl ctl; memset(&ctl, 0, sizeof ctl);
     ctl.pool_top = 1; ctl.root = 0;
     cudaError_t e = cudaMemcpy(c.ctl, &ctl, sizeof ctl, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { int s = fail(b, e, "tree control block upload"); mctsb_tree_destroy(t); return s; }
     TTRY(write_node(t, 0, *root));
-    for (int i = 0; i < 4; i++) {
-        e = cudaEventCreate(&t->ev[i]);
+    for (int i = 0; i < 2; i++) {
+        e = cudaEventCreateWithFlags(&t->ev_selected[i], cudaEventDisableTiming);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_played[i], cudaEventDisableTiming);
         if (e != cudaSuccess) { int s = fail(b, e, "cudaEventCreate"); mctsb_tree_destroy(t); return s; }
+    }
+    {
+        int lo = 0, hi = 0;                              // the tree's kernels are short and on the critical path: highest priority
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&t->tree_stream, cudaStreamNonBlocking, hi);
+        if (e != cudaSuccess) { int s = fail(b, e, "cudaStreamCreateWithPriority"); mctsb_tree_destroy(t); return s; }
     }
     // the selection kernel synchronises its CTAs between levels: all of them must be resident (cooperative launch)
     int dev_sms = 0, per_sm = 0, coop = 0;
     cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, b->device);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_select_kernel, TREE_THREADS, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_select_kernel, SELECT_THREADS, 0);
     if (!coop || per_sm < 1 || dev_sms < 1) { snprintf(b->cuda_err, sizeof b->cuda_err, "cooperative launch not available"); mctsb_tree_destroy(t); return MCTSB_ERR_CUDA; }
     t->select_blocks = dev_sms;
     *out = t;
@@ -229,10 +247,49 @@ int mctsb_tree_destroy(mctsb_tree *t) {
     cudaSetDevice(t->b->device);
     cudaStreamSynchronize(t->b->stream);
     for (int i = 0; i < t->n_allocs; i++) cudaFree(t->allocs[i]);
-    for (int i = 0; i < 4; i++) if (t->ev[i]) cudaEventDestroy(t->ev[i]);
+    if (t->tree_stream) { cudaStreamSynchronize(t->tree_stream); cudaStreamDestroy(t->tree_stream); }
+    for (int i = 0; i < 2; i++) { if (t->ev_selected[i]) cudaEventDestroy(t->ev_selected[i]); if (t->ev_played[i]) cudaEventDestroy(t->ev_played[i]); }
     delete t;
     return MCTSB_OK;
 }
+
+int mctsb_tree_set_overlap(mctsb_tree *t, int on) {
+    if (!t) return MCTSB_ERR_BAD_ARG;
+    t->overlap = on != 0;
+    return MCTSB_OK;
+}
+
+namespace {
+
+// the launches of one flush, split so that the two modes can order them differently
+int launch_select(mctsb_tree *t, int slot, uint32_t n, cudaStream_t st) {
+    mctsb_backend *b = t->b;
+    void *args[] = {(void *)&t->ctx[slot], (void *)&n, (void *)&t->d_leaf_states[slot]};
+    TCK(cudaLaunchCooperativeKernel((const void *)tree_select_kernel, dim3(t->select_blocks), dim3(SELECT_THREADS), args, 0, st));
+    b->launches++;
+    return MCTSB_OK;
+}
+
+int launch_playouts(mctsb_tree *t, int slot, uint32_t n, uint64_t first_id) {      // on the backend's stream
+    mctsb_backend *b = t->b;
+    TCK(cudaMemsetAsync(t->d_sums[slot], 0, (size_t)n * sizeof(mctsb_leaf_sum), b->stream));
+    RolloutParams p; memset(&p, 0, sizeof p);
+    p.states = t->d_leaf_states[slot]; p.n_leaves = n; p.rollouts_per_leaf = t->R; p.n_rollouts = (uint64_t)n * t->R;
+    p.seed = b->seed; p.first_rollout_id = first_id; p.sums = t->d_sums[slot]; p.counters = b->d_counters;
+    p.leave_room = t->overlap ? 1u : 0u;
+    return mctsb_internal_launch_rollouts(b, MCTSB_GAME_QUORIDOR, t->policy, false, p);
+}
+
+int launch_backprop(mctsb_tree *t, int slot, uint32_t n, cudaStream_t st) {
+    mctsb_backend *b = t->b;
+    tree_results_kernel<<<(n + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, st>>>(t->ctx[slot], n, t->d_sums[slot], t->d_w[slot]);
+    tree_backprop_kernel<<<t->select_blocks * 2, TREE_THREADS, 0, st>>>(t->ctx[slot], t->d_w[slot]);
+    TCK(cudaGetLastError());
+    b->launches += 2;
+    return MCTSB_OK;
+}
+
+}  // namespace
 
 int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flush, uint64_t first_rollout_id) {
     if (!t || leaves_per_flush == 0 || leaves_per_flush > t->K) return MCTSB_ERR_BAD_ARG;
@@ -241,47 +298,70 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
     TCK(cudaSetDevice(b->device));
     b->res_game = -1; b->res_leaves = 0;
     t->ms[0] = t->ms[1] = t->ms[2] = 0.0f;
-    std::vector<cudaEvent_t> evs;           // per-flush phase marks, read after the last flush
     const uint32_t n_flushes = (iterations + leaves_per_flush - 1) / leaves_per_flush;
-    const bool timed = n_flushes <= 4096;
-    if (timed) {
-        evs.resize((size_t)n_flushes * 4);
-        for (auto &e : evs) TCK(cudaEventCreate(&e));
-    }
-    uint32_t done = 0, f = 0;
     int status = MCTSB_OK;
-    while (done < iterations && status == MCTSB_OK) {
-        uint32_t n = iterations - done < leaves_per_flush ? iterations - done : leaves_per_flush;
-        if (timed) cudaEventRecord(evs[4 * f + 0], b->stream);
-        void *args[] = {(void *)&t->ctx, (void *)&n, (void *)&t->d_leaf_states};
-        cudaError_t e = cudaLaunchCooperativeKernel((const void *)tree_select_kernel, dim3(t->select_blocks), dim3(TREE_THREADS), args, 0, b->stream);
-        if (e != cudaSuccess) { status = fail(b, e, "tree select launch"); break; }
-        b->launches++;
-        if (timed) cudaEventRecord(evs[4 * f + 1], b->stream);
-        e = cudaMemsetAsync(t->d_sums, 0, (size_t)n * sizeof(mctsb_leaf_sum), b->stream);
-        if (e != cudaSuccess) { status = fail(b, e, "cudaMemsetAsync"); break; }
-        RolloutParams p; memset(&p, 0, sizeof p);
-        p.states = t->d_leaf_states; p.n_leaves = n; p.rollouts_per_leaf = t->R; p.n_rollouts = (uint64_t)n * t->R;
-        p.seed = b->seed; p.first_rollout_id = first_rollout_id + (uint64_t)done * t->R; p.sums = t->d_sums; p.counters = b->d_counters;
-        status = mctsb_internal_launch_rollouts(b, MCTSB_GAME_QUORIDOR, t->policy, false, p);
-        if (status != MCTSB_OK) break;
-        if (timed) cudaEventRecord(evs[4 * f + 2], b->stream);
-        tree_results_kernel<<<(n + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, b->stream>>>(t->ctx, n, t->d_sums, t->d_w);
-        tree_backprop_kernel<<<t->select_blocks * 2, TREE_THREADS, 0, b->stream>>>(t->ctx, t->d_w);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) { status = fail(b, e, "tree backprop launch"); break; }
-        b->launches += 2;
-        if (timed) cudaEventRecord(evs[4 * f + 3], b->stream);
-        done += n; f++;
-        t->flushes++; t->rollouts += (uint64_t)n * t->R;
-    }
-    cudaError_t e = cudaStreamSynchronize(b->stream);
-    if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
-    if (timed) {
-        if (status == MCTSB_OK)
-            for (uint32_t i = 0; i < f; i++)
-                for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, evs[4 * i + k], evs[4 * i + k + 1]); t->ms[k] += ms; }
-        for (auto &ev : evs) cudaEventDestroy(ev);
+    uint32_t done = 0, f = 0;
+    std::vector<cudaEvent_t> evs;           // synchronous mode: per-flush phase marks, read after the last flush
+    if (!t->overlap) {
+        // Selection(f) -> playouts(f) -> Backpropagation(f), all on the backend's stream
+        const bool timed = n_flushes <= 4096;
+        if (timed) { evs.resize((size_t)n_flushes * 4); for (auto &e : evs) TCK(cudaEventCreate(&e)); }
+        while (done < iterations && status == MCTSB_OK) {
+            const uint32_t n = iterations - done < leaves_per_flush ? iterations - done : leaves_per_flush;
+            if (timed) cudaEventRecord(evs[4 * f + 0], b->stream);
+            status = launch_select(t, 0, n, b->stream);
+            if (timed) cudaEventRecord(evs[4 * f + 1], b->stream);
+            if (status == MCTSB_OK) status = launch_playouts(t, 0, n, first_rollout_id + (uint64_t)done * t->R);
+            if (timed) cudaEventRecord(evs[4 * f + 2], b->stream);
+            if (status == MCTSB_OK) status = launch_backprop(t, 0, n, b->stream);
+            if (timed) cudaEventRecord(evs[4 * f + 3], b->stream);
+            if (status != MCTSB_OK) break;
+            done += n; f++;
+            t->flushes++; t->rollouts += (uint64_t)n * t->R;
+        }
+        cudaError_t e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
+        if (timed) {
+            if (status == MCTSB_OK)
+                for (uint32_t i = 0; i < f; i++)
+                    for (int k = 0; k < 3; k++) { float ms = 0; cudaEventElapsedTime(&ms, evs[4 * i + k], evs[4 * i + k + 1]); t->ms[k] += ms; }
+            for (auto &ev : evs) cudaEventDestroy(ev);
+        }
+    } else {
+        // One flush in flight, the order of the host tree with MCTS_batching::overlap (host/mcts.cpp grow_tree):
+        //   S(1)  S(2) B(1)  S(3) B(2) ...  S(n) B(n-1)  B(n)
+        // Selection and Backpropagation on the tree's own stream, playouts on the backend's: S(f+1) runs while the
+        // playouts of flush f are on the SMs, B(f) as soon as they are done.  Flush f uses slot f & 1 of the per-flush arrays.
+        cudaStream_t ts = t->tree_stream;
+        uint32_t n_prev = 0;
+        cudaError_t e = cudaSuccess;
+        while (done < iterations && status == MCTSB_OK) {
+            const uint32_t n = iterations - done < leaves_per_flush ? iterations - done : leaves_per_flush;
+            const int slot = (int)(f & 1u);
+            status = launch_select(t, slot, n, ts);
+            if (status != MCTSB_OK) break;
+            if ((e = cudaEventRecord(t->ev_selected[slot], ts)) != cudaSuccess) { status = fail(b, e, "cudaEventRecord"); break; }
+            if (f > 0) {                                   // the flush before: its playouts must be done
+                if ((e = cudaStreamWaitEvent(ts, t->ev_played[slot ^ 1], 0)) != cudaSuccess) { status = fail(b, e, "cudaStreamWaitEvent"); break; }
+                status = launch_backprop(t, slot ^ 1, n_prev, ts);
+                if (status != MCTSB_OK) break;
+            }
+            if ((e = cudaStreamWaitEvent(b->stream, t->ev_selected[slot], 0)) != cudaSuccess) { status = fail(b, e, "cudaStreamWaitEvent"); break; }
+            status = launch_playouts(t, slot, n, first_rollout_id + (uint64_t)done * t->R);
+            if (status != MCTSB_OK) break;
+            if ((e = cudaEventRecord(t->ev_played[slot], b->stream)) != cudaSuccess) { status = fail(b, e, "cudaEventRecord"); break; }
+            n_prev = n; done += n; f++;
+            t->flushes++; t->rollouts += (uint64_t)n * t->R;
+        }
+        if (status == MCTSB_OK && f > 0) {
+            const int last = (int)((f - 1) & 1u);
+            if ((e = cudaStreamWaitEvent(ts, t->ev_played[last], 0)) != cudaSuccess) status = fail(b, e, "cudaStreamWaitEvent");
+            else status = launch_backprop(t, last, n_prev, ts);
+        }
+        e = cudaStreamSynchronize(b->stream);
+        if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
+        e = cudaStreamSynchronize(ts);
+        if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
     }
     if (status != MCTSB_OK) return status;
     TreeCtl ctl;
@@ -303,7 +383,7 @@ int mctsb_tree_get_info(mctsb_tree *t, mctsb_tree_info *info) {
     int s = read_ctl(t, &ctl);
     if (s != MCTSB_OK) return s;
     memset(info, 0, sizeof *info);
-    const TreePool &P = t->ctx.pool;
+    const TreePool &P = t->ctx[0].pool;
     unsigned long long sims = 0; uint16_t nc = 0;
     TCK(cudaMemcpy(&sims, P.sims + ctl.root, 8, cudaMemcpyDeviceToHost));
     TCK(cudaMemcpy(&info->root_score, P.score + ctl.root, 8, cudaMemcpyDeviceToHost));
@@ -367,7 +447,7 @@ int mctsb_tree_advance(mctsb_tree *t, int32_t move_id) {
     for (int i = 0; i < v.nc; i++) if (v.move[i] == move_id) next = v.first + i;
     if (next >= 0) {
         const int32_t minus1 = -1;
-        TCK(cudaMemcpy(t->ctx.pool.parent + next, &minus1, 4, cudaMemcpyHostToDevice));
+        TCK(cudaMemcpy(t->ctx[0].pool.parent + next, &minus1, 4, cudaMemcpyHostToDevice));
     } else {                                              // "Didn't find child node. Had to start over." (mcts.cpp:149-152)
         QState q;
         q_unpack(q, v.state);
@@ -379,9 +459,9 @@ int mctsb_tree_advance(mctsb_tree *t, int32_t move_id) {
         s = write_node(t, (uint32_t)next, st);
         if (s != MCTSB_OK) return s;
         const uint32_t top = v.ctl.pool_top + 1;
-        TCK(cudaMemcpy(&t->ctx.ctl->pool_top, &top, 4, cudaMemcpyHostToDevice));
+        TCK(cudaMemcpy(&t->ctx[0].ctl->pool_top, &top, 4, cudaMemcpyHostToDevice));
     }
-    TCK(cudaMemcpy(&t->ctx.ctl->root, &next, 4, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(&t->ctx[0].ctl->root, &next, 4, cudaMemcpyHostToDevice));
     return MCTSB_OK;
 }
 
@@ -392,7 +472,7 @@ int mctsb_tree_root_state(mctsb_tree *t, mctsb_qstate *out) {
     TreeCtl ctl;
     int s = read_ctl(t, &ctl);
     if (s != MCTSB_OK) return s;
-    TCK(cudaMemcpy(out, t->ctx.pool.state + ctl.root, sizeof *out, cudaMemcpyDeviceToHost));
+    TCK(cudaMemcpy(out, t->ctx[0].pool.state + ctl.root, sizeof *out, cudaMemcpyDeviceToHost));
     return MCTSB_OK;
 }
 
@@ -405,7 +485,7 @@ int mctsb_tree_dump(mctsb_tree *t, uint64_t cap, int32_t *depth, int32_t *move_i
     int s = read_ctl(t, &ctl);
     if (s != MCTSB_OK) return s;
     const size_t N = ctl.pool_top;
-    const TreePool &P = t->ctx.pool;
+    const TreePool &P = t->ctx[0].pool;
     std::vector<int32_t> first(N); std::vector<uint16_t> nc(N); std::vector<uint8_t> mv(N);
     std::vector<unsigned long long> sm(N); std::vector<double> sc(N); std::vector<uint32_t> sz(N);
     TCK(cudaMemcpy(first.data(), P.first_child, N * 4, cudaMemcpyDeviceToHost));

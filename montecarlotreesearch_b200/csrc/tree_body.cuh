@@ -110,7 +110,6 @@ struct TreeItem { int32_t node; uint32_t start, count, level; };
 
 struct TreeCtl {                      // lives in device memory
     uint32_t pool_top;                // next free node id
-    uint32_t n_items;                 // items of the current flush (all levels)
     uint32_t error;                   // TR_ERR_* bits
     int32_t root;
     uint32_t level_begin, level_end;  // item range of the level being processed (select kernel)
@@ -120,9 +119,10 @@ struct TreeCtl {                      // lives in device memory
     unsigned long long level_ns[8];   // time spent per level of the selection kernel, summed over flushes (levels >= 7 in the last slot)
 };
 
-struct TreeCtx {
-    TreePool pool;
+struct TreeCtx {                      // the pool and the per-flush arrays of ONE flush slot (two slots: a flush may be
+    TreePool pool;                    // selected while the playouts of the one before are still running)
     TreeCtl *ctl;
+    uint32_t *n_items;                // items of this slot's flush (all levels)
     TreeItem *items; uint32_t items_cap;
     uint32_t *idx;                    // [TR_MAX_LEVELS][K]: idx[l*K + p] = descent number, lists of level l items
     uint8_t *choice;                  // [K] scratch: child picked by the step at list position p
@@ -490,7 +490,7 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     }
     // --- the next level's items ---
     uint32_t ibase = 0;
-    if (lane == 0) ibase = TR_ATOMIC_ADD32(&t.ctl->n_items, n_new);
+    if (lane == 0) ibase = TR_ATOMIC_ADD32(t.n_items, n_new);
     ibase = LS_SHFL(ibase, 0);
     if (ibase + n_new > t.items_cap) {                      // cannot happen with items_cap >= K * TR_MAX_LEVELS; stop here if it does
         if (lane == 0) TR_ATOMIC_OR32(&t.ctl->error, (uint32_t)TR_ERR_ITEMS);

@@ -31,8 +31,8 @@ class EmuLib:
             L.emu_tree_create.restype = vp
             L.emu_tree_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32]
             L.emu_tree_destroy.argtypes = [vp]
-            L.emu_tree_select.argtypes = [vp, C.c_uint32, vp]
-            L.emu_tree_backprop.argtypes = [vp, vp]
+            L.emu_tree_select.argtypes = [vp, C.c_int, C.c_uint32, vp]
+            L.emu_tree_backprop.argtypes = [vp, C.c_int, vp]
             L.emu_tree_dump.restype = C.c_uint64
             L.emu_tree_dump.argtypes = [vp, C.c_uint64] + [vp] * 7
             L.emu_tree_advance.argtypes = [vp, C.c_int]
@@ -184,16 +184,17 @@ class EmuTree:
             self.lib.emu_tree_destroy(self.h)
             self.h = None
 
-    def select(self, n):
+    def select(self, n, slot=0):
+        """Selection + Expansion of a flush of n descents into flush slot 0 / 1 -> (leaf positions, error bits)"""
         leaves = np.zeros(n, dtype=QSTATE_DTYPE)
-        err = self.lib.emu_tree_select(self.h, n, leaves.ctypes.data)
+        err = self.lib.emu_tree_select(self.h, slot, n, leaves.ctypes.data)
         assert err >= 0
         return leaves, err
 
-    def backprop(self, sums):
+    def backprop(self, sums, slot=0):
         from oracle.reflib import LEAFSUM_DTYPE
         s = np.ascontiguousarray(sums, dtype=LEAFSUM_DTYPE)
-        return self.lib.emu_tree_backprop(self.h, s.ctypes.data)
+        return self.lib.emu_tree_backprop(self.h, slot, s.ctypes.data)
 
     def advance(self, move_id):
         return self.lib.emu_tree_advance(self.h, int(move_id)) == 0

@@ -240,25 +240,27 @@ int emu_warp_width() { return LS_WARP; }
 // level, one warp per item); the playouts of a flush are the caller's (the test feeds the same results to the
 // host tree and to this one).
 #if defined(MCTSB_EMU_WARP32)
+struct EmuSlot {
+    std::vector<TreeItem> items; std::vector<uint32_t> idx; std::vector<uint8_t> choice, created; std::vector<int32_t> leaf_of;
+    uint32_t n_items, n_last;
+};
 struct EmuTree {
-    TreeCtx t; TreeCtl ctl;
+    TreeCtx t[2]; TreeCtl ctl; EmuSlot slot[2];
     std::vector<mctsb_qstate> state; std::vector<uint64_t> lh, lv; std::vector<double> score; std::vector<unsigned long long> sims;
     std::vector<uint32_t> virt, size; std::vector<int32_t> parent, first_child; std::vector<uint16_t> n_children, n_moves;
     std::vector<uint8_t> move, flags;
-    std::vector<TreeItem> items; std::vector<uint32_t> idx; std::vector<uint8_t> choice, created; std::vector<int32_t> leaf_of;
     std::vector<double> logtab;
-    uint32_t n_last;
 };
-struct EmuTreeLaunch { EmuTree *T; uint32_t begin, end; const double *w; TreeWarpSmem *wsm; };
+struct EmuTreeLaunch { EmuTree *T; int slot; uint32_t begin, end; const double *w; TreeWarpSmem *wsm; };
 static void emu_tree_select_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
     const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
-    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_select_item(L->T->t, L->T->items[i], lane, L->wsm[warp]);
+    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_select_item(L->T->t[L->slot], L->T->slot[L->slot].items[i], lane, L->wsm[warp]);
 }
 static void emu_tree_backprop_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
     const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
-    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_backprop_item(L->T->t, L->T->items[i], lane, L->w);
+    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_backprop_item(L->T->t[L->slot], L->T->slot[L->slot].items[i], lane, L->w);
 }
 
 void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t pool_cap, double c, uint32_t logtab_n) {
@@ -266,52 +268,59 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
     T->state.resize(pool_cap); T->lh.resize(pool_cap); T->lv.resize(pool_cap); T->score.resize(pool_cap); T->sims.resize(pool_cap);
     T->virt.resize(pool_cap); T->size.resize(pool_cap); T->parent.resize(pool_cap); T->first_child.resize(pool_cap);
     T->n_children.resize(pool_cap); T->n_moves.resize(pool_cap); T->move.resize(pool_cap); T->flags.resize(pool_cap);
-    T->items.resize((size_t)K * TR_MAX_LEVELS); T->idx.resize((size_t)K * TR_MAX_LEVELS); T->choice.resize(K); T->created.resize(K); T->leaf_of.resize(K);
     T->logtab.resize(logtab_n);
     for (uint32_t m = 0; m < logtab_n; m++) T->logtab[m] = log((double)((unsigned long long)m * R));
-    TreeCtx &t = T->t;
-    t.pool.state = T->state.data(); t.pool.lh = T->lh.data(); t.pool.lv = T->lv.data(); t.pool.score = T->score.data(); t.pool.sims = T->sims.data();
-    t.pool.virt = T->virt.data(); t.pool.size = T->size.data(); t.pool.parent = T->parent.data(); t.pool.first_child = T->first_child.data();
-    t.pool.n_children = T->n_children.data(); t.pool.n_moves = T->n_moves.data(); t.pool.move = T->move.data(); t.pool.flags = T->flags.data();
-    t.ctl = &T->ctl; t.items = T->items.data(); t.items_cap = (uint32_t)T->items.size(); t.idx = T->idx.data(); t.choice = T->choice.data();
-    t.leaf_of = T->leaf_of.data(); t.created = T->created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
-    t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
+    for (int k = 0; k < 2; k++) {
+        EmuSlot &S = T->slot[k];
+        S.items.resize((size_t)K * TR_MAX_LEVELS); S.idx.resize((size_t)K * TR_MAX_LEVELS); S.choice.resize(K); S.created.resize(K); S.leaf_of.resize(K);
+        S.n_items = 0; S.n_last = 0;
+        TreeCtx &t = T->t[k];
+        t.pool.state = T->state.data(); t.pool.lh = T->lh.data(); t.pool.lv = T->lv.data(); t.pool.score = T->score.data(); t.pool.sims = T->sims.data();
+        t.pool.virt = T->virt.data(); t.pool.size = T->size.data(); t.pool.parent = T->parent.data(); t.pool.first_child = T->first_child.data();
+        t.pool.n_children = T->n_children.data(); t.pool.n_moves = T->n_moves.data(); t.pool.move = T->move.data(); t.pool.flags = T->flags.data();
+        t.ctl = &T->ctl; t.n_items = &S.n_items; t.items = S.items.data(); t.items_cap = (uint32_t)S.items.size(); t.idx = S.idx.data(); t.choice = S.choice.data();
+        t.leaf_of = S.leaf_of.data(); t.created = S.created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
+        t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
+    }
     memset(&T->ctl, 0, sizeof T->ctl);
     QState s; q_unpack(s, *root);
     T->state[0] = *root; T->score[0] = 0; T->sims[0] = 0; T->virt[0] = 0; T->size[0] = 0; T->parent[0] = -1; T->first_child[0] = -1;
     T->n_children[0] = 0; T->n_moves[0] = TR_UNLISTED; T->move[0] = 0xff; T->flags[0] = q_winner(s) ? TR_FLAG_TERMINAL : 0;
-    T->ctl.pool_top = 1; T->ctl.root = 0; T->n_last = 0;
+    T->ctl.pool_top = 1; T->ctl.root = 0;
     return T;
 }
 void emu_tree_destroy(void *h) { delete (EmuTree *)h; }
 
-// Selection + Expansion of one flush of n descents; leaf_states[d] = position of the leaf descent d ended at
-int emu_tree_select(void *h, uint32_t n, mctsb_qstate *leaf_states) {
+// Selection + Expansion of one flush of n descents into flush slot `slot`; leaf_states[d] = position of the leaf
+// descent d ended at
+int emu_tree_select(void *h, int slot, uint32_t n, mctsb_qstate *leaf_states) {
     EmuTree *T = (EmuTree *)h;
-    if (n == 0 || n > T->t.K) return -1;
-    for (uint32_t d = 0; d < n; d++) T->idx[d] = d;
+    if (n == 0 || n > T->t[0].K || slot < 0 || slot > 1) return -1;
+    EmuSlot &S = T->slot[slot];
+    for (uint32_t d = 0; d < n; d++) S.idx[d] = d;
     TreeItem r; r.node = T->ctl.root; r.start = 0; r.count = n; r.level = 0;
-    T->items[0] = r; T->ctl.n_items = 1;
+    S.items[0] = r; S.n_items = 1;
     std::vector<TreeWarpSmem> wsm(4);
     memset(wsm.data(), 0xa5, sizeof(TreeWarpSmem) * 4);
     uint32_t begin = 0, end = 1;
     while (begin < end) {
-        EmuTreeLaunch L{T, begin, end, nullptr, wsm.data()};
+        EmuTreeLaunch L{T, slot, begin, end, nullptr, wsm.data()};
         simt::launch(1, 128, emu_tree_select_thread, &L);
-        begin = end; end = T->ctl.n_items;
+        begin = end; end = S.n_items;
     }
-    for (uint32_t d = 0; d < n; d++) leaf_states[d] = T->state[T->leaf_of[d]];
-    T->n_last = n;
+    for (uint32_t d = 0; d < n; d++) leaf_states[d] = T->state[S.leaf_of[d]];
+    S.n_last = n;
     return (int)T->ctl.error;
 }
 
-// Backpropagation of the flush selected last: sums[d] = exact result of the R playouts of descent d
-int emu_tree_backprop(void *h, const mctsb_leaf_sum *sums) {
+// Backpropagation of the flush selected last into `slot`: sums[d] = exact result of the R playouts of descent d
+int emu_tree_backprop(void *h, int slot, const mctsb_leaf_sum *sums) {
     EmuTree *T = (EmuTree *)h;
-    std::vector<double> w(T->n_last);
-    for (uint32_t d = 0; d < T->n_last; d++) w[d] = tr_leaf_sum_to_double(sums[d].lo, sums[d].hi);
-    for (uint32_t d = 0; d < T->n_last; d++) tree_backprop_created(T->t, d, w.data());
-    EmuTreeLaunch L{T, 0, T->ctl.n_items, w.data(), nullptr};
+    EmuSlot &S = T->slot[slot];
+    std::vector<double> w(S.n_last);
+    for (uint32_t d = 0; d < S.n_last; d++) w[d] = tr_leaf_sum_to_double(sums[d].lo, sums[d].hi);
+    for (uint32_t d = 0; d < S.n_last; d++) tree_backprop_created(T->t[slot], d, w.data());
+    EmuTreeLaunch L{T, slot, 0, S.n_items, w.data(), nullptr};
     simt::launch(1, 128, emu_tree_backprop_thread, &L);
     return (int)T->ctl.error;
 }
@@ -345,7 +354,7 @@ int emu_tree_advance(void *h, int move_id) {            // the child that carrie
 }
 void emu_tree_stats(void *h, uint32_t *out4) {
     const EmuTree *T = (const EmuTree *)h;
-    out4[0] = T->ctl.pool_top; out4[1] = T->ctl.n_items; out4[2] = T->ctl.error; out4[3] = T->ctl.exact_evals;
+    out4[0] = T->ctl.pool_top; out4[1] = T->slot[0].n_items + T->slot[1].n_items; out4[2] = T->ctl.error; out4[3] = T->ctl.exact_evals;
 }
 #endif
 

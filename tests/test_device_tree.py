@@ -87,6 +87,45 @@ def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, c_c
     return st, log
 
 
+def test_emulated_device_tree_with_one_flush_in_flight(host, emu32):
+    """overlap mode: S(1) S(2) B(1) S(3) B(2) ... B(n) — the host tree's order with MCTS_batching::overlap; every flush is
+    selected while the one before still carries its virtual losses"""
+    from tests.hostemu.emulib import EmuTree
+    to_double = emu32.lib.emu_leaf_sum_to_double
+    for root, R, K, flushes in ((m.quoridor_opening(), 4, 64, 9), (m.quoridor_opening(), 1, 512, 5)):
+        def cb(game, policy, states, n_leaves, Rr, first_id, out, user):
+            for i in range(n_leaves):
+                lo, hi = fake_sum(C.string_at(states + 32 * i, 32), first_id + i * Rr, Rr)
+                out[i] = to_double(lo, hi)
+        base_id = 1 << 40
+        host.mcts_host_set_next_rollout_id(base_id)
+        ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, callback=cb)
+        ht.set_overlap(1)
+        tail = K // 2 + 1
+        ht.grow(K * (flushes - 1) + tail)
+        dt = EmuTree(emu32, root, R, K)
+        pending = None
+        for f in range(flushes):
+            n = K if f < flushes - 1 else tail
+            leaves, err = dt.select(n, slot=f & 1)
+            assert err == 0
+            sums = np.zeros(n, dtype=LEAFSUM_DTYPE)
+            for d in range(n):
+                lo, hi = fake_sum(leaves[d].tobytes(), base_id + (f * K + d) * R, R)
+                sums[d] = (lo, hi, R)
+            if pending is not None:
+                assert dt.backprop(pending[0], slot=pending[1]) == 0
+            pending = (sums, f & 1)
+        assert dt.backprop(pending[0], slot=pending[1]) == 0
+        a, b = ht.dump(), dt.dump()
+        assert len(a["depth"]) == len(b["depth"])
+        for k in ("depth", "move", "n_children", "sims", "size"):
+            assert (a[k] == b[k]).all(), (k, np.flatnonzero(a[k] != b[k])[:8])
+        assert a["score"].tobytes() == b["score"].tobytes()
+        assert (b["virt"] == 0).all()
+        ht.close(); dt.close()
+
+
 def test_leaf_sum_conversion_matches_the_abi_helper(emu32, port):
     """tr_leaf_sum_to_double (device code) = mctsb_leaf_sum_to_double's correctly rounded exact sum"""
     rng = np.random.default_rng(5)
@@ -123,6 +162,37 @@ def test_emulated_device_tree_with_oracle_playouts(host, emu32, port):
 
 
 # ---- the kernels, on the GPU ---------------------------------------------------------------------------------------
+def compare_gpu_overlapped(host, root, R, K, flushes, policy=0):
+    """one flush in flight on both sides: host tree with MCTS_batching::overlap vs mctsb_tree_set_overlap"""
+    be = m.RolloutBackend(0, m.DEFAULT_SEED)
+    base_id = 1 << 43
+    iters = K * (flushes - 1) + K // 2 + 1
+    host.mcts_host_set_next_rollout_id(base_id)
+    ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, policy=policy)
+    ht.set_overlap(1)
+    dt = m.DeviceTree(be, root, R, K, policy=policy)
+    dt.set_overlap(True)
+    for rep in range(2):                     # two grows: the second starts from a tree whose pipeline has drained
+        ht.grow(iters)
+        dt.grow(iters, base_id + rep * iters * R)
+        a, b = ht.dump(), dt.dump()
+        assert len(a["depth"]) == len(b["depth"]), (len(a["depth"]), len(b["depth"]))
+        for k in ("depth", "move", "n_children", "sims", "size"):
+            assert (a[k] == b[k]).all(), (k, np.flatnonzero(a[k] != b[k])[:8])
+        assert a["score"].tobytes() == b["score"].tobytes()
+        assert ht.best_move() == dt.best_move()
+    info = dt.info()
+    ht.close(); dt.close(); be.close()
+    return info
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("R,K,flushes", [(4, 16, 12), (16, 1024, 6), (16, 4096, 5), (256, 256, 5)])
+def test_device_tree_with_one_flush_in_flight_equals_host_tree_on_gpu(host, R, K, flushes):
+    info = compare_gpu_overlapped(host, m.quoridor_opening(), R, K, flushes)
+    assert info["flags"] == 0
+
+
 def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0):
     """device tree vs host tree (both playing their rollouts on the GPU, same Philox ids): identical after every grow"""
     be = m.RolloutBackend(0, m.DEFAULT_SEED)

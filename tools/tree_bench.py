@@ -30,6 +30,16 @@ def main():
         # device-resident tree: one warm-up grow (first-touch of the pool, kernel load), then the timed search from scratch
         for rep in range(2):
             dt = m.DeviceTree(be, root, R, K, policy=a.policy)
+            dt.set_overlap(True)
+            t0 = time.perf_counter()
+            dt.grow(iters, 1 << 42)
+            wall = time.perf_counter() - t0
+            info = dt.info()
+            dt.close()
+        row["device_tree_1_in_flight"] = {"wall_ms_per_flush": 1e3 * wall / a.flushes, "rollouts_per_sec": iters * R / wall, "iterations_per_sec": iters / wall,
+                                          "nodes_used": info["nodes_used"]}
+        for rep in range(2):
+            dt = m.DeviceTree(be, root, R, K, policy=a.policy)
             t0 = time.perf_counter()
             dt.grow(iters, 1 << 42)
             wall = time.perf_counter() - t0
@@ -41,7 +51,7 @@ def main():
                               "deepest_level": info["deepest_level"], "exact_evals": info["exact_evals"],
                               "host_share": max(0.0, 1.0 - (info["ms_select"] + info["ms_rollout"] + info["ms_backprop"]) / (1e3 * wall))}
         if not a.no_host:
-            for mode, overlap in (("host_tree_sync", 0), ("host_tree_2_in_flight", 2)):
+            for mode, overlap in (("host_tree_sync", 0), ("host_tree_1_in_flight", 1), ("host_tree_2_in_flight", 2)):
                 for rep in range(2):
                     host.mcts_host_set_next_rollout_id(1 << 42)
                     ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, policy=a.policy)
@@ -54,7 +64,8 @@ def main():
                     ht.close()
                 row[mode] = {"wall_ms_per_flush": 1e3 * wall / a.flushes, "rollouts_per_sec": iters * R / wall, "iterations_per_sec": iters / wall,
                              "host_share": (tot - backend) / tot}
-            row["speedup_vs_host_sync"] = row["host_tree_sync"]["wall_ms_per_flush"] / row["device_tree"]["wall_ms_per_flush"]
+            row["speedup_sync"] = row["host_tree_sync"]["wall_ms_per_flush"] / row["device_tree"]["wall_ms_per_flush"]
+            row["speedup_1_in_flight"] = row["host_tree_1_in_flight"]["wall_ms_per_flush"] / row["device_tree_1_in_flight"]["wall_ms_per_flush"]
         out.append(row)
         print(json.dumps(row), flush=True)
     be.close()
