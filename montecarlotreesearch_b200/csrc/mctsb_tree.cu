@@ -30,7 +30,7 @@ constexpr int TREE_WARPS = TREE_THREADS / 32;
 // playouts of the current one are running (mctsb_tree_set_overlap), and all its CTAs stay resident for the grid barrier.
 constexpr int SELECT_THREADS = 32;
 
-__global__ void __launch_bounds__(SELECT_THREADS) tree_select_kernel(TreeCtx t, uint32_t n, mctsb_qstate *leaf_states) {
+__global__ void __launch_bounds__(SELECT_THREADS, 16) tree_select_kernel(TreeCtx t, uint32_t n, mctsb_qstate *leaf_states) {
     cg::grid_group grid = cg::this_grid();
     __shared__ TreeWarpSmem wsm[1];
     const int lane = threadIdx.x & 31, wib = 0;

@@ -241,7 +241,7 @@ struct TreeWarpSmem {
 struct TreeSteps { uint32_t start, ne, count; unsigned long long n0; int nc; bool p1; };
 
 template <int NS>
-LS_NOINLINE void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, const TreeSteps st) {
+LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, const TreeSteps st) {
     const uint32_t R = t.R;
     const double Rd = (double)R;
     const bool p1 = st.p1;
@@ -260,7 +260,6 @@ LS_NOINLINE void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int la
     float coef_lane = 0.0f;
     double lp_lane = 0.0;
     uint32_t my_choice = 0;
-    int prev = -1;                                         // the child picked by the step before (-1: none yet)
     const unsigned long long m0 = st.n0 / R;
     const bool on_grid = m0 * R == st.n0;
     LS_UNROLL1
@@ -270,18 +269,6 @@ LS_NOINLINE void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int la
             const float np = (float)(st.n0 + (unsigned long long)(j + (uint32_t)lane) * R);
             coef_lane = t.c > 0 ? cf * TR_FSQRT(TR_LOGF(np)) : 0.0f;
             lp_lane = t.c > 0 ? tr_log_parent(t, st.n0, m0, on_grid, j + (uint32_t)lane) : 0.0;    // the exact ln N, should a tie need it
-        }
-        // in the shadow of this step's ranking pass: the terms of the child picked last after one more pick (every lane
-        // computes them, the owner keeps them)
-        if (prev >= 0) {
-            float nex, nis;
-            tr_rank_terms(W.sc[prev], W.vis[prev] + Rd, (double)W.vq[prev] + Rd, p1, nex, nis);
-            const bool own = (prev & 31) == lane;
-            switch (prev >> 5) {
-#define TR_CASE(q) case q: if (q < NS) { exn[q < NS ? q : 0] = own ? nex : exn[q < NS ? q : 0]; isn[q < NS ? q : 0] = own ? nis : isn[q < NS ? q : 0]; } break;
-                TR_CASE(0) TR_CASE(1) TR_CASE(2) TR_CASE(3) TR_CASE(4) TR_CASE(5) TR_CASE(6)
-#undef TR_CASE
-            }
         }
         int pick;                                          // child index
         if (nc == 1) pick = 0;
@@ -337,16 +324,18 @@ LS_NOINLINE void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int la
                 }
             }
         }
-        // the picked child carries R more simulations in flight: its owner lane swaps the prepared terms in and keeps the books
-        {
-            const bool own = (pick & 31) == lane;
+        // the picked child carries R more simulations in flight: its owner lane swaps the prepared terms in, keeps the
+        // books and prepares the terms of the pick after this one
+        if ((pick & 31) == lane) {
+            const uint32_t nvq = W.vq[pick] + R; const double nvis = W.vis[pick] + Rd;
+            float nex, nis;
+            tr_rank_terms(W.sc[pick], nvis + Rd, (double)nvq + Rd, p1, nex, nis);
+            W.vq[pick] = nvq; W.vis[pick] = nvis; W.cnt[pick]++;
             switch (pick >> 5) {
-#define TR_CASE(q) case q: if (q < NS) { ex[q < NS ? q : 0] = own ? exn[q < NS ? q : 0] : ex[q < NS ? q : 0]; is[q < NS ? q : 0] = own ? isn[q < NS ? q : 0] : is[q < NS ? q : 0]; } break;
+#define TR_CASE(q) case q: if (q < NS) { ex[q < NS ? q : 0] = exn[q < NS ? q : 0]; is[q < NS ? q : 0] = isn[q < NS ? q : 0]; exn[q < NS ? q : 0] = nex; isn[q < NS ? q : 0] = nis; } break;
                 TR_CASE(0) TR_CASE(1) TR_CASE(2) TR_CASE(3) TR_CASE(4) TR_CASE(5) TR_CASE(6)
 #undef TR_CASE
             }
-            if (own) { W.vq[pick] += R; W.vis[pick] += Rd; W.cnt[pick]++; }
-            prev = pick;
         }
         if ((int)rel == lane) my_choice = (uint32_t)pick;
         if (rel == 31u || j + 1 == st.count) {             // 32 choices at a time go to memory
