@@ -367,9 +367,10 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
     TreeCtl ctl;
     int s = read_ctl(t, &ctl);
     if (s != MCTSB_OK) return s;
-    if (ctl.error & (TR_ERR_POOL | TR_ERR_ITEMS | TR_ERR_DEPTH)) {
-        snprintf(b->cuda_err, sizeof b->cuda_err, "device tree: %s%s%s", (ctl.error & TR_ERR_POOL) ? "node pool exhausted " : "",
-                 (ctl.error & TR_ERR_DEPTH) ? "selection path deeper than the level buffers " : "", (ctl.error & TR_ERR_ITEMS) ? "item list full" : "");
+    if (ctl.error & (TR_ERR_POOL | TR_ERR_ITEMS | TR_ERR_DEPTH | TR_ERR_COUNT)) {
+        snprintf(b->cuda_err, sizeof b->cuda_err, "device tree: %s%s%s%s", (ctl.error & TR_ERR_POOL) ? "node pool exhausted " : "",
+                 (ctl.error & TR_ERR_DEPTH) ? "selection path deeper than the level buffers " : "", (ctl.error & TR_ERR_ITEMS) ? "item list full " : "",
+                 (ctl.error & TR_ERR_COUNT) ? "a node has more than 2^31 simulations" : "");
         return MCTSB_ERR_TREE_FULL;
     }
     return MCTSB_OK;

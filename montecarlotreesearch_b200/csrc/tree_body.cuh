@@ -47,6 +47,8 @@ static inline uint32_t tr_emu_add32(uint32_t *p, uint32_t v) { uint32_t o = *p; 
 #define TR_REDUCE_MAXU(v) simt_or_self_maxu((uint32_t)(v), __LINE__)
 #define TR_FRSQRT(x) (1.0f / sqrtf(x))
 #define TR_FDIV(a, b) ((a) / (b))
+#define TR_HILO2D(h, l) tr_emu_hilo2d((h), (l))
+static inline double tr_emu_hilo2d(uint32_t h, uint32_t l) { uint64_t b = ((uint64_t)h << 32) | l; double x; memcpy(&x, &b, 8); return x; }
 #define TR_DHI(x) tr_emu_dhi(x)
 #define TR_DLO(x) tr_emu_dlo(x)
 static inline uint32_t tr_emu_dhi(double x) { uint64_t b; memcpy(&b, &x, 8); return (uint32_t)(b >> 32); }
@@ -70,6 +72,7 @@ static inline float tr_emu_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
 #define TR_REDUCE_MAXU(v) __reduce_max_sync(0xffffffffu, (unsigned)(v))
 #define TR_FRSQRT(x) rsqrtf(x)
 #define TR_FDIV(a, b) __fdividef((a), (b))
+#define TR_HILO2D(h, l) __hiloint2double((int)(h), (int)(l))
 #define TR_DHI(x) ((uint32_t)__double2hiint(x))
 #define TR_DLO(x) ((uint32_t)__double2loint(x))
 #define TR_FSQRT(x) __fsqrt_rn(x)
@@ -85,11 +88,13 @@ static inline float tr_emu_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
 namespace mctsb {
 
 static constexpr float TR_RANK_MARGIN = 3e-6f;
+static constexpr double TR_RANK_MARGIN2 = 1e-11;    // second (double) ranking pass: 1000 x its error bound
 static constexpr int TR_SLOTS = 7;                  // children per lane: 7 * 32 = 224 >= MCTSB_Q_NUM_MOVES
 static constexpr int TR_MAX_LEVELS = 128;           // deepest selection path of one flush
 static constexpr uint16_t TR_UNLISTED = 0xffffu;    // n_moves of a node whose move list has not been asked for yet
 enum { TR_FLAG_TERMINAL = 1 };
-enum { TR_ERR_POOL = 1, TR_ERR_ITEMS = 2, TR_ERR_DEPTH = 4, TR_ERR_LOG = 8 };   // TR_ERR_LOG is informational: ln N taken from the device's log()
+enum { TR_ERR_POOL = 1, TR_ERR_ITEMS = 2, TR_ERR_DEPTH = 4, TR_ERR_LOG = 8, TR_ERR_COUNT = 16 };   // COUNT: a child with >= 2^31 simulations
+//   // TR_ERR_LOG is informational: ln N taken from the device's log()
 
 // Node pool, structure of arrays over node ids: the children of a node are `n_moves` consecutive ids reserved when
 // the node is first expanded, so a warp reads the statistics of all children of a node in coalesced runs.
@@ -144,22 +149,16 @@ LS_NOINLINE double tr_uct_exact(double score, double visits, double virt, bool p
     return d_add(exploit, d_mul(c, TR_DSQRT(d_div(log_parent, visits))));
 }
 
-// what the ranking pass keeps per child: the exploitation term as the side choosing here sees it, and n^-1/2.
-// Error budget of the float value a = ex + coef * is against the exact double, relative to (1 + a), with 2-ulp float
-// division and reciprocal square root, a correctly rounded square root and a 1-ulp logf:
-//   ex   : s, n rounded to float (2 x 6e-8) + division 2.4e-7 (+ 6e-8 for 1 - q)        <= 4.2e-7
-//   is   : n rounded (3e-8) + rsqrt 2.4e-7                                             <= 2.7e-7  (relative)
-//   coef : logf 1.2e-7, sqrt halves it + 6e-8, c rounded 6e-8, product 6e-8            <= 2.4e-7  (relative)
-//   a    : 4.2e-7 + (2.7e-7 + 2.4e-7 + 6e-8) * coef*is/(1+a) + 6e-8                     <= 1.05e-6
-// Two values can therefore swap places only when they are closer than 2.1e-6 * (1 + a); the candidate test keeps
+// Error budget of the ranking pass.  Its value of a child is a = ex + coef * is in float, ex = wins / n (wins = the
+// chooser's wins among the finished simulations, n = finished + in flight), is = n^-1/2, coef = c sqrt(ln N); against
+// the reference's double expression, relative to (1 + a):
+//   ex   : wins, n rounded to float (2 x 6e-8) + reciprocal 1.2e-7 + product 6e-8          <= 3.0e-7
+//   is   : n rounded (3e-8) + rsqrt.approx 2.4e-7                                         <= 2.7e-7  (relative)
+//   coef : logf 1.2e-7, sqrt halves it + 6e-8, c rounded 6e-8, product 6e-8               <= 2.4e-7  (relative)
+//   a    : 3.0e-7 + (2.7e-7 + 2.4e-7 + 6e-8) * coef*is/(1+a) + 6e-8                        <= 0.93e-6
+// Two values can therefore swap places only when they are closer than 1.9e-6 * (1 + a); the candidate test keeps
 // everything within TR_RANK_MARGIN = 3e-6 * (1 + amax) of the float maximum (the host tree, whose ranking terms are
 // rounded from doubles, uses 1e-5: any margin above the error bound selects the same child).
-LS_DEV void tr_rank_terms(double score, double visits, double virt, bool p1, float &exploit, float &inv_sqrt) {
-    const float s = (float)(p1 ? score : score + virt), n = (float)visits;
-    const float q = TR_FDIV(s, n);
-    exploit = p1 ? q : 1.0f - q;
-    inv_sqrt = TR_FRSQRT(n);
-}
 
 // ln N of a step: N = n0 + j*R; when n0 is a multiple of R (always, in a tree grown with one R) the host's table
 // has it at m0 + j
@@ -229,36 +228,93 @@ LS_DEV void tr_list_moves(const QState &s, int lane, uint64_t &lh, uint64_t &lv)
 struct TreeWarpSmem {
     double sc[32 * TR_SLOTS], vis[32 * TR_SLOTS];       // per child: score, simulations finished + in flight
     uint32_t vq[32 * TR_SLOTS], cnt[32 * TR_SLOTS];     // simulations in flight, descents handed to the child by this item
+    uint32_t real[32 * TR_SLOTS];                       // finished simulations (constant while the item is processed)
     uint32_t cursor[32 * TR_SLOTS];                     // hand-down: next free place of the child's list
 };
 #if LS_WARP == 32
 // ---- the selection steps of one item: descents ne .. count-1 pick a child each, in order.  NS = slots in use ------
-// Per child two floats in registers: ex = exploitation term as the side choosing here sees it, is = n^-1/2 (missing
-// children: ex = -1, is = 0, so their value is -1 and they never win).  exn / isn = the same terms after ONE MORE pick:
-// a pick swaps them in at once, and the terms after the pick that follows are computed in the shadow of the next
-// step's ranking pass, off the step-to-step critical path.  The exact statistics (read on ties, updated for the
-// picked child) live in shared memory.
+// One step = one float multiply-add per child, a warp maximum, a vote.  Everything the step-to-step chain needs of a
+// child lives in registers of its owner lane (child i: lane i % 32, slot i / 32), indexed statically:
+//   ex, is       exploitation term as the side choosing here sees it, and n^-1/2 (a missing child: -1 and 0 — its
+//                value is -1 and it never wins).  Simulations in flight count as losses for the side choosing, so
+//                the numerator of ex is a CONSTANT of the flush: the chooser's wins among the finished simulations
+//                (score for the first player, finished - score for the second); only n moves.
+//   rcpn, rsqn   1/(n+R) and (n+R)^-1/2, what a pick swaps in: the special-function unit delivered them after the
+//                pick before, nobody waits for them
+//   nf2          float(n + 2R), converted after the pick before: the operand of the next pair of reciprocals
+//   nint         n as an integer (finished + in flight; < 2^31, checked)
+// so a pick costs its owner two multiplies, two reciprocal issues, one conversion issue and an add — no memory, no
+// double, nothing to wait for.  The exact statistics of shared memory (W.vis, W.vq) are brought up to date from the
+// registers only when a tie needs them, and W.cnt once at the end.
 struct TreeSteps { uint32_t start, ne, count; unsigned long long n0; int nc; bool p1; };
+
+LS_DEV float tr_rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return 1.0f / x;
+#endif
+}
+LS_DEV float tr_rsq(float x) {
+#if defined(__CUDA_ARCH__)
+    float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+// double reciprocal and reciprocal square root to a few ulp, without the IEEE slow paths (second ranking pass)
+LS_DEV double tr_drcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double r; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+    r = __fma_rn(r, __fma_rn(-x, r, 1.0), r);
+    return r;
+#else
+    return 1.0 / x;
+#endif
+}
+LS_DEV double tr_drsq(double x) {
+#if defined(__CUDA_ARCH__)
+    double r; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    const double hx = 0.5 * x;
+    r = __fma_rn(r, __fma_rn(-hx * r, r, 0.5), r);
+    r = __fma_rn(r, __fma_rn(-hx * r, r, 0.5), r);
+    return r;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
 
 template <int NS>
 LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, const TreeSteps st) {
     const uint32_t R = t.R;
-    const double Rd = (double)R;
     const bool p1 = st.p1;
     const int nc = st.nc;
-    float ex[NS], is[NS], exn[NS], isn[NS];
+    float ex[NS], is[NS], rcpn[NS], rsqn[NS], nf2[NS], wf[NS];
+    uint32_t nint[NS];
+    bool too_big = false;
 #pragma unroll
     for (int q = 0; q < NS; q++) {
         const int i = lane + 32 * q;
-        ex[q] = -1.0f; is[q] = 0.0f; exn[q] = -1.0f; isn[q] = 0.0f;
+        ex[q] = -1.0f; is[q] = 0.0f; rcpn[q] = 0.0f; rsqn[q] = 0.0f; nf2[q] = 1.0f; wf[q] = 0.0f; nint[q] = 0u;
         if (i < nc) {
-            tr_rank_terms(W.sc[i], W.vis[i], (double)W.vq[i], p1, ex[q], is[q]);
-            tr_rank_terms(W.sc[i], W.vis[i] + Rd, (double)W.vq[i] + Rd, p1, exn[q], isn[q]);
+            const double vis = W.vis[i], sc = W.sc[i];
+            too_big = too_big || !(vis < 2147483648.0 - 3.0 * (double)R * (double)st.count);
+            nint[q] = (uint32_t)vis;
+            const uint32_t real = nint[q] - W.vq[i];                 // finished simulations
+            W.real[i] = real; W.cnt[i] = nint[q];                    // W.cnt holds n at the start until the end of the loop
+            wf[q] = (float)(p1 ? sc : (double)real - sc);            // the chooser's wins among them
+            const float nf = (float)nint[q];
+            ex[q] = wf[q] * tr_rcp(nf); is[q] = tr_rsq(nf);
+            const float nf1 = (float)(nint[q] + R);
+            rcpn[q] = tr_rcp(nf1); rsqn[q] = tr_rsq(nf1);
+            nf2[q] = (float)(nint[q] + 2u * R);
         }
     }
+    if (LS_BALLOT(too_big) != 0u && lane == 0) TR_ATOMIC_OR32(&t.ctl->error, (uint32_t)TR_ERR_COUNT);
     const float cf = (float)t.c;
     float coef_lane = 0.0f;
-    double lp_lane = 0.0;
+    double lp_lane = 0.0, cs_lane = 0.0;
     uint32_t my_choice = 0;
     const unsigned long long m0 = st.n0 / R;
     const bool on_grid = m0 * R == st.n0;
@@ -269,6 +325,7 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
             const float np = (float)(st.n0 + (unsigned long long)(j + (uint32_t)lane) * R);
             coef_lane = t.c > 0 ? cf * TR_FSQRT(TR_LOGF(np)) : 0.0f;
             lp_lane = t.c > 0 ? tr_log_parent(t, st.n0, m0, on_grid, j + (uint32_t)lane) : 0.0;    // the exact ln N, should a tie need it
+            cs_lane = t.c > 0 ? t.c * TR_DSQRT(lp_lane) : 0.0;
         }
         int pick;                                          // child index
         if (nc == 1) pick = 0;
@@ -293,46 +350,75 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
             const bool alone = (cm & (cm - 1u)) == 0u && (cm == 0u || mine == lowest);
             if (LS_BALLOT(!alone) == 0u) pick = lowest;    // one candidate: it is the maximum
             else {
-                // several children within the margin of the maximum.  Children with the same statistics have the same
-                // value: when all candidates are alike (leaves made by this flush, all of them R losses in flight) the
-                // first one wins without any arithmetic
-                LS_SYNCWARP();                              // the owners' updates of earlier steps are visible
+                // several children within the margin of the maximum: their exact statistics are needed
+#pragma unroll
+                for (int q = 0; q < NS; q++) {
+                    const int i = lane + 32 * q;
+                    if (i < nc) { W.vis[i] = (double)nint[q]; W.vq[i] = nint[q] - W.real[i]; }
+                }
+                LS_SYNCWARP();
+                // Children with the same statistics have the same value: when all candidates are alike (leaves made by
+                // this flush, all of them R losses in flight) the first one wins without any arithmetic
                 const double s0 = W.sc[lowest], v0 = W.vis[lowest]; const uint32_t q0 = W.vq[lowest];
                 bool same = true;
                 LS_UNROLL1
                 for (uint32_t mq = cm; mq; mq &= mq - 1u) { const int i = lane + 32 * (LS_FFS(mq) - 1); same = same && W.sc[i] == s0 && W.vis[i] == v0 && W.vq[i] == q0; }
                 if (LS_BALLOT(!same) == 0u) { pick = lowest; if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->ties_same, 1u); }
                 else {
-                    // the reference's expression decides, first strict maximum.  The values are >= 0, so the order of
-                    // the doubles is the order of their bit patterns: maximum of the high words, then of the low words
-                    // among those, then the lowest index among those
-                    const double lp = LS_SHFL(lp_lane, (int)rel);
-                    double bv = -1.0; int bi = 1 << 20;
+                    // second ranking pass, in double: wins / n + c sqrt(ln N) n^-1/2 with reciprocals good to a few ulp is
+                    // within 1e-14 (1 + v) of the reference's expression; a child that leads by TR_RANK_MARGIN2 is the maximum
+                    const double cs = LS_SHFL(cs_lane, (int)rel);
+                    double bv = -1.0; uint32_t cm2 = 0;
                     LS_UNROLL1
                     for (uint32_t mq = cm; mq; mq &= mq - 1u) {
-                        const int i = lane + 32 * (LS_FFS(mq) - 1);
-                        const double v = tr_uct_exact(W.sc[i], W.vis[i], (double)W.vq[i], p1, t.c, lp);
-                        if (v > bv) { bv = v; bi = i; }
+                        const int q = LS_FFS(mq) - 1, i = lane + 32 * q;
+                        const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
+                        const double v = wins * tr_drcp(n) + cs * tr_drsq(n);
+                        bv = v > bv ? v : bv;
                     }
-                    const bool has = bv >= 0.0;
-                    const uint32_t hi = has ? TR_DHI(bv) : 0u, mhi = TR_REDUCE_MAXU(hi);
-                    const bool top = has && hi == mhi;
-                    const uint32_t lo = top ? TR_DLO(bv) : 0u, mlo = TR_REDUCE_MAXU(lo);
-                    const int win = -TR_REDUCE_MAX(top && lo == mlo ? -bi : -(1 << 20));
-                    pick = win < nc ? win : 0;
-                    if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->exact_evals, 1u);
+                    // maximum over the warp: the values are >= 0, so the order of the doubles is the order of their bit patterns
+                    uint32_t hi = bv >= 0.0 ? TR_DHI(bv) : 0u; const uint32_t mhi = TR_REDUCE_MAXU(hi);
+                    uint32_t lo = bv >= 0.0 && hi == mhi ? TR_DLO(bv) : 0u; const uint32_t mlo = TR_REDUCE_MAXU(lo);
+                    const double vmax = TR_HILO2D(mhi, mlo), thr2 = vmax - TR_RANK_MARGIN2 * (1.0 + vmax);
+                    LS_UNROLL1
+                    for (uint32_t mq = cm; mq; mq &= mq - 1u) {
+                        const int q = LS_FFS(mq) - 1, i = lane + 32 * q;
+                        const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
+                        const double v = wins * tr_drcp(n) + cs * tr_drsq(n);
+                        if (v >= thr2) cm2 |= 1u << q;
+                    }
+                    const int mine2 = cm2 ? lane + 32 * (LS_FFS(cm2) - 1) : (1 << 20);
+                    const int lowest2 = -TR_REDUCE_MAX(-mine2);
+                    const bool alone2 = (cm2 & (cm2 - 1u)) == 0u && (cm2 == 0u || mine2 == lowest2);
+                    if (LS_BALLOT(!alone2) == 0u) pick = lowest2;
+                    else {
+                        // the reference's expression decides, first strict maximum: maximum of the high words, then of the low
+                        // words among those, then the lowest index among those
+                        const double lp = LS_SHFL(lp_lane, (int)rel);
+                        double ev = -1.0; int bi = 1 << 20;
+                        LS_UNROLL1
+                        for (uint32_t mq = cm2; mq; mq &= mq - 1u) {
+                            const int i = lane + 32 * (LS_FFS(mq) - 1);
+                            const double v = tr_uct_exact(W.sc[i], W.vis[i], (double)W.vq[i], p1, t.c, lp);
+                            if (v > ev) { ev = v; bi = i; }
+                        }
+                        const bool has = ev >= 0.0;
+                        hi = has ? TR_DHI(ev) : 0u; const uint32_t ehi = TR_REDUCE_MAXU(hi);
+                        const bool top = has && hi == ehi;
+                        lo = top ? TR_DLO(ev) : 0u; const uint32_t elo = TR_REDUCE_MAXU(lo);
+                        const int win = -TR_REDUCE_MAX(top && lo == elo ? -bi : -(1 << 20));
+                        pick = win < nc ? win : 0;
+                        if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->exact_evals, 1u);
+                    }
                 }
             }
         }
-        // the picked child carries R more simulations in flight: its owner lane swaps the prepared terms in, keeps the
-        // books and prepares the terms of the pick after this one
+        // the picked child carries R more simulations in flight: its owner lane swaps the prepared terms in and starts the
+        // reciprocals of the pick after this one
         if ((pick & 31) == lane) {
-            const uint32_t nvq = W.vq[pick] + R; const double nvis = W.vis[pick] + Rd;
-            float nex, nis;
-            tr_rank_terms(W.sc[pick], nvis + Rd, (double)nvq + Rd, p1, nex, nis);
-            W.vq[pick] = nvq; W.vis[pick] = nvis; W.cnt[pick]++;
             switch (pick >> 5) {
-#define TR_CASE(q) case q: if (q < NS) { ex[q < NS ? q : 0] = exn[q < NS ? q : 0]; is[q < NS ? q : 0] = isn[q < NS ? q : 0]; exn[q < NS ? q : 0] = nex; isn[q < NS ? q : 0] = nis; } break;
+#define TR_CASE(q) case q: if (q < NS) { const int z = q < NS ? q : 0; ex[z] = wf[z] * rcpn[z]; is[z] = rsqn[z]; rcpn[z] = tr_rcp(nf2[z]); rsqn[z] = tr_rsq(nf2[z]); \
+                                         nint[z] += R; nf2[z] = (float)(nint[z] + 2u * R); } break;
                 TR_CASE(0) TR_CASE(1) TR_CASE(2) TR_CASE(3) TR_CASE(4) TR_CASE(5) TR_CASE(6)
 #undef TR_CASE
             }
@@ -342,6 +428,12 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
             const uint32_t base = j - rel;
             if ((uint32_t)lane <= rel) t.choice[st.start + base + lane] = (uint8_t)my_choice;
         }
+    }
+    // how many descents every child received (the hand-down reads it)
+#pragma unroll
+    for (int q = 0; q < NS; q++) {
+        const int i = lane + 32 * q;
+        if (i < nc) W.cnt[i] = (nint[q] - W.cnt[i]) / R;
     }
 }
 
