@@ -352,10 +352,8 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
             else {
                 // several children within the margin of the maximum: their exact statistics are needed
 #pragma unroll
-                for (int q = 0; q < NS; q++) {
-                    const int i = lane + 32 * q;
-                    if (i < nc) { W.vis[i] = (double)nint[q]; W.vq[i] = nint[q] - W.real[i]; }
-                }
+                for (int q = 0; q < NS; q++)
+                    if ((cm >> q) & 1u) { const int i = lane + 32 * q; W.vis[i] = (double)nint[q]; W.vq[i] = nint[q] - W.real[i]; }
                 LS_SYNCWARP();
                 // Children with the same statistics have the same value: when all candidates are alike (leaves made by
                 // this flush, all of them R losses in flight) the first one wins without any arithmetic
@@ -369,8 +367,14 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
                     // within 1e-14 (1 + v) of the reference's expression; a child that leads by TR_RANK_MARGIN2 is the maximum
                     const double cs = LS_SHFL(cs_lane, (int)rel);
                     double bv = -1.0; uint32_t cm2 = 0;
+                    if (cm) {                              // the first candidate of the lane (most lanes have at most one)
+                        const int i = lane + 32 * (LS_FFS(cm) - 1);
+                        const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
+                        bv = wins * tr_drcp(n) + cs * tr_drsq(n);
+                    }
+                    const double v_first = bv;
                     LS_UNROLL1
-                    for (uint32_t mq = cm; mq; mq &= mq - 1u) {
+                    for (uint32_t mq = cm & (cm - 1u); mq; mq &= mq - 1u) {
                         const int q = LS_FFS(mq) - 1, i = lane + 32 * q;
                         const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
                         const double v = wins * tr_drcp(n) + cs * tr_drsq(n);
@@ -380,8 +384,9 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
                     uint32_t hi = bv >= 0.0 ? TR_DHI(bv) : 0u; const uint32_t mhi = TR_REDUCE_MAXU(hi);
                     uint32_t lo = bv >= 0.0 && hi == mhi ? TR_DLO(bv) : 0u; const uint32_t mlo = TR_REDUCE_MAXU(lo);
                     const double vmax = TR_HILO2D(mhi, mlo), thr2 = vmax - TR_RANK_MARGIN2 * (1.0 + vmax);
+                    if (cm && v_first >= thr2) cm2 = cm & (0u - cm);          // lowest set bit: the first candidate
                     LS_UNROLL1
-                    for (uint32_t mq = cm; mq; mq &= mq - 1u) {
+                    for (uint32_t mq = cm & (cm - 1u); mq; mq &= mq - 1u) {
                         const int q = LS_FFS(mq) - 1, i = lane + 32 * q;
                         const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
                         const double v = wins * tr_drcp(n) + cs * tr_drsq(n);
@@ -415,13 +420,15 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
         }
         // the picked child carries R more simulations in flight: its owner lane swaps the prepared terms in and starts the
         // reciprocals of the pick after this one
-        if ((pick & 31) == lane) {
-            switch (pick >> 5) {
-#define TR_CASE(q) case q: if (q < NS) { const int z = q < NS ? q : 0; ex[z] = wf[z] * rcpn[z]; is[z] = rsqn[z]; rcpn[z] = tr_rcp(nf2[z]); rsqn[z] = tr_rsq(nf2[z]); \
-                                         nint[z] += R; nf2[z] = (float)(nint[z] + 2u * R); } break;
-                TR_CASE(0) TR_CASE(1) TR_CASE(2) TR_CASE(3) TR_CASE(4) TR_CASE(5) TR_CASE(6)
-#undef TR_CASE
-            }
+        {
+            const bool own = (pick & 31) == lane;
+            const int qs = pick >> 5;
+#pragma unroll
+            for (int q = 0; q < NS; q++)
+                if (own && qs == q) {                      // straight-line, predicated: branches cost more than the six instructions
+                    ex[q] = wf[q] * rcpn[q]; is[q] = rsqn[q]; rcpn[q] = tr_rcp(nf2[q]); rsqn[q] = tr_rsq(nf2[q]);
+                    nint[q] += R; nf2[q] = (float)(nint[q] + 2u * R);
+                }
         }
         if ((int)rel == lane) my_choice = (uint32_t)pick;
         if (rel == 31u || j + 1 == st.count) {             // 32 choices at a time go to memory
