@@ -395,6 +395,36 @@ def main():
                 lat[str(size)] = {"median_ms": med, "min_ms": mn, "rollouts_per_sec": size / (1e-3 * med)}
             extra["call_latency"] = {"what": "synchronous mctsb_rollout_batch from the opening position (host buffers, H2D + kernel + D2H), host clock; 65536 = one configs[3] flush",
                                      "sizes": lat}
+            # the search around the path: MCTS from the opening, flushes of 4096 leaves x 16 playouts, the tree
+            # on the host (MCTS_tree, one thread) and resident on the device (mctsb_tree_*); one flush in flight in both
+            if not uni:
+                try:
+                    from montecarlotreesearch_b200.hosttree import Session, load as load_host
+                    hostlib = load_host()
+                    K, R, F = 4096, 16, 12
+                    rows = {}
+                    for name in ("host_tree", "device_tree"):
+                        for rep in range(2):                                   # the first search warms up, the second is timed
+                            if name == "host_tree":
+                                hostlib.mcts_host_set_next_rollout_id(9000 * (1 << 20))
+                                t = Session(hostlib, G, opening[0], rollouts_per_leaf=R, leaves_per_flush=K, device=local_rank, seed=m.DEFAULT_SEED)
+                                t.set_gpu_expand(True); t.set_overlap(1)
+                                t0 = time.perf_counter(); t.grow(K * F); w = time.perf_counter() - t0
+                                tot, backend_s = t.times()
+                                host_share = (tot - backend_s) / tot
+                                best = t.best_move(); t.close()
+                            else:
+                                t = m.DeviceTree(be, opening[0], R, K)
+                                t.set_overlap(True)
+                                t0 = time.perf_counter(); t.grow(K * F, 9000 * (1 << 20)); w = time.perf_counter() - t0
+                                host_share = max(0.0, 1.0 - 1e-3 * t.info()["ms_total"] / w)
+                                best = t.best_move(); t.close()
+                        rows[name] = {"ms_per_flush": 1e3 * w / F, "iterations_per_sec": K * F / w, "rollouts_per_sec": K * F * R / w,
+                                      "host_share_of_wall": host_share, "best_move_id": best}
+                    extra["tree_search"] = {"what": "MCTS from the opening, %d flushes of %d leaves x %d REF playouts, one flush in flight; same Philox ids, so both trees are the same tree (tests/test_device_tree.py)" % (F, K, R),
+                                            "same_best_move": rows["host_tree"]["best_move_id"] == rows["device_tree"]["best_move_id"], **rows}
+                except Exception as e:                                        # never lose the main line to the secondary block
+                    extra["tree_search"] = {"error": repr(e)}
         barrier()
 
     counters = be.counters()

@@ -271,8 +271,8 @@ typedef struct mctsb_tree_info {
     uint32_t exact_evals;          /* selections settled by the double-precision expression                       */
     uint32_t flags;                /* bit 3: some ln N came from the device's log() instead of the host's table   */
     uint64_t flushes, rollouts;    /* flushes played, playouts played                                             */
-    float    ms_select, ms_rollout, ms_backprop;   /* CUDA-event time of the three phases, summed over the last mctsb_tree_grow */
-    uint32_t reserved;
+    float    ms_select, ms_rollout, ms_backprop;   /* CUDA-event time of the three phases, summed over the last mctsb_tree_grow (synchronous mode) */
+    float    ms_total;             /* CUDA-event time from the first launch of the last mctsb_tree_grow to the end of its last one */
 } mctsb_tree_info;
 int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *root, int policy,
                       uint32_t rollouts_per_leaf, uint32_t max_leaves_per_flush, uint64_t max_nodes, double uct_c);

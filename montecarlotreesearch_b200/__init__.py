@@ -45,7 +45,7 @@ EXPORTS = [
 TREE_INFO_DTYPE = np.dtype([("root_sims", "<u8"), ("root_score", "<f8"), ("root_size", "<u4"), ("root_children", "<u4"),
                             ("nodes_used", "<u4"), ("deepest_level", "<u4"), ("exact_evals", "<u4"), ("flags", "<u4"),
                             ("flushes", "<u8"), ("rollouts", "<u8"), ("ms_select", "<f4"), ("ms_rollout", "<f4"),
-                            ("ms_backprop", "<f4"), ("reserved", "<u4")])
+                            ("ms_backprop", "<f4"), ("ms_total", "<f4")])
 SUBMIT_LEGAL = 1
 Q_GOOD_MAX = 144
 COMM_ID_BYTES = 128

@@ -94,7 +94,8 @@ struct mctsb_tree {
     cudaStream_t tree_stream;           // Selection / Backpropagation kernels in overlap mode (the playouts stay on the backend's stream)
     cudaEvent_t ev_selected[2], ev_played[2];
     uint64_t flushes, rollouts;
-    float ms[3];
+    float ms[3], ms_total;
+    cudaEvent_t ev_begin, ev_end;       // GPU span of the last grow
 };
 
 namespace {
@@ -225,6 +226,9 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&t->ev_played[i], cudaEventDisableTiming);
         if (e != cudaSuccess) { int s = fail(b, e, "cudaEventCreate"); mctsb_tree_destroy(t); return s; }
     }
+    e = cudaEventCreate(&t->ev_begin);
+    if (e == cudaSuccess) e = cudaEventCreate(&t->ev_end);
+    if (e != cudaSuccess) { int s = fail(b, e, "cudaEventCreate"); mctsb_tree_destroy(t); return s; }
     {
         int lo = 0, hi = 0;                              // the tree's kernels are short and on the critical path: highest priority
         cudaDeviceGetStreamPriorityRange(&lo, &hi);
@@ -248,6 +252,8 @@ int mctsb_tree_destroy(mctsb_tree *t) {
     cudaStreamSynchronize(t->b->stream);
     for (int i = 0; i < t->n_allocs; i++) cudaFree(t->allocs[i]);
     if (t->tree_stream) { cudaStreamSynchronize(t->tree_stream); cudaStreamDestroy(t->tree_stream); }
+    if (t->ev_begin) cudaEventDestroy(t->ev_begin);
+    if (t->ev_end) cudaEventDestroy(t->ev_end);
     for (int i = 0; i < 2; i++) { if (t->ev_selected[i]) cudaEventDestroy(t->ev_selected[i]); if (t->ev_played[i]) cudaEventDestroy(t->ev_played[i]); }
     delete t;
     return MCTSB_OK;
@@ -297,7 +303,9 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
     if (b->pending) return MCTSB_ERR_BUSY;
     TCK(cudaSetDevice(b->device));
     b->res_game = -1; b->res_leaves = 0;
-    t->ms[0] = t->ms[1] = t->ms[2] = 0.0f;
+    t->ms[0] = t->ms[1] = t->ms[2] = t->ms_total = 0.0f;
+    cudaStream_t first_stream = t->overlap ? t->tree_stream : b->stream;      // both modes start with a Selection and end with a Backpropagation
+    TCK(cudaEventRecord(t->ev_begin, first_stream));
     const uint32_t n_flushes = (iterations + leaves_per_flush - 1) / leaves_per_flush;
     int status = MCTSB_OK;
     uint32_t done = 0, f = 0;
@@ -364,6 +372,9 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
         if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
     }
     if (status != MCTSB_OK) return status;
+    TCK(cudaEventRecord(t->ev_end, first_stream));
+    TCK(cudaEventSynchronize(t->ev_end));
+    TCK(cudaEventElapsedTime(&t->ms_total, t->ev_begin, t->ev_end));
     TreeCtl ctl;
     int s = read_ctl(t, &ctl);
     if (s != MCTSB_OK) return s;
@@ -396,7 +407,7 @@ int mctsb_tree_get_info(mctsb_tree *t, mctsb_tree_info *info) {
         fprintf(stderr, "tree: steps %u (unique or alike %u, same-statistics ties %u, settled by the exact expression %u) | level ms: %.3f %.3f %.3f %.3f %.3f %.3f %.3f %.3f\n", ctl.steps,
                 ctl.steps - ctl.ties_same - ctl.exact_evals, ctl.ties_same, ctl.exact_evals, ctl.level_ns[0] * 1e-6, ctl.level_ns[1] * 1e-6, ctl.level_ns[2] * 1e-6,
                 ctl.level_ns[3] * 1e-6, ctl.level_ns[4] * 1e-6, ctl.level_ns[5] * 1e-6, ctl.level_ns[6] * 1e-6, ctl.level_ns[7] * 1e-6);
-    info->ms_select = t->ms[0]; info->ms_rollout = t->ms[1]; info->ms_backprop = t->ms[2];
+    info->ms_select = t->ms[0]; info->ms_rollout = t->ms[1]; info->ms_backprop = t->ms[2]; info->ms_total = t->ms_total;
     return MCTSB_OK;
 }
 

@@ -5,6 +5,7 @@
 #include "mcts.h"
 #include "Quoridor.h"
 #include "TicTacToe.h"
+#include "device_tree.h"
 #include "mctsb.h"
 #include "../csrc/qcore.cuh"
 #include <cstring>
@@ -272,6 +273,47 @@ int mcts_host_current_state(void *hs, void *packed_out) {
     HostSession *h = (HostSession *)hs;
     return h->tree->get_current_state()->gpu_pack(packed_out) ? 0 : -1;
 }
+
+// ---- the C++ face of the device-resident tree (MCTS_device_tree): same calls as a host-tree session ------------------
+struct DeviceTreeSession { std::unique_ptr<CudaRolloutBackend> backend; std::unique_ptr<MCTS_device_tree> tree; };
+
+void *mcts_host_dtree_create(const mctsb_qstate *root, int policy, int device, uint64_t seed, uint32_t rollouts_per_leaf,
+                             uint32_t leaves_per_flush, int overlap, uint64_t max_nodes, char *err, int err_cap) {
+    try {
+        mcts_set_verbose(false);
+        std::unique_ptr<DeviceTreeSession> h(new DeviceTreeSession());
+        h->backend.reset(new CudaRolloutBackend(device, seed));
+        MCTS_batching b; b.rollouts_per_leaf = rollouts_per_leaf; b.leaves_per_flush = leaves_per_flush; b.overlap = overlap != 0;
+        Quoridor_state start(*root, policy);
+        h->tree.reset(new MCTS_device_tree(start, h->backend.get(), b, max_nodes));
+        return h.release();
+    } catch (const std::exception &e) { comm_fail(e, err, err_cap); return NULL; }
+}
+void mcts_host_dtree_destroy(void *hs) { delete (DeviceTreeSession *)hs; }
+int mcts_host_dtree_grow(void *hs, int max_iter, double max_seconds, char *err, int err_cap) {
+    try { ((DeviceTreeSession *)hs)->tree->grow_tree(max_iter, max_seconds); return 0; }
+    catch (const std::exception &e) { return comm_fail(e, err, err_cap); }
+}
+int mcts_host_dtree_best_move(void *hs) {
+    try {
+        Quoridor_move *m = ((DeviceTreeSession *)hs)->tree->select_best_child();
+        if (m == NULL) return -1;
+        const int id = m->canonical_id();
+        delete m;
+        return id;
+    } catch (const std::exception &) { return -2; }
+}
+int mcts_host_dtree_advance(void *hs, int move_id) {
+    try {
+        DeviceTreeSession *h = (DeviceTreeSession *)hs;
+        Quoridor_move *m = Quoridor_move::from_canonical_id(move_id, ((const Quoridor_state *)h->tree->get_current_state())->whose_turn());
+        h->tree->advance_tree(m);
+        delete m;
+        return h->tree->get_current_state()->is_terminal() ? 1 : 0;
+    } catch (const std::exception &) { return -1; }
+}
+unsigned int mcts_host_dtree_size(void *hs) { return ((DeviceTreeSession *)hs)->tree->get_size(); }
+void mcts_host_dtree_print_stats(void *hs) { ((DeviceTreeSession *)hs)->tree->print_stats(); }
 
 // the Philox stream id the next flush of ANY tree in this process will start at (ids are never reused)
 uint64_t mcts_host_peek_rollout_id(void) { return next_rollout_ids(0); }

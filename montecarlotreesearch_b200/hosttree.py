@@ -43,6 +43,15 @@ def load():
     L.mcts_host_comm_init_rank.argtypes = [vp, vp, C.c_int, C.c_int, C.c_char_p, C.c_int]
     L.mcts_host_merge_root.argtypes = [vp, C.c_char_p, C.c_int]
     L.mcts_host_allreduce.argtypes = [vp, vp, C.c_int, C.c_char_p, C.c_int]
+    L.mcts_host_dtree_create.restype = vp
+    L.mcts_host_dtree_create.argtypes = [vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.c_uint64, C.c_char_p, C.c_int]
+    L.mcts_host_dtree_destroy.argtypes = [vp]
+    L.mcts_host_dtree_grow.argtypes = [vp, C.c_int, C.c_double, C.c_char_p, C.c_int]
+    L.mcts_host_dtree_best_move.argtypes = [vp]
+    L.mcts_host_dtree_advance.argtypes = [vp, C.c_int]
+    L.mcts_host_dtree_size.argtypes = [vp]
+    L.mcts_host_dtree_size.restype = C.c_uint
+    L.mcts_host_dtree_print_stats.argtypes = [vp]
     return L
 
 

@@ -29,6 +29,51 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 
+class DeviceTreeSession:
+    """The tree resident in HBM (mctsb_tree_*) behind the few calls play_game makes of a host-tree Session."""
+
+    def __init__(self, m, args, seed, device):
+        self.m = m
+        self.be = m.RolloutBackend(device, seed)
+        self.tree = m.DeviceTree(self.be, m.quoridor_opening(), args.rollouts_per_leaf, args.leaves_per_flush, max_nodes=args.device_tree_nodes)
+        if args.overlap:
+            self.tree.set_overlap(True)
+        self.R, self.next_id = args.rollouts_per_leaf, 0
+        self.wall, self.gpu_ms = 0.0, 0.0
+
+    def grow(self, iters):
+        t0 = time.perf_counter()
+        self.tree.grow(iters, self.next_id)
+        self.wall += time.perf_counter() - t0
+        self.next_id += iters * self.R
+        self.gpu_ms += self.tree.info()["ms_total"]
+
+    def best_move(self):
+        return self.tree.best_move()
+
+    def advance(self, mv):
+        self.tree.advance(mv)
+        s = self.tree.root_state()
+        return int(s["wx"]) == 8 or int(s["bx"]) == 0
+
+    def counters(self):
+        i = self.tree.info()
+        return i["flushes"], i["rollouts"]
+
+    def times(self):
+        """(seconds inside grow, seconds of them the GPU was busy with the tree's launches)"""
+        return self.wall, 1e-3 * self.gpu_ms
+
+    def current_state(self):
+        return self.tree.root_state()
+
+    def info(self):
+        return self.tree.info()
+
+    def close(self):
+        self.tree.close(); self.be.close()
+
+
 def play_game(tree, args, dist_ready, follow=None):
     """One game on `tree`.  follow = list of move ids to play instead of the tree's own choice (agreement rerun).
     Returns (moves, own_choices, terminal, seconds in grow, seconds in merge)."""
@@ -71,6 +116,9 @@ def main():
                     help="1 = every flush also returns its leaves' legal-move masks from the move-generation kernel (no host movegen); 0 = actions_to_try() on the CPU")
     ap.add_argument("--agreement", action="store_true", help="replay the game on one GPU at rank 0's seed and report per-move best-child agreement")
     ap.add_argument("--check-agreement-across-ranks", type=int, default=1)
+    ap.add_argument("--device-tree", type=int, default=0,
+                    help="1 = the tree itself lives on the GPU (mctsb_tree_*: Selection, Expansion and Backpropagation as kernels); one GPU only")
+    ap.add_argument("--device-tree-nodes", type=int, default=1 << 26, help="node pool of the device tree (86 bytes per node)")
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
 
@@ -96,6 +144,9 @@ def main():
     host = load()
 
     def new_tree(seed, device):
+        if args.device_tree:
+            assert world == 1, "the device-resident tree runs on one GPU (root-parallel merge: host tree)"
+            return DeviceTreeSession(m, args, seed, device)
         t = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
                     leaves_per_flush=args.leaves_per_flush, device=device, seed=seed)
         if args.overlap:
@@ -146,6 +197,7 @@ def main():
             "rollouts_total": rollouts_all, "rollouts_per_sec": rollouts_all / wall, "wall_s": wall,
             "leaves_per_flush": args.leaves_per_flush, "rollouts_per_leaf": args.rollouts_per_leaf,
             "flushes_in_flight": args.overlap, "gpu_expand": bool(args.gpu_expand),
+            "tree": "device (mctsb_tree_*: host share = time of grow the GPU was NOT busy with the tree's launches)" if args.device_tree else "host (MCTS_tree)",
             "flushes_rank0": flushes, "ms_per_flush": 1e3 * t_grow / max(1, flushes),
             "host_tree_share_of_search_time": (sec_total - sec_backend) / sec_total if sec_total > 0 else None,
             "search_seconds": sec_total, "backend_seconds": sec_backend,

@@ -263,3 +263,33 @@ def test_device_tree_full_pool_and_bad_arguments():
     t.advance(13)                                                              # never expanded: fresh root (mcts.cpp:149-152)
     assert t.info()["root_sims"] == 0 and int(t.root_state()["turn"]) == 1
     t.close(); be.close()
+
+
+@pytest.mark.gpu
+def test_cpp_device_tree_class_plays_the_host_trees_game(host):
+    """MCTS_device_tree (host/device_tree.h: MCTS_tree's interface over the C ABI) against MCTS_tree: same moves, same sizes"""
+    root = np.ascontiguousarray(m.quoridor_opening())
+    err = C.create_string_buffer(512)
+    games = []
+    for device_tree in (False, True):
+        host.mcts_host_set_next_rollout_id(1 << 44)
+        if device_tree:
+            h = host.mcts_host_dtree_create(root.ctypes.data, 0, 0, m.DEFAULT_SEED, 8, 512, 0, 1 << 22, err, 512)
+            assert h, err.value
+            grow = lambda n: host.mcts_host_dtree_grow(h, n, 1e9, err, 512)
+            best, advance, size = (lambda: host.mcts_host_dtree_best_move(h)), (lambda mv: host.mcts_host_dtree_advance(h, mv)), (lambda: host.mcts_host_dtree_size(h))
+        else:
+            t = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=8, leaves_per_flush=512)
+            grow = lambda n: (t.grow(n), 0)[1]
+            best, advance, size = t.best_move, (lambda mv: int(t.advance(mv))), (lambda: int(t.root_stats()["size"]))
+        moves = []
+        for ply in range(6):
+            assert grow(2048) == 0, err.value
+            moves.append((best(), size()))
+            assert advance(moves[-1][0]) == 0
+        games.append(moves)
+        if device_tree:
+            host.mcts_host_dtree_destroy(h)
+        else:
+            t.close()
+    assert games[0] == games[1], games
