@@ -36,25 +36,39 @@ __global__ void __launch_bounds__(SELECT_THREADS, 16) tree_select_kernel(TreeCtx
     const int lane = threadIdx.x & 31, wib = 0;
     const uint32_t gtid = blockIdx.x * SELECT_THREADS + threadIdx.x, gthreads = gridDim.x * SELECT_THREADS;
     const uint32_t warp = blockIdx.x, nwarps = gridDim.x;
+    // The flush in chunks of t.chunk descents, chunk c one level behind chunk c - 1: wave w = level w - c of every chunk c
+    // that has started and still has items.  All CTAs keep the same table of item ranges (read after the grid barrier).
+    __shared__ uint32_t cbegin[TR_MAX_CHUNKS], cend[TR_MAX_CHUNKS];
+    const uint32_t nch = (n + t.chunk - 1) / t.chunk;
     for (uint32_t d = gtid; d < n; d += gthreads) t.idx[d] = d;               // level 0: every descent starts at the root
-    if (gtid == 0) {
-        TreeItem r; r.node = t.ctl->root; r.start = 0; r.count = n; r.level = 0;
-        t.items[0] = r; *t.n_items = 1;
+    if (gtid < nch) {
+        const uint32_t c = gtid;
+        TreeItem r; r.node = t.ctl->root; r.start = c * t.chunk; r.count = n - r.start < t.chunk ? n - r.start : t.chunk; r.level = 0; r.n0 = 0; r.pad = 0;
+        t.items[(size_t)c * t.items_per_chunk] = r; t.n_items[c] = 1;
     }
+    if (lane < (int)TR_MAX_CHUNKS / 32 * 32) for (int c = lane; c < TR_MAX_CHUNKS; c += 32) { cbegin[c] = 0; cend[c] = c < (int)nch ? 1u : 0u; }
     grid.sync();
-    uint32_t begin = 0, end = 1, level = 0;
     unsigned long long t0 = 0;
     if (gtid == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    while (begin < end) {
-        for (uint32_t i = begin + warp; i < end; i += nwarps) tree_select_item(t, t.items[i], lane, wsm[wib]);
+    for (uint32_t wave = 0;; wave++) {
+        // this wave's work: items [cbegin[c], cend[c]) of every chunk c <= wave
+        const uint32_t started = wave + 1 < nch ? wave + 1 : nch;
+        uint32_t total = 0;
+        for (uint32_t c = 0; c < started; c++) total += cend[c] - cbegin[c];
+        if (total == 0 && wave >= nch) break;
+        for (uint32_t g = warp; g < total; g += nwarps) {
+            uint32_t c = 0, r = g;
+            while (r >= cend[c] - cbegin[c]) { r -= cend[c] - cbegin[c]; c++; }
+            tree_select_item(t, t.items[(size_t)c * t.items_per_chunk + cbegin[c] + r], lane, wsm[wib]);
+        }
         grid.sync();
         if (gtid == 0) {
             unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-            t.ctl->level_ns[level < 7 ? level : 7] += t1 - t0; t0 = t1;
+            t.ctl->level_ns[wave < 7 ? wave : 7] += t1 - t0; t0 = t1;
         }
-        begin = end; end = *(volatile uint32_t *)t.n_items; level++;
+        for (int c = lane; c < (int)started; c += 32) { cbegin[c] = cend[c]; cend[c] = *(volatile uint32_t *)(t.n_items + c); }
+        __syncwarp();
     }
-    if (gtid == 0 && level > t.ctl->depth_max) t.ctl->depth_max = level;
     for (uint32_t d = gtid; d < n; d += gthreads)                              // the rollout kernel's input, in selection order
         ls_store_qstate(leaf_states, d, tr_load_qstate(t.pool.state, (uint32_t)t.leaf_of[d]));
 }
@@ -66,11 +80,13 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_results_kernel(TreeCtx t, u
     tree_backprop_created(t, d, w);
 }
 
-__global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, const double *w) {
+// one launch per chunk, in order: a node's results are added in selection order, and a node is in several chunks
+__global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, const double *w, uint32_t chunk) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * TREE_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * TREE_WARPS;
-    const uint32_t n_items = *t.n_items;
-    for (uint32_t i = warp; i < n_items; i += nwarps) tree_backprop_item(t, t.items[i], lane, w);
+    const uint32_t n_items = t.n_items[chunk];
+    const TreeItem *items = t.items + (size_t)chunk * t.items_per_chunk;
+    for (uint32_t i = warp; i < n_items; i += nwarps) tree_backprop_item(t, items[i], lane, w);
 }
 
 int fail(mctsb_backend *b, cudaError_t e, const char *what) {
@@ -197,11 +213,14 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     TTRY(dev_alloc(t, &c.pool.flags, N));
     TTRY(dev_alloc(t, &c.ctl, 1));
     c.K = t->K; c.pool_cap = (uint32_t)max_nodes; c.R = t->R; c.c = uct_c;
-    c.items_cap = (uint32_t)(K * TR_MAX_LEVELS < (1u << 30) ? K * TR_MAX_LEVELS : (1u << 30));
+    // chunks of 512 descents (more for flushes beyond 64 x 512), a whole number of warps' worth each
+    c.chunk = (uint32_t)(K <= 512 * (size_t)TR_MAX_CHUNKS ? 512 : ((K + TR_MAX_CHUNKS - 1) / TR_MAX_CHUNKS + 31) / 32 * 32);
+    { const char *ev = getenv("MCTSB_TREE_CHUNK"); if (ev && atoi(ev) >= 32) { c.chunk = (uint32_t)atoi(ev) / 32 * 32; if ((K + c.chunk - 1) / c.chunk > TR_MAX_CHUNKS) c.chunk = (uint32_t)(((K + TR_MAX_CHUNKS - 1) / TR_MAX_CHUNKS + 31) / 32 * 32); } }
+    c.items_per_chunk = c.chunk * (uint32_t)TR_MAX_LEVELS;
     t->ctx[1] = c;
     for (int k = 0; k < 2; k++) {                      // per-flush arrays, one set per slot
         TreeCtx &f = t->ctx[k];
-        TTRY(dev_alloc(t, &f.n_items, 1)); TTRY(dev_alloc(t, &f.items, (size_t)f.items_cap));
+        TTRY(dev_alloc(t, &f.n_items, TR_MAX_CHUNKS)); TTRY(dev_alloc(t, &f.items, (size_t)f.items_per_chunk * ((K + f.chunk - 1) / f.chunk)));
         TTRY(dev_alloc(t, &f.idx, K * TR_MAX_LEVELS)); TTRY(dev_alloc(t, &f.choice, K)); TTRY(dev_alloc(t, &f.leaf_of, K)); TTRY(dev_alloc(t, &f.created, K));
         TTRY(dev_alloc(t, &t->d_leaf_states[k], K)); TTRY(dev_alloc(t, &t->d_sums[k], K)); TTRY(dev_alloc(t, &t->d_w[k], K));
     }
@@ -289,9 +308,10 @@ int launch_playouts(mctsb_tree *t, int slot, uint32_t n, uint64_t first_id) {   
 int launch_backprop(mctsb_tree *t, int slot, uint32_t n, cudaStream_t st) {
     mctsb_backend *b = t->b;
     tree_results_kernel<<<(n + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, st>>>(t->ctx[slot], n, t->d_sums[slot], t->d_w[slot]);
-    tree_backprop_kernel<<<t->select_blocks * 2, TREE_THREADS, 0, st>>>(t->ctx[slot], t->d_w[slot]);
+    const uint32_t nch = (n + t->ctx[slot].chunk - 1) / t->ctx[slot].chunk;
+    for (uint32_t c = 0; c < nch; c++) tree_backprop_kernel<<<t->select_blocks, TREE_THREADS, 0, st>>>(t->ctx[slot], t->d_w[slot], c);
     TCK(cudaGetLastError());
-    b->launches += 2;
+    b->launches += 1 + nch;
     return MCTSB_OK;
 }
 

@@ -43,6 +43,7 @@
 static inline uint32_t tr_emu_add32(uint32_t *p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 #define TR_ATOMIC_ADD32(p, v) tr_emu_add32((p), (v))
 #define TR_ATOMIC_OR32(p, v) do { *(p) |= (v); } while (0)
+#define TR_ATOMIC_MAX32(p, v) do { if (*(p) < (v)) *(p) = (v); } while (0)
 #define TR_HIBIT64(x) (63 - __builtin_clzll(x))
 #define TR_REDUCE_MAXU(v) simt_or_self_maxu((uint32_t)(v), __LINE__)
 #define TR_FRSQRT(x) (1.0f / sqrtf(x))
@@ -68,6 +69,7 @@ static inline float tr_emu_i2f(int i) { float x; memcpy(&x, &i, 4); return x; }
 #define TR_MATCH_ANY(v) __match_any_sync(0xffffffffu, (uint32_t)(v))
 #define TR_ATOMIC_ADD32(p, v) atomicAdd((p), (v))
 #define TR_ATOMIC_OR32(p, v) atomicOr((p), (v))
+#define TR_ATOMIC_MAX32(p, v) atomicMax((p), (v))
 #define TR_HIBIT64(x) (63 - __clzll((long long)(x)))
 #define TR_REDUCE_MAXU(v) __reduce_max_sync(0xffffffffu, (unsigned)(v))
 #define TR_FRSQRT(x) rsqrtf(x)
@@ -91,6 +93,7 @@ static constexpr float TR_RANK_MARGIN = 3e-6f;
 static constexpr double TR_RANK_MARGIN2 = 1e-11;    // second (double) ranking pass: 1000 x its error bound
 static constexpr int TR_SLOTS = 7;                  // children per lane: 7 * 32 = 224 >= MCTSB_Q_NUM_MOVES
 static constexpr int TR_MAX_LEVELS = 128;           // deepest selection path of one flush
+static constexpr int TR_MAX_CHUNKS = 64;            // chunks of one flush (see TreeCtx::chunk)
 static constexpr uint16_t TR_UNLISTED = 0xffffu;    // n_moves of a node whose move list has not been asked for yet
 enum { TR_FLAG_TERMINAL = 1 };
 enum { TR_ERR_POOL = 1, TR_ERR_ITEMS = 2, TR_ERR_DEPTH = 4, TR_ERR_LOG = 8, TR_ERR_COUNT = 16 };   // COUNT: a child with >= 2^31 simulations
@@ -111,7 +114,7 @@ struct TreePool {
     uint8_t *flags;
 };
 
-struct TreeItem { int32_t node; uint32_t start, count, level; };
+struct TreeItem { int32_t node; uint32_t start, count, level; uint32_t n0, pad; };   // n0 = the node's simulations (finished + in flight) before these descents; set by the parent, unused at the root
 
 struct TreeCtl {                      // lives in device memory
     uint32_t pool_top;                // next free node id
@@ -127,8 +130,15 @@ struct TreeCtl {                      // lives in device memory
 struct TreeCtx {                      // the pool and the per-flush arrays of ONE flush slot (two slots: a flush may be
     TreePool pool;                    // selected while the playouts of the one before are still running)
     TreeCtl *ctl;
-    uint32_t *n_items;                // items of this slot's flush (all levels)
-    TreeItem *items; uint32_t items_cap;
+    // A flush is selected in CHUNKS of `chunk` consecutive descents, staggered by one level: wave w of the selection
+    // kernel processes level w - c of chunk c for every chunk at once (the root takes its descents chunk by chunk, and
+    // while it plays chunk c its children already play chunk c - 1 ...).  A deep, narrow tree — the endgame, where most
+    // descents follow one line for twenty levels — then costs about K + depth * chunk steps instead of K * depth.
+    // The chunks are independent because a node's simulations in flight are kept by its PARENT (added when the
+    // descents are handed down), so an item reads nothing that an item of the same wave writes.
+    uint32_t *n_items;                // [TR_MAX_CHUNKS] items of every chunk of this slot's flush (all levels)
+    TreeItem *items; uint32_t items_per_chunk;   // chunk c owns items[c * items_per_chunk ...]
+    uint32_t chunk;                   // descents per chunk
     uint32_t *idx;                    // [TR_MAX_LEVELS][K]: idx[l*K + p] = descent number, lists of level l items
     uint8_t *choice;                  // [K] scratch: child picked by the step at list position p
     int32_t *leaf_of;                 // [K] node every descent ended at
@@ -229,6 +239,7 @@ struct TreeWarpSmem {
     double sc[32 * TR_SLOTS], vis[32 * TR_SLOTS];       // per child: score, simulations finished + in flight
     uint32_t vq[32 * TR_SLOTS], cnt[32 * TR_SLOTS];     // simulations in flight, descents handed to the child by this item
     uint32_t real[32 * TR_SLOTS];                       // finished simulations (constant while the item is processed)
+    uint32_t vis0[32 * TR_SLOTS];                       // simulations finished + in flight when the item began
     uint32_t cursor[32 * TR_SLOTS];                     // hand-down: next free place of the child's list
 };
 #if LS_WARP == 32
@@ -302,7 +313,7 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
             too_big = too_big || !(vis < 2147483648.0 - 3.0 * (double)R * (double)st.count);
             nint[q] = (uint32_t)vis;
             const uint32_t real = nint[q] - W.vq[i];                 // finished simulations
-            W.real[i] = real; W.cnt[i] = nint[q];                    // W.cnt holds n at the start until the end of the loop
+            W.real[i] = real; W.vis0[i] = nint[q];
             wf[q] = (float)(p1 ? sc : (double)real - sc);            // the chooser's wins among them
             const float nf = (float)nint[q];
             ex[q] = wf[q] * tr_rcp(nf); is[q] = tr_rsq(nf);
@@ -440,20 +451,21 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
 #pragma unroll
     for (int q = 0; q < NS; q++) {
         const int i = lane + 32 * q;
-        if (i < nc) W.cnt[i] = (nint[q] - W.cnt[i]) / R;
+        if (i < nc) W.cnt[i] = (nint[q] - W.vis0[i]) / R;
     }
 }
 
 LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane, TreeWarpSmem &W) {
     const TreePool &P = t.pool;
     uint32_t *cursor = W.cursor;
+    if (lane == 0 && it.level + 1 > t.ctl->depth_max) TR_ATOMIC_MAX32(&t.ctl->depth_max, it.level + 1);
     const int X = it.node;
     const uint32_t K = t.K, R = t.R;
     const uint32_t *my_idx = t.idx + (size_t)it.level * K + it.start;       // the descents that reach X, in order
     // --- terminal node: every descent ends here and re-scores it (mcts.cpp:38-40) ---
     if (P.flags[X] & TR_FLAG_TERMINAL) {
         for (uint32_t j = lane; j < it.count; j += 32) { const uint32_t d = my_idx[j]; t.leaf_of[d] = X; t.created[d] = 0; }
-        if (lane == 0) P.virt[X] += it.count * R;
+        if (lane == 0 && it.level == 0u) P.virt[X] += it.count * R;        // below the root the parent has already counted them
         return;
     }
     QState s;
@@ -462,7 +474,9 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     // everything the lanes read of X's header is read here, before any lane writes to it
     int n_moves = P.n_moves[X], first = P.first_child[X], nc = P.n_children[X];
     uint64_t lh = P.lh[X], lv = P.lv[X];
-    const unsigned long long n0 = P.sims[X] + P.virt[X];      // N of the first step; every step adds R
+    // N of the first step (every step adds R): the root reads its own counters; below it the parent wrote the number into
+    // the item when it handed the descents down — P.virt[X] may already hold the next chunk's descents
+    const unsigned long long n0 = it.level == 0u ? P.sims[X] + P.virt[X] : (unsigned long long)it.n0;
     LS_SYNCWARP();
     // --- move list on first use ---
     const uint32_t steps = q_step_mask(s);
@@ -473,7 +487,7 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     }
     if (n_moves == 0) {                                   // no legal move and not terminal: plays out where it stands
         for (uint32_t j = lane; j < it.count; j += 32) { const uint32_t d = my_idx[j]; t.leaf_of[d] = X; t.created[d] = 0; }
-        if (lane == 0) P.virt[X] += it.count * R;
+        if (lane == 0 && it.level == 0u) P.virt[X] += it.count * R;        // below the root the parent has already counted them
         return;
     }
     // --- the children's ids: n_moves consecutive ones, reserved at the first expansion ---
@@ -484,7 +498,7 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
         if ((unsigned long long)f + (unsigned)n_moves > t.pool_cap) {            // pool full: the descents stop here
             if (lane == 0) TR_ATOMIC_OR32(&t.ctl->error, (uint32_t)TR_ERR_POOL);
             for (uint32_t j = lane; j < it.count; j += 32) { const uint32_t d = my_idx[j]; t.leaf_of[d] = X; t.created[d] = 0; }
-            if (lane == 0) P.virt[X] += it.count * R;
+            if (lane == 0 && it.level == 0u) P.virt[X] += it.count * R;        // below the root the parent has already counted them
             return;
         }
         first = (int)f;
@@ -537,7 +551,7 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
             default: tr_select_steps<TR_SLOTS>(t, W, lane, st); break;
         }
     }
-    if (lane == 0) { P.n_children[X] = (uint16_t)nc; P.virt[X] += it.count * R; TR_ATOMIC_ADD32(&t.ctl->steps, it.count - ne); }
+    if (lane == 0) { P.n_children[X] = (uint16_t)nc; if (it.level == 0u) P.virt[X] += it.count * R; TR_ATOMIC_ADD32(&t.ctl->steps, it.count - ne); }
     const uint32_t n_down = it.count - ne;
     if (n_down == 0u) return;
     if (it.level + 1 >= (uint32_t)TR_MAX_LEVELS) {         // deeper than the level buffers: the descents stop at X
@@ -548,12 +562,12 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     // --- hand the descents down: child i receives the ordered sub-list of the steps that picked it ---
     uint32_t run = it.start + ne, n_new = 0;
     uint32_t off[TR_SLOTS];
-#pragma unroll
     uint32_t cnt[TR_SLOTS];
     LS_SYNCWARP();
 #pragma unroll
     for (int q = 0; q < TR_SLOTS; q++) {                   // exclusive prefix of cnt in child order
         cnt[q] = W.cnt[lane + 32 * q];
+        if (cnt[q] != 0u) P.virt[first + lane + 32 * q] += cnt[q] * R;      // the children's simulations in flight are kept here, by the parent
         uint32_t v = cnt[q];
         for (int o = 1; o < 32; o <<= 1) { const uint32_t u = LS_SHFL_UP(v, o); if (lane >= o) v += u; }
         off[q] = run + v - cnt[q];
@@ -577,10 +591,12 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
         LS_SYNCWARP();
     }
     // --- the next level's items ---
+    const uint32_t chunk_id = it.start / t.chunk;           // an item's list lies inside its chunk's range of descents
+    TreeItem *chunk_items = t.items + (size_t)chunk_id * t.items_per_chunk;
     uint32_t ibase = 0;
-    if (lane == 0) ibase = TR_ATOMIC_ADD32(t.n_items, n_new);
+    if (lane == 0) ibase = TR_ATOMIC_ADD32(t.n_items + chunk_id, n_new);
     ibase = LS_SHFL(ibase, 0);
-    if (ibase + n_new > t.items_cap) {                      // cannot happen with items_cap >= K * TR_MAX_LEVELS; stop here if it does
+    if (ibase + n_new > t.items_per_chunk) {                // cannot happen with items_per_chunk >= chunk * TR_MAX_LEVELS; stop here if it does
         if (lane == 0) TR_ATOMIC_OR32(&t.ctl->error, (uint32_t)TR_ERR_ITEMS);
         return;
     }
@@ -588,8 +604,8 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     for (int q = 0; q < TR_SLOTS; q++) {
         const uint32_t has = LS_BALLOT(cnt[q] != 0u);
         if (cnt[q] != 0u) {
-            TreeItem ni; ni.node = first + lane + 32 * q; ni.start = off[q]; ni.count = cnt[q]; ni.level = it.level + 1;
-            t.items[ibase + LS_POPC(has & ((1u << lane) - 1u))] = ni;
+            TreeItem ni; ni.node = first + lane + 32 * q; ni.start = off[q]; ni.count = cnt[q]; ni.level = it.level + 1; ni.n0 = W.vis0[lane + 32 * q]; ni.pad = 0u;
+            chunk_items[ibase + LS_POPC(has & ((1u << lane) - 1u))] = ni;
         }
         ibase += LS_POPC(has);
     }

@@ -40,13 +40,17 @@ class DeviceTreeSession:
             self.tree.set_overlap(True)
         self.R, self.next_id = args.rollouts_per_leaf, 0
         self.wall, self.gpu_ms = 0.0, 0.0
+        self.phase_ms = {"select": 0.0, "rollout": 0.0, "backprop": 0.0}
 
     def grow(self, iters):
         t0 = time.perf_counter()
         self.tree.grow(iters, self.next_id)
         self.wall += time.perf_counter() - t0
         self.next_id += iters * self.R
-        self.gpu_ms += self.tree.info()["ms_total"]
+        i = self.tree.info()
+        self.gpu_ms += i["ms_total"]
+        for k in self.phase_ms:                      # CUDA-event time of the three phases (measured in synchronous mode only)
+            self.phase_ms[k] += i["ms_" + k]
 
     def best_move(self):
         return self.tree.best_move()
@@ -172,6 +176,11 @@ def main():
     wall = time.perf_counter() - t0
     flushes, rollouts = tree.counters()
     sec_total, sec_backend = tree.times()
+    device_tree_info = None
+    if args.device_tree:
+        i = tree.info()
+        device_tree_info = {"ms_per_flush_by_phase": {k: v / max(1, flushes) for k, v in tree.phase_ms.items()} if not args.overlap else None,
+                            "nodes_used": i["nodes_used"], "deepest_level": i["deepest_level"], "exact_evals": i["exact_evals"], "flags": i["flags"]}
     final = tree.current_state()
     rollouts_all = float(tree.allreduce(np.array([float(rollouts)]))[0]) if dist is not None else float(rollouts)
     tree.close()
@@ -203,6 +212,7 @@ def main():
             "search_seconds": sec_total, "backend_seconds": sec_backend,
             "merge_ms_per_move": 1e3 * t_merge / max(1, len(moves)) if dist is not None else 0.0,
             "merge": "MCTS_tree::merge_root_stats -> mctsb_allreduce_root_stats (NCCL behind the C ABI); includes waiting for the slowest rank" if dist is not None else None,
+            "device_tree": device_tree_info,
             "agreement_with_1gpu_rerun": agreement,
             "move_ids": moves,
         }) + "\n").encode())

@@ -29,7 +29,7 @@ class EmuLib:
         L.emu_uni_lockstep.argtypes = [vp, C.c_int, C.c_uint32, C.c_uint64, C.c_uint64, vp, C.c_uint32, C.c_uint32, vp, vp, vp, vp, C.c_int, C.c_int, vp]
         if warp32:
             L.emu_tree_create.restype = vp
-            L.emu_tree_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32]
+            L.emu_tree_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32]
             L.emu_tree_destroy.argtypes = [vp]
             L.emu_tree_select.argtypes = [vp, C.c_int, C.c_uint32, vp]
             L.emu_tree_backprop.argtypes = [vp, C.c_int, vp]
@@ -173,11 +173,12 @@ class EmuLib:
 class EmuTree:
     """The device-resident tree (csrc/tree_body.cuh) on emulated 32-lane warps; the playouts of a flush are the caller's."""
 
-    def __init__(self, emu, root, R, K, pool_cap=1 << 18, c=1.41, logtab_n=1 << 16):
+    def __init__(self, emu, root, R, K, pool_cap=1 << 18, c=1.41, logtab_n=1 << 16, chunk=512):
         assert emu.lib.emu_warp_width() == 32
         self.lib, self.R, self.K = emu.lib, R, K
         r = np.ascontiguousarray(root, dtype=QSTATE_DTYPE)
-        self.h = self.lib.emu_tree_create(r.ctypes.data, R, K, pool_cap, c, logtab_n)
+        self.h = self.lib.emu_tree_create(r.ctypes.data, R, K, pool_cap, c, logtab_n, chunk)
+        assert self.h, "bad chunk size"
 
     def close(self):
         if self.h:

@@ -11,6 +11,7 @@
 #include "../../montecarlotreesearch_b200/csrc/quoridor_uni_lockstep_body.cuh"
 #include "../../montecarlotreesearch_b200/csrc/tree_body.cuh"
 #include <vector>
+#include <algorithm>
 #include <string.h>
 using namespace mctsb;
 
@@ -242,7 +243,7 @@ int emu_warp_width() { return LS_WARP; }
 #if defined(MCTSB_EMU_WARP32)
 struct EmuSlot {
     std::vector<TreeItem> items; std::vector<uint32_t> idx; std::vector<uint8_t> choice, created; std::vector<int32_t> leaf_of;
-    uint32_t n_items, n_last;
+    uint32_t n_items[TR_MAX_CHUNKS], n_last;
 };
 struct EmuTree {
     TreeCtx t[2]; TreeCtl ctl; EmuSlot slot[2];
@@ -251,19 +252,20 @@ struct EmuTree {
     std::vector<uint8_t> move, flags;
     std::vector<double> logtab;
 };
-struct EmuTreeLaunch { EmuTree *T; int slot; uint32_t begin, end; const double *w; TreeWarpSmem *wsm; };
+struct EmuTreeLaunch { EmuTree *T; int slot; std::vector<TreeItem> work; const double *w; TreeWarpSmem *wsm; };
 static void emu_tree_select_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
     const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
-    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_select_item(L->T->t[L->slot], L->T->slot[L->slot].items[i], lane, L->wsm[warp]);
+    for (size_t i = warp; i < L->work.size(); i += nwarps) tree_select_item(L->T->t[L->slot], L->work[i], lane, L->wsm[warp]);
 }
 static void emu_tree_backprop_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
     const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
-    for (uint32_t i = L->begin + warp; i < L->end; i += nwarps) tree_backprop_item(L->T->t[L->slot], L->T->slot[L->slot].items[i], lane, L->w);
+    for (size_t i = warp; i < L->work.size(); i += nwarps) tree_backprop_item(L->T->t[L->slot], L->work[i], lane, L->w);
 }
 
-void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t pool_cap, double c, uint32_t logtab_n) {
+void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t pool_cap, double c, uint32_t logtab_n, uint32_t chunk) {
+    if (chunk < 32 || (K + chunk - 1) / chunk > (uint32_t)TR_MAX_CHUNKS) return nullptr;
     EmuTree *T = new EmuTree();
     T->state.resize(pool_cap); T->lh.resize(pool_cap); T->lv.resize(pool_cap); T->score.resize(pool_cap); T->sims.resize(pool_cap);
     T->virt.resize(pool_cap); T->size.resize(pool_cap); T->parent.resize(pool_cap); T->first_child.resize(pool_cap);
@@ -272,13 +274,14 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
     for (uint32_t m = 0; m < logtab_n; m++) T->logtab[m] = log((double)((unsigned long long)m * R));
     for (int k = 0; k < 2; k++) {
         EmuSlot &S = T->slot[k];
-        S.items.resize((size_t)K * TR_MAX_LEVELS); S.idx.resize((size_t)K * TR_MAX_LEVELS); S.choice.resize(K); S.created.resize(K); S.leaf_of.resize(K);
-        S.n_items = 0; S.n_last = 0;
+        const uint32_t nch = (K + chunk - 1) / chunk;
+        S.items.resize((size_t)chunk * TR_MAX_LEVELS * nch); S.idx.resize((size_t)K * TR_MAX_LEVELS); S.choice.resize(K); S.created.resize(K); S.leaf_of.resize(K);
+        memset(S.n_items, 0, sizeof S.n_items); S.n_last = 0;
         TreeCtx &t = T->t[k];
         t.pool.state = T->state.data(); t.pool.lh = T->lh.data(); t.pool.lv = T->lv.data(); t.pool.score = T->score.data(); t.pool.sims = T->sims.data();
         t.pool.virt = T->virt.data(); t.pool.size = T->size.data(); t.pool.parent = T->parent.data(); t.pool.first_child = T->first_child.data();
         t.pool.n_children = T->n_children.data(); t.pool.n_moves = T->n_moves.data(); t.pool.move = T->move.data(); t.pool.flags = T->flags.data();
-        t.ctl = &T->ctl; t.n_items = &S.n_items; t.items = S.items.data(); t.items_cap = (uint32_t)S.items.size(); t.idx = S.idx.data(); t.choice = S.choice.data();
+        t.ctl = &T->ctl; t.n_items = S.n_items; t.items = S.items.data(); t.items_per_chunk = chunk * (uint32_t)TR_MAX_LEVELS; t.chunk = chunk; t.idx = S.idx.data(); t.choice = S.choice.data();
         t.leaf_of = S.leaf_of.data(); t.created = S.created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
         t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
     }
@@ -298,15 +301,27 @@ int emu_tree_select(void *h, int slot, uint32_t n, mctsb_qstate *leaf_states) {
     if (n == 0 || n > T->t[0].K || slot < 0 || slot > 1) return -1;
     EmuSlot &S = T->slot[slot];
     for (uint32_t d = 0; d < n; d++) S.idx[d] = d;
-    TreeItem r; r.node = T->ctl.root; r.start = 0; r.count = n; r.level = 0;
-    S.items[0] = r; S.n_items = 1;
+    const TreeCtx &t = T->t[slot];
+    const uint32_t nch = (n + t.chunk - 1) / t.chunk;
+    std::vector<uint32_t> cbegin(nch, 0), cend(nch, 1);
+    for (uint32_t c = 0; c < nch; c++) {
+        TreeItem r; r.node = T->ctl.root; r.start = c * t.chunk; r.count = n - r.start < t.chunk ? n - r.start : t.chunk; r.level = 0; r.n0 = 0; r.pad = 0;
+        S.items[(size_t)c * t.items_per_chunk] = r; S.n_items[c] = 1;
+    }
     std::vector<TreeWarpSmem> wsm(4);
     memset(wsm.data(), 0xa5, sizeof(TreeWarpSmem) * 4);
-    uint32_t begin = 0, end = 1;
-    while (begin < end) {
-        EmuTreeLaunch L{T, slot, begin, end, nullptr, wsm.data()};
-        simt::launch(1, 128, emu_tree_select_thread, &L);
-        begin = end; end = S.n_items;
+    // the waves of the selection kernel: level wave - c of every chunk c <= wave, all in one launch (their order inside
+    // the launch is whatever the fibers make of it — the items of a wave must be independent)
+    for (uint32_t wave = 0;; wave++) {
+        const uint32_t started = wave + 1 < nch ? wave + 1 : nch;
+        EmuTreeLaunch L{T, slot, {}, nullptr, wsm.data()};
+        for (uint32_t c = 0; c < started; c++)
+            for (uint32_t i = cbegin[c]; i < cend[c]; i++) L.work.push_back(S.items[(size_t)c * t.items_per_chunk + i]);
+        if (L.work.empty() && wave >= nch) break;
+        // reverse order: the later chunks' shallow items run BEFORE the earlier chunks' deep ones
+        std::reverse(L.work.begin(), L.work.end());
+        if (!L.work.empty()) simt::launch(1, 128, emu_tree_select_thread, &L);
+        for (uint32_t c = 0; c < started; c++) { cbegin[c] = cend[c]; cend[c] = S.n_items[c]; }
     }
     for (uint32_t d = 0; d < n; d++) leaf_states[d] = T->state[S.leaf_of[d]];
     S.n_last = n;
@@ -320,8 +335,13 @@ int emu_tree_backprop(void *h, int slot, const mctsb_leaf_sum *sums) {
     std::vector<double> w(S.n_last);
     for (uint32_t d = 0; d < S.n_last; d++) w[d] = tr_leaf_sum_to_double(sums[d].lo, sums[d].hi);
     for (uint32_t d = 0; d < S.n_last; d++) tree_backprop_created(T->t[slot], d, w.data());
-    EmuTreeLaunch L{T, slot, 0, S.n_items, w.data(), nullptr};
-    simt::launch(1, 128, emu_tree_backprop_thread, &L);
+    const TreeCtx &t = T->t[slot];
+    const uint32_t nch = (S.n_last + t.chunk - 1) / t.chunk;
+    for (uint32_t c = 0; c < nch; c++) {                   // chunk by chunk: a node's results are added in selection order
+        EmuTreeLaunch L{T, slot, {}, w.data(), nullptr};
+        for (uint32_t i = 0; i < S.n_items[c]; i++) L.work.push_back(S.items[(size_t)c * t.items_per_chunk + i]);
+        simt::launch(1, 128, emu_tree_backprop_thread, &L);
+    }
     return (int)T->ctl.error;
 }
 
@@ -354,7 +374,7 @@ int emu_tree_advance(void *h, int move_id) {            // the child that carrie
 }
 void emu_tree_stats(void *h, uint32_t *out4) {
     const EmuTree *T = (const EmuTree *)h;
-    out4[0] = T->ctl.pool_top; out4[1] = T->slot[0].n_items + T->slot[1].n_items; out4[2] = T->ctl.error; out4[3] = T->ctl.exact_evals;
+    out4[0] = T->ctl.pool_top; out4[1] = T->slot[0].n_items[0] + T->slot[1].n_items[0]; out4[2] = T->ctl.error; out4[3] = T->ctl.exact_evals;
 }
 #endif
 

@@ -31,7 +31,7 @@ def fake_sum(state_bytes, first_id, R):
     return a % (R << 29), b % ((R << 28) + 1)
 
 
-def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, c_checks=True):
+def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, chunk=64):
     """grow the host tree and the emulated device tree side by side; compare after every flush"""
     from tests.hostemu.emulib import EmuTree
     to_double = emu32.lib.emu_leaf_sum_to_double
@@ -53,7 +53,7 @@ def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, c_c
     base_id = 1 << 40
     host.mcts_host_set_next_rollout_id(base_id)
     ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, callback=cb)
-    dt = EmuTree(emu32, root, R, K)
+    dt = EmuTree(emu32, root, R, K, chunk=max(chunk, (K + 63) // 64 // 32 * 32 + 32))
     done = 0
     for f in range(flushes):
         n = K if not isinstance(flushes, list) else K
@@ -103,7 +103,7 @@ def test_emulated_device_tree_with_one_flush_in_flight(host, emu32):
         ht.set_overlap(1)
         tail = K // 2 + 1
         ht.grow(K * (flushes - 1) + tail)
-        dt = EmuTree(emu32, root, R, K)
+        dt = EmuTree(emu32, root, R, K, chunk=32)
         pending = None
         for f in range(flushes):
             n = K if f < flushes - 1 else tail
@@ -140,9 +140,10 @@ def test_leaf_sum_conversion_matches_the_abi_helper(emu32, port):
     assert to_double(0, 0) == 0.0
 
 
-@pytest.mark.parametrize("R,K,flushes", [(4, 1, 40), (4, 16, 12), (16, 256, 6), (1, 1024, 4)])
-def test_emulated_device_tree_equals_host_tree(host, emu32, R, K, flushes):
-    st, _ = drive_both(host, emu32, m.quoridor_opening(), R, K, flushes)
+@pytest.mark.parametrize("R,K,flushes,chunk", [(4, 1, 40, 32), (4, 16, 12, 32), (16, 256, 6, 64), (1, 1024, 4, 32), (1, 1024, 3, 512)])
+def test_emulated_device_tree_equals_host_tree(host, emu32, R, K, flushes, chunk):
+    """chunk = descents per chunk of the wavefront (the flush is selected in chunks staggered by one level)"""
+    st, _ = drive_both(host, emu32, m.quoridor_opening(), R, K, flushes, chunk=chunk)
     assert st["error"] == 0
 
 
