@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 16) tree_select_kernel(TreeCtx
         TreeItem r; r.node = t.ctl->root; r.start = c * t.chunk; r.count = n - r.start < t.chunk ? n - r.start : t.chunk; r.level = 0; r.n0 = 0; r.pad = 0;
         t.items[(size_t)c * t.items_per_chunk] = r; t.n_items[c] = 1;
     }
+    for (uint32_t k = gtid; k < nch * (uint32_t)TR_MAX_LEVELS; k += gthreads) t.level_items[k] = 0u;
     if (lane < (int)TR_MAX_CHUNKS / 32 * 32) for (int c = lane; c < TR_MAX_CHUNKS; c += 32) { cbegin[c] = 0; cend[c] = c < (int)nch ? 1u : 0u; }
     grid.sync();
     unsigned long long t0 = 0;
@@ -59,16 +60,18 @@ __global__ void __launch_bounds__(SELECT_THREADS, 16) tree_select_kernel(TreeCtx
         for (uint32_t g = warp; g < total; g += nwarps) {
             uint32_t c = 0, r = g;
             while (r >= cend[c] - cbegin[c]) { r -= cend[c] - cbegin[c]; c++; }
-            tree_select_item(t, t.items[(size_t)c * t.items_per_chunk + cbegin[c] + r], lane, wsm[wib]);
+            tree_select_item(t, t.items[(size_t)c * t.items_per_chunk + cbegin[c] + r], lane, wsm[wib], cend[c]);
         }
         grid.sync();
         if (gtid == 0) {
             unsigned long long t1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
             t.ctl->level_ns[wave < 7 ? wave : 7] += t1 - t0; t0 = t1;
         }
-        for (int c = lane; c < (int)started; c += 32) { cbegin[c] = cend[c]; cend[c] = *(volatile uint32_t *)(t.n_items + c); }
+        // chunk c closed level wave - c; its items of level wave - c + 1 were counted in a word nobody touches any more
+        for (int c = lane; c < (int)started; c += 32) { const uint32_t lvl = wave - (uint32_t)c + 1u; cbegin[c] = cend[c]; cend[c] += lvl < (uint32_t)TR_MAX_LEVELS ? *(volatile uint32_t *)(t.level_items + c * TR_MAX_LEVELS + lvl) : 0u; }
         __syncwarp();
     }
+    if (blockIdx.x == 0) for (int c = lane; c < (int)nch; c += 32) t.n_items[c] = cend[c];      // what Backpropagation walks
     for (uint32_t d = gtid; d < n; d += gthreads)                              // the rollout kernel's input, in selection order
         ls_store_qstate(leaf_states, d, tr_load_qstate(t.pool.state, (uint32_t)t.leaf_of[d]));
 }
@@ -221,7 +224,7 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     t->ctx[1] = c;
     for (int k = 0; k < 2; k++) {                      // per-flush arrays, one set per slot
         TreeCtx &f = t->ctx[k];
-        TTRY(dev_alloc(t, &f.n_items, TR_MAX_CHUNKS)); TTRY(dev_alloc(t, &f.items, (size_t)f.items_per_chunk * ((K + f.chunk - 1) / f.chunk)));
+        TTRY(dev_alloc(t, &f.n_items, TR_MAX_CHUNKS)); TTRY(dev_alloc(t, &f.level_items, (size_t)TR_MAX_CHUNKS * TR_MAX_LEVELS)); TTRY(dev_alloc(t, &f.items, (size_t)f.items_per_chunk * ((K + f.chunk - 1) / f.chunk)));
         TTRY(dev_alloc(t, &f.idx, K * TR_MAX_LEVELS)); TTRY(dev_alloc(t, &f.choice, K)); TTRY(dev_alloc(t, &f.leaf_of, K)); TTRY(dev_alloc(t, &f.created, K));
         TTRY(dev_alloc(t, &t->d_leaf_states[k], K)); TTRY(dev_alloc(t, &t->d_sums[k], K)); TTRY(dev_alloc(t, &t->d_w[k], K));
     }

@@ -136,7 +136,9 @@ struct TreeCtx {                      // the pool and the per-flush arrays of ON
     // descents follow one line for twenty levels — then costs about K + depth * chunk steps instead of K * depth.
     // The chunks are independent because a node's simulations in flight are kept by its PARENT (added when the
     // descents are handed down), so an item reads nothing that an item of the same wave writes.
-    uint32_t *n_items;                // [TR_MAX_CHUNKS] items of every chunk of this slot's flush (all levels)
+    uint32_t *n_items;                // [TR_MAX_CHUNKS] items of every chunk of this slot's flush (all levels; written when the selection ends)
+    uint32_t *level_items;            // [TR_MAX_CHUNKS][TR_MAX_LEVELS] items per chunk and level: a wave appends to the counters of the
+                                      // NEXT level while everybody reads the ones of the level just closed — never the same word
     TreeItem *items; uint32_t items_per_chunk;   // chunk c owns items[c * items_per_chunk ...]
     uint32_t chunk;                   // descents per chunk
     uint32_t *idx;                    // [TR_MAX_LEVELS][K]: idx[l*K + p] = descent number, lists of level l items
@@ -361,71 +363,68 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
             const bool alone = (cm & (cm - 1u)) == 0u && (cm == 0u || mine == lowest);
             if (LS_BALLOT(!alone) == 0u) pick = lowest;    // one candidate: it is the maximum
             else {
-                // several children within the margin of the maximum: their exact statistics are needed
+                // Several children within the margin of the maximum.  A candidate's exact statistics come from its owner's
+                // registers (n) and from the two constants of the flush in shared memory (score, finished simulations) —
+                // nothing to write, nothing to wait for.
+                bool settled = false;
+                pick = lowest;
+                {
+                    // this lane's first candidate (the one with the lowest index), and whether its other candidates are like it
+                    const int q1 = cm ? LS_FFS(cm) - 1 : 0;
+                    uint32_t n1 = 0u;
 #pragma unroll
-                for (int q = 0; q < NS; q++)
-                    if ((cm >> q) & 1u) { const int i = lane + 32 * q; W.vis[i] = (double)nint[q]; W.vq[i] = nint[q] - W.real[i]; }
-                LS_SYNCWARP();
-                // Children with the same statistics have the same value: when all candidates are alike (leaves made by
-                // this flush, all of them R losses in flight) the first one wins without any arithmetic
-                const double s0 = W.sc[lowest], v0 = W.vis[lowest]; const uint32_t q0 = W.vq[lowest];
-                bool same = true;
-                LS_UNROLL1
-                for (uint32_t mq = cm; mq; mq &= mq - 1u) { const int i = lane + 32 * (LS_FFS(mq) - 1); same = same && W.sc[i] == s0 && W.vis[i] == v0 && W.vq[i] == q0; }
-                if (LS_BALLOT(!same) == 0u) { pick = lowest; if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->ties_same, 1u); }
-                else {
-                    // second ranking pass, in double: wins / n + c sqrt(ln N) n^-1/2 with reciprocals good to a few ulp is
-                    // within 1e-14 (1 + v) of the reference's expression; a child that leads by TR_RANK_MARGIN2 is the maximum
-                    const double cs = LS_SHFL(cs_lane, (int)rel);
-                    double bv = -1.0; uint32_t cm2 = 0;
-                    if (cm) {                              // the first candidate of the lane (most lanes have at most one)
-                        const int i = lane + 32 * (LS_FFS(cm) - 1);
-                        const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
-                        bv = wins * tr_drcp(n) + cs * tr_drsq(n);
+                    for (int q = 0; q < NS; q++) n1 = q == q1 ? nint[q] : n1;
+                    const int i1 = cm ? mine : 0;
+                    const double sc1 = W.sc[i1]; const uint32_t real1 = W.real[i1];
+                    bool alike = true;
+#pragma unroll
+                    for (int q = 0; q < NS; q++)
+                        if (((cm >> q) & 1u) && q != q1) { const int i = lane + 32 * q; alike = alike && nint[q] == n1 && W.sc[i] == sc1 && W.real[i] == real1; }
+                    // children with the same statistics have the same value: when all candidates are alike (leaves made
+                    // by this flush, all of them R losses in flight) the first one wins without any arithmetic
+                    const int ol = lowest & 31;
+                    const double s0 = LS_SHFL(sc1, ol); const uint32_t n0c = LS_SHFL(n1, ol), r0 = LS_SHFL(real1, ol);
+                    if (LS_BALLOT(cm != 0u && !(alike && sc1 == s0 && n1 == n0c && real1 == r0)) == 0u) {
+                        settled = true;
+                        if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->ties_same, 1u);
+                    } else if (LS_BALLOT((cm & (cm - 1u)) != 0u) == 0u) {           // at most one candidate per lane (nearly always)
+                        // second ranking pass, in double: wins / n + c sqrt(ln N) n^-1/2 with reciprocals good to a few ulp
+                        // is within 1e-14 (1 + v) of the reference's expression; a child that leads by TR_RANK_MARGIN2
+                        // is the maximum
+                        const double cs = LS_SHFL(cs_lane, (int)rel);
+                        const double n = (double)(cm ? n1 : 1u), wins = p1 ? sc1 : (double)real1 - sc1;
+                        const double v = cm ? wins * tr_drcp(n) + cs * tr_drsq(n) : -1.0;
+                        // maximum over the warp: the values are >= 0, so the order of the doubles is the order of their bit patterns
+                        const uint32_t hi = v >= 0.0 ? TR_DHI(v) : 0u, mhi = TR_REDUCE_MAXU(hi);
+                        const uint32_t lo = v >= 0.0 && hi == mhi ? TR_DLO(v) : 0u, mlo = TR_REDUCE_MAXU(lo);
+                        const double vmax = TR_HILO2D(mhi, mlo), thr2 = vmax - TR_RANK_MARGIN2 * (1.0 + vmax);
+                        const uint32_t close = LS_BALLOT(cm != 0u && v >= thr2);
+                        if ((close & (close - 1u)) == 0u) { settled = true; pick = LS_SHFL(mine, LS_FFS(close) - 1); }
                     }
-                    const double v_first = bv;
+                }
+                if (!settled) {
+                    // the general way (a lane with several candidates, or values that the double pass cannot separate):
+                    // the candidates' statistics go to shared memory and the reference's expression decides — first strict
+                    // maximum: maximum of the high words, then of the low words among those, then the lowest index
+#pragma unroll
+                    for (int q = 0; q < NS; q++)
+                        if ((cm >> q) & 1u) { const int i = lane + 32 * q; W.vis[i] = (double)nint[q]; W.vq[i] = nint[q] - W.real[i]; }
+                    LS_SYNCWARP();
+                    const double lp = LS_SHFL(lp_lane, (int)rel);
+                    double ev = -1.0; int bi = 1 << 20;
                     LS_UNROLL1
-                    for (uint32_t mq = cm & (cm - 1u); mq; mq &= mq - 1u) {
-                        const int q = LS_FFS(mq) - 1, i = lane + 32 * q;
-                        const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
-                        const double v = wins * tr_drcp(n) + cs * tr_drsq(n);
-                        bv = v > bv ? v : bv;
+                    for (uint32_t mq = cm; mq; mq &= mq - 1u) {
+                        const int i = lane + 32 * (LS_FFS(mq) - 1);
+                        const double v = tr_uct_exact(W.sc[i], W.vis[i], (double)W.vq[i], p1, t.c, lp);
+                        if (v > ev) { ev = v; bi = i; }
                     }
-                    // maximum over the warp: the values are >= 0, so the order of the doubles is the order of their bit patterns
-                    uint32_t hi = bv >= 0.0 ? TR_DHI(bv) : 0u; const uint32_t mhi = TR_REDUCE_MAXU(hi);
-                    uint32_t lo = bv >= 0.0 && hi == mhi ? TR_DLO(bv) : 0u; const uint32_t mlo = TR_REDUCE_MAXU(lo);
-                    const double vmax = TR_HILO2D(mhi, mlo), thr2 = vmax - TR_RANK_MARGIN2 * (1.0 + vmax);
-                    if (cm && v_first >= thr2) cm2 = cm & (0u - cm);          // lowest set bit: the first candidate
-                    LS_UNROLL1
-                    for (uint32_t mq = cm & (cm - 1u); mq; mq &= mq - 1u) {
-                        const int q = LS_FFS(mq) - 1, i = lane + 32 * q;
-                        const double n = W.vis[i], wins = p1 ? W.sc[i] : (double)W.real[i] - W.sc[i];
-                        const double v = wins * tr_drcp(n) + cs * tr_drsq(n);
-                        if (v >= thr2) cm2 |= 1u << q;
-                    }
-                    const int mine2 = cm2 ? lane + 32 * (LS_FFS(cm2) - 1) : (1 << 20);
-                    const int lowest2 = -TR_REDUCE_MAX(-mine2);
-                    const bool alone2 = (cm2 & (cm2 - 1u)) == 0u && (cm2 == 0u || mine2 == lowest2);
-                    if (LS_BALLOT(!alone2) == 0u) pick = lowest2;
-                    else {
-                        // the reference's expression decides, first strict maximum: maximum of the high words, then of the low
-                        // words among those, then the lowest index among those
-                        const double lp = LS_SHFL(lp_lane, (int)rel);
-                        double ev = -1.0; int bi = 1 << 20;
-                        LS_UNROLL1
-                        for (uint32_t mq = cm2; mq; mq &= mq - 1u) {
-                            const int i = lane + 32 * (LS_FFS(mq) - 1);
-                            const double v = tr_uct_exact(W.sc[i], W.vis[i], (double)W.vq[i], p1, t.c, lp);
-                            if (v > ev) { ev = v; bi = i; }
-                        }
-                        const bool has = ev >= 0.0;
-                        hi = has ? TR_DHI(ev) : 0u; const uint32_t ehi = TR_REDUCE_MAXU(hi);
-                        const bool top = has && hi == ehi;
-                        lo = top ? TR_DLO(ev) : 0u; const uint32_t elo = TR_REDUCE_MAXU(lo);
-                        const int win = -TR_REDUCE_MAX(top && lo == elo ? -bi : -(1 << 20));
-                        pick = win < nc ? win : 0;
-                        if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->exact_evals, 1u);
-                    }
+                    const bool has = ev >= 0.0;
+                    const uint32_t hi = has ? TR_DHI(ev) : 0u, ehi = TR_REDUCE_MAXU(hi);
+                    const bool top = has && hi == ehi;
+                    const uint32_t lo = top ? TR_DLO(ev) : 0u, elo = TR_REDUCE_MAXU(lo);
+                    const int win = -TR_REDUCE_MAX(top && lo == elo ? -bi : -(1 << 20));
+                    pick = win < nc ? win : 0;
+                    if (lane == 0) TR_ATOMIC_ADD32(&t.ctl->exact_evals, 1u);
                 }
             }
         }
@@ -455,7 +454,8 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
     }
 }
 
-LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane, TreeWarpSmem &W) {
+LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane, TreeWarpSmem &W, const uint32_t next_base) {
+    // next_base = where the items of the next level of this item's chunk begin (= end of the current level's)
     const TreePool &P = t.pool;
     uint32_t *cursor = W.cursor;
     if (lane == 0 && it.level + 1 > t.ctl->depth_max) TR_ATOMIC_MAX32(&t.ctl->depth_max, it.level + 1);
@@ -594,7 +594,7 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     const uint32_t chunk_id = it.start / t.chunk;           // an item's list lies inside its chunk's range of descents
     TreeItem *chunk_items = t.items + (size_t)chunk_id * t.items_per_chunk;
     uint32_t ibase = 0;
-    if (lane == 0) ibase = TR_ATOMIC_ADD32(t.n_items + chunk_id, n_new);
+    if (lane == 0) ibase = next_base + TR_ATOMIC_ADD32(t.level_items + chunk_id * (uint32_t)TR_MAX_LEVELS + it.level + 1u, n_new);
     ibase = LS_SHFL(ibase, 0);
     if (ibase + n_new > t.items_per_chunk) {                // cannot happen with items_per_chunk >= chunk * TR_MAX_LEVELS; stop here if it does
         if (lane == 0) TR_ATOMIC_OR32(&t.ctl->error, (uint32_t)TR_ERR_ITEMS);

@@ -244,6 +244,7 @@ int emu_warp_width() { return LS_WARP; }
 struct EmuSlot {
     std::vector<TreeItem> items; std::vector<uint32_t> idx; std::vector<uint8_t> choice, created; std::vector<int32_t> leaf_of;
     uint32_t n_items[TR_MAX_CHUNKS], n_last;
+    std::vector<uint32_t> level_items;
 };
 struct EmuTree {
     TreeCtx t[2]; TreeCtl ctl; EmuSlot slot[2];
@@ -252,11 +253,11 @@ struct EmuTree {
     std::vector<uint8_t> move, flags;
     std::vector<double> logtab;
 };
-struct EmuTreeLaunch { EmuTree *T; int slot; std::vector<TreeItem> work; const double *w; TreeWarpSmem *wsm; };
+struct EmuTreeLaunch { EmuTree *T; int slot; std::vector<TreeItem> work; std::vector<uint32_t> next_base; const double *w; TreeWarpSmem *wsm; };
 static void emu_tree_select_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
     const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
-    for (size_t i = warp; i < L->work.size(); i += nwarps) tree_select_item(L->T->t[L->slot], L->work[i], lane, L->wsm[warp]);
+    for (size_t i = warp; i < L->work.size(); i += nwarps) tree_select_item(L->T->t[L->slot], L->work[i], lane, L->wsm[warp], L->next_base[i]);
 }
 static void emu_tree_backprop_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
@@ -276,12 +277,12 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
         EmuSlot &S = T->slot[k];
         const uint32_t nch = (K + chunk - 1) / chunk;
         S.items.resize((size_t)chunk * TR_MAX_LEVELS * nch); S.idx.resize((size_t)K * TR_MAX_LEVELS); S.choice.resize(K); S.created.resize(K); S.leaf_of.resize(K);
-        memset(S.n_items, 0, sizeof S.n_items); S.n_last = 0;
+        memset(S.n_items, 0, sizeof S.n_items); S.n_last = 0; S.level_items.assign((size_t)TR_MAX_CHUNKS * TR_MAX_LEVELS, 0u);
         TreeCtx &t = T->t[k];
         t.pool.state = T->state.data(); t.pool.lh = T->lh.data(); t.pool.lv = T->lv.data(); t.pool.score = T->score.data(); t.pool.sims = T->sims.data();
         t.pool.virt = T->virt.data(); t.pool.size = T->size.data(); t.pool.parent = T->parent.data(); t.pool.first_child = T->first_child.data();
         t.pool.n_children = T->n_children.data(); t.pool.n_moves = T->n_moves.data(); t.pool.move = T->move.data(); t.pool.flags = T->flags.data();
-        t.ctl = &T->ctl; t.n_items = S.n_items; t.items = S.items.data(); t.items_per_chunk = chunk * (uint32_t)TR_MAX_LEVELS; t.chunk = chunk; t.idx = S.idx.data(); t.choice = S.choice.data();
+        t.ctl = &T->ctl; t.n_items = S.n_items; t.level_items = S.level_items.data(); t.items = S.items.data(); t.items_per_chunk = chunk * (uint32_t)TR_MAX_LEVELS; t.chunk = chunk; t.idx = S.idx.data(); t.choice = S.choice.data();
         t.leaf_of = S.leaf_of.data(); t.created = S.created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
         t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
     }
@@ -308,21 +309,23 @@ int emu_tree_select(void *h, int slot, uint32_t n, mctsb_qstate *leaf_states) {
         TreeItem r; r.node = T->ctl.root; r.start = c * t.chunk; r.count = n - r.start < t.chunk ? n - r.start : t.chunk; r.level = 0; r.n0 = 0; r.pad = 0;
         S.items[(size_t)c * t.items_per_chunk] = r; S.n_items[c] = 1;
     }
+    std::fill(S.level_items.begin(), S.level_items.end(), 0u);
     std::vector<TreeWarpSmem> wsm(4);
     memset(wsm.data(), 0xa5, sizeof(TreeWarpSmem) * 4);
     // the waves of the selection kernel: level wave - c of every chunk c <= wave, all in one launch (their order inside
     // the launch is whatever the fibers make of it — the items of a wave must be independent)
     for (uint32_t wave = 0;; wave++) {
         const uint32_t started = wave + 1 < nch ? wave + 1 : nch;
-        EmuTreeLaunch L{T, slot, {}, nullptr, wsm.data()};
+        EmuTreeLaunch L{T, slot, {}, {}, nullptr, wsm.data()};
         for (uint32_t c = 0; c < started; c++)
-            for (uint32_t i = cbegin[c]; i < cend[c]; i++) L.work.push_back(S.items[(size_t)c * t.items_per_chunk + i]);
+            for (uint32_t i = cbegin[c]; i < cend[c]; i++) { L.work.push_back(S.items[(size_t)c * t.items_per_chunk + i]); L.next_base.push_back(cend[c]); }
         if (L.work.empty() && wave >= nch) break;
         // reverse order: the later chunks' shallow items run BEFORE the earlier chunks' deep ones
-        std::reverse(L.work.begin(), L.work.end());
+        std::reverse(L.work.begin(), L.work.end()); std::reverse(L.next_base.begin(), L.next_base.end());
         if (!L.work.empty()) simt::launch(1, 128, emu_tree_select_thread, &L);
-        for (uint32_t c = 0; c < started; c++) { cbegin[c] = cend[c]; cend[c] = S.n_items[c]; }
+        for (uint32_t c = 0; c < started; c++) { const uint32_t lvl = wave - c + 1; cbegin[c] = cend[c]; cend[c] += lvl < (uint32_t)TR_MAX_LEVELS ? S.level_items[(size_t)c * TR_MAX_LEVELS + lvl] : 0u; }
     }
+    for (uint32_t c = 0; c < nch; c++) S.n_items[c] = cend[c];
     for (uint32_t d = 0; d < n; d++) leaf_states[d] = T->state[S.leaf_of[d]];
     S.n_last = n;
     return (int)T->ctl.error;
@@ -338,7 +341,7 @@ int emu_tree_backprop(void *h, int slot, const mctsb_leaf_sum *sums) {
     const TreeCtx &t = T->t[slot];
     const uint32_t nch = (S.n_last + t.chunk - 1) / t.chunk;
     for (uint32_t c = 0; c < nch; c++) {                   // chunk by chunk: a node's results are added in selection order
-        EmuTreeLaunch L{T, slot, {}, w.data(), nullptr};
+        EmuTreeLaunch L{T, slot, {}, {}, w.data(), nullptr};
         for (uint32_t i = 0; i < S.n_items[c]; i++) L.work.push_back(S.items[(size_t)c * t.items_per_chunk + i]);
         simt::launch(1, 128, emu_tree_backprop_thread, &L);
     }
