@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--flushes", type=int, default=16)
     ap.add_argument("--policy", type=int, default=0)
     ap.add_argument("--no-host", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="skip the one-flush-in-flight run of the device tree (profiling runs: one stream)")
     a = ap.parse_args()
     host = load()
     be = m.RolloutBackend(0, m.DEFAULT_SEED)
@@ -28,7 +29,7 @@ def main():
         iters = K * a.flushes
         row = {"leaves_per_flush": K, "rollouts_per_leaf": R, "flushes": a.flushes, "policy": "REF" if a.policy == 0 else "UNI"}
         # device-resident tree: one warm-up grow (first-touch of the pool, kernel load), then the timed search from scratch
-        for rep in range(2):
+        for rep in range(0 if a.no_overlap else 2):
             dt = m.DeviceTree(be, root, R, K, policy=a.policy)
             dt.set_overlap(True)
             t0 = time.perf_counter()
@@ -36,7 +37,8 @@ def main():
             wall = time.perf_counter() - t0
             info = dt.info()
             dt.close()
-        row["device_tree_1_in_flight"] = {"wall_ms_per_flush": 1e3 * wall / a.flushes, "rollouts_per_sec": iters * R / wall, "iterations_per_sec": iters / wall,
+        if not a.no_overlap:
+            row["device_tree_1_in_flight"] = {"wall_ms_per_flush": 1e3 * wall / a.flushes, "rollouts_per_sec": iters * R / wall, "iterations_per_sec": iters / wall,
                                           "nodes_used": info["nodes_used"]}
         for rep in range(2):
             dt = m.DeviceTree(be, root, R, K, policy=a.policy)
