@@ -294,3 +294,25 @@ def test_cpp_device_tree_class_plays_the_host_trees_game(host):
         else:
             t.close()
     assert games[0] == games[1], games
+
+
+@pytest.mark.gpu
+def test_cpp_selfplay_program_device_tree_vs_host_tree(tmp_path):
+    """integration/selfplay_device_tree.cpp: the reference's self-play loop (examples/Quoridor/main.cpp:129-169) as a plain C++
+    program over MCTS_device_tree and, with `host`, over MCTS_tree — no Python in the loop; the two play the same game"""
+    import json
+    import os
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    pkg = os.path.join(root, "montecarlotreesearch_b200")
+    exe = str(tmp_path / "selfplay_device_tree")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(root, "include"), "-I", os.path.join(pkg, "host"),
+                           os.path.join(root, "integration", "selfplay_device_tree.cpp"), "-L", pkg, "-lmcts_host", "-lmctsb",
+                           "-Wl,-rpath," + pkg, "-o", exe])
+    lines = []
+    for where in ("device", "host"):
+        r = subprocess.run([exe, "2048", "512", "8", "10", where], capture_output=True, text=True, timeout=300)
+        assert r.returncode == 0, r.stderr[-500:]
+        lines.append(json.loads(r.stdout.strip().splitlines()[-1]))
+    assert lines[0]["moves"] == 10 and lines[0]["move_ids"] == lines[1]["move_ids"], lines
+    assert lines[0]["rollouts_total"] == lines[1]["rollouts_total"] == 10 * 2048 * 8
