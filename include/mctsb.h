@@ -292,6 +292,11 @@ int mctsb_tree_best_move(mctsb_tree *t, int32_t *move_id);
 /* advance_tree (mcts.cpp:132-157,260-264): the child that carries the move becomes the root (its subtree is kept);
  * a move without a child starts a fresh root.  MCTSB_ERR_BAD_ARG for an illegal move. */
 int mctsb_tree_advance(mctsb_tree *t, int32_t move_id);
+/* Root-parallel trees (one per GPU, same root, different Philox keys): sum the root children's statistics over the
+ * GPUs `b` is joined with (mctsb_comm_*), as MCTS_tree::merge_root_stats does for host trees; afterwards
+ * mctsb_tree_best_move applies the reference's final rule to the same numbers on every rank.  The root must be fully
+ * expanded (MCTSB_ERR_BAD_STATE otherwise).  A backend that stands alone (no communicator, or a world of one): no-op. */
+int mctsb_tree_merge_root(mctsb_tree *t);
 int mctsb_tree_root_state(mctsb_tree *t, mctsb_qstate *out);
 /* the whole tree in pre-order (children in creation order), one row per node, at most `cap` rows written; *n = nodes */
 int mctsb_tree_dump(mctsb_tree *t, uint64_t cap, int32_t *depth, int32_t *move_id, uint64_t *sims, double *score,

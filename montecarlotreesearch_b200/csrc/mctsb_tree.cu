@@ -501,6 +501,39 @@ int mctsb_tree_advance(mctsb_tree *t, int32_t move_id) {
     return MCTSB_OK;
 }
 
+// Root-parallel search: trees of the same root grown on several GPUs add their root-child statistics
+// before the final choice, as MCTS_tree::merge_root_stats does on the host — slot k = the k-th move of the root's
+// generate_all_moves order = the root's k-th child, the same on every rank.  After the sum every rank holds the same
+// (simulations, score) per child and the root holds their totals (MCTS_tree::import_root_stats).
+int mctsb_tree_merge_root(mctsb_tree *t) {
+    if (!t) return MCTSB_ERR_BAD_ARG;
+    mctsb_backend *b = t->b;
+    int world = 1;
+    mctsb_comm_info(b, &world, nullptr);
+    if (world <= 1) return MCTSB_OK;                       // a lone backend: nothing to add (as MCTS_tree::merge_root_stats)
+    TCK(cudaSetDevice(b->device));
+    RootView v;
+    int s = read_root(t, v);
+    if (s != MCTSB_OK) return s;
+    uint16_t n_moves = 0;
+    TCK(cudaMemcpy(&n_moves, t->ctx[0].pool.n_moves + v.ctl.root, 2, cudaMemcpyDeviceToHost));
+    // every rank must own the same slots: the root has to be fully expanded (true after n_moves iterations)
+    if (n_moves == TR_UNLISTED || v.nc != (int)n_moves || v.nc == 0) return MCTSB_ERR_BAD_STATE;
+    std::vector<double> stats(2 * (size_t)v.nc);
+    for (int i = 0; i < v.nc; i++) { stats[2 * i] = (double)v.sims[i]; stats[2 * i + 1] = v.score[i]; }
+    s = mctsb_allreduce_root_stats(b, stats.data(), 2 * v.nc);
+    if (s != MCTSB_OK) return s;
+    double sims = 0, score = 0;
+    for (int i = 0; i < v.nc; i++) { v.sims[i] = (unsigned long long)stats[2 * i]; v.score[i] = stats[2 * i + 1]; sims += stats[2 * i]; score += stats[2 * i + 1]; }
+    const TreePool &P = t->ctx[0].pool;
+    const unsigned long long root_sims = (unsigned long long)sims;
+    TCK(cudaMemcpy(P.sims + v.first, v.sims.data(), (size_t)v.nc * 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.score + v.first, v.score.data(), (size_t)v.nc * 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.sims + v.ctl.root, &root_sims, 8, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.score + v.ctl.root, &score, 8, cudaMemcpyHostToDevice));
+    return MCTSB_OK;
+}
+
 int mctsb_tree_root_state(mctsb_tree *t, mctsb_qstate *out) {
     if (!t || !out) return MCTSB_ERR_BAD_ARG;
     mctsb_backend *b = t->b;

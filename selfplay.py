@@ -55,6 +55,16 @@ class DeviceTreeSession:
     def best_move(self):
         return self.tree.best_move()
 
+    # root-parallel trees: the same calls a host-tree Session offers
+    def comm_init_rank(self, unique_id, world, rank):
+        self.be.comm_init_rank(unique_id, world, rank)
+
+    def merge_root(self):
+        self.tree.merge_root()
+
+    def allreduce(self, vec):
+        return self.be.allreduce_root_stats(vec)
+
     def advance(self, mv):
         self.tree.advance(mv)
         s = self.tree.root_state()
@@ -121,7 +131,7 @@ def main():
     ap.add_argument("--agreement", action="store_true", help="replay the game on one GPU at rank 0's seed and report per-move best-child agreement")
     ap.add_argument("--check-agreement-across-ranks", type=int, default=1)
     ap.add_argument("--device-tree", type=int, default=0,
-                    help="1 = the tree itself lives on the GPU (mctsb_tree_*: Selection, Expansion and Backpropagation as kernels); one GPU only")
+                    help="1 = the tree itself lives on the GPU (mctsb_tree_*: Selection, Expansion and Backpropagation as kernels); under torchrun one tree per GPU, merged per move by mctsb_tree_merge_root")
     ap.add_argument("--device-tree-nodes", type=int, default=1 << 26, help="node pool of the device tree (86 bytes per node)")
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
@@ -149,7 +159,6 @@ def main():
 
     def new_tree(seed, device):
         if args.device_tree:
-            assert world == 1, "the device-resident tree runs on one GPU (root-parallel merge: host tree)"
             return DeviceTreeSession(m, args, seed, device)
         t = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
                     leaves_per_flush=args.leaves_per_flush, device=device, seed=seed)

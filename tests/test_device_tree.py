@@ -316,3 +316,41 @@ def test_cpp_selfplay_program_device_tree_vs_host_tree(tmp_path):
         lines.append(json.loads(r.stdout.strip().splitlines()[-1]))
     assert lines[0]["moves"] == 10 and lines[0]["move_ids"] == lines[1]["move_ids"], lines
     assert lines[0]["rollouts_total"] == lines[1]["rollouts_total"] == 10 * 2048 * 8
+
+
+@pytest.mark.gpu
+def test_root_merge_of_device_trees_equals_the_host_trees_merge(host):
+    """mctsb_tree_merge_root is MCTS_tree::merge_root_stats for device trees: a no-op for a lone backend; over every GPU of
+    the box (different Philox keys) all ranks end with the same root-child statistics — the sums — and the same best move"""
+    root = m.quoridor_opening()
+    be = m.RolloutBackend(0, m.DEFAULT_SEED)
+    host.mcts_host_set_next_rollout_id(1 << 46)
+    ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=8, leaves_per_flush=128)
+    dt = m.DeviceTree(be, root, 8, 128)
+    ht.grow(512); dt.grow(512, 1 << 46)
+    ht.merge_root(); dt.merge_root()                            # lone backends: both leave the tree as it is
+    a, b = ht.dump(), dt.dump()
+    for k in ("depth", "move", "n_children", "sims", "size"):
+        assert (a[k] == b[k]).all(), k
+    assert a["score"].tobytes() == b["score"].tobytes() and ht.best_move() == dt.best_move()
+    ht.close(); dt.close(); be.close()
+    n = m.device_count()
+    if n >= 2:
+        bes = [m.RolloutBackend(g, m.DEFAULT_SEED + g) for g in range(n)]
+        m.comm_init_all(bes)
+        trees = [m.DeviceTree(b_, root, 8, 128) for b_ in bes]
+        trees[0].grow(64, 0)
+        with pytest.raises(m.BackendError):
+            trees[0].merge_root()                               # root not fully expanded yet: its slots are not all there
+        trees[0].grow(448, 64 * 8)
+        for t in trees[1:]:
+            t.grow(512, 0)
+        import threading
+        th = [threading.Thread(target=t.merge_root) for t in trees]     # one blocking all-reduce per rank: issue them together
+        [x.start() for x in th]; [x.join() for x in th]
+        kids = [t.root_children() for t in trees]
+        for k in kids[1:]:
+            assert all((x == y).all() for x, y in zip(k, kids[0]))
+        assert len({t.best_move() for t in trees}) == 1
+        assert int(kids[0][1].sum()) == n * 512 * 8
+        [t.close() for t in trees]; [b_.close() for b_ in bes]
