@@ -11,6 +11,7 @@
 #include "tree_body.cuh"
 #include "mctsb_backend_internal.cuh"
 #include <cooperative_groups.h>
+#include <cuda.h>                      // types of the driver's green contexts; the entry points are fetched at run time
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -111,6 +112,13 @@ struct mctsb_tree {
     int select_blocks;
     bool overlap;                       // select flush f+1 while the playouts of flush f run (host tree: MCTS_batching::overlap)
     cudaStream_t tree_stream;           // Selection / Backpropagation kernels in overlap mode (the playouts stay on the backend's stream)
+    // overlap mode, when the driver can partition the GPU (green contexts): the tree's kernels own a few SMs and the
+    // playouts the rest, so that the root's chain of picks — one warp's issue latency — does not share its SM with
+    // sixteen playout warps.  Falls back to the two plain streams above where that is not available.
+    bool part_tried, part_ok;
+    CUgreenCtx part_tree_ctx, part_play_ctx;
+    cudaStream_t part_tree_stream, part_play_stream;
+    int part_tree_sms, part_play_sms, part_select_blocks;
     cudaEvent_t ev_selected[2], ev_played[2];
     uint64_t flushes, rollouts;
     float ms[3], ms_total;
@@ -131,6 +139,8 @@ int read_ctl(mctsb_tree *t, TreeCtl *out) {
     mctsb_backend *b = t->b;
     TCK(cudaStreamSynchronize(b->stream));
     if (t->tree_stream) TCK(cudaStreamSynchronize(t->tree_stream));
+    if (t->part_tree_stream) TCK(cudaStreamSynchronize(t->part_tree_stream));
+    if (t->part_play_stream) TCK(cudaStreamSynchronize(t->part_play_stream));
     TCK(cudaMemcpy(out, t->ctx[0].ctl, sizeof *out, cudaMemcpyDeviceToHost));
     return MCTSB_OK;
 }
@@ -186,6 +196,56 @@ int read_root(mctsb_tree *t, RootView &v) {
         TCK(cudaMemcpy(v.score.data(), P.score + v.first, (size_t)nc * 8, cudaMemcpyDeviceToHost));
     }
     return MCTSB_OK;
+}
+
+}  // namespace
+
+namespace {
+
+// Split the device's SMs into a small group for the tree and the rest for the playouts (CUDA driver API, green
+// contexts; entry points through cudaGetDriverEntryPoint so that the library does not link libcuda).  Any failure
+// leaves part_ok false: the caller then runs both kinds of kernels on all SMs, as before.
+void make_partition(mctsb_tree *t) {
+    t->part_tried = true; t->part_ok = false;
+    if (getenv("MCTSB_TREE_NO_PARTITION")) return;
+    typedef CUresult (*fn_dev_get)(CUdevice *, int);
+    typedef CUresult (*fn_get_res)(CUdevice, CUdevResource *, CUdevResourceType);
+    typedef CUresult (*fn_split)(CUdevResource *, unsigned int *, const CUdevResource *, CUdevResource *, unsigned int, unsigned int);
+    typedef CUresult (*fn_desc)(CUdevResourceDesc *, CUdevResource *, unsigned int);
+    typedef CUresult (*fn_gctx)(CUgreenCtx *, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*fn_gstream)(CUstream *, CUgreenCtx, unsigned int, int);
+    void *p[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const char *names[6] = {"cuDeviceGet", "cuDeviceGetDevResource", "cuDevSmResourceSplitByCount", "cuDevResourceGenerateDesc", "cuGreenCtxCreate", "cuGreenCtxStreamCreate"};
+    for (int i = 0; i < 6; i++) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint(names[i], &p[i], cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess || !p[i]) { cudaGetLastError(); return; }
+    }
+    CUdevice dev;
+    if (((fn_dev_get)p[0])(&dev, t->b->device) != CUDA_SUCCESS) return;
+    CUdevResource all, tree_res, play_res;
+    if (((fn_get_res)p[1])(dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return;
+    unsigned int groups = 1;
+    const char *ev = getenv("MCTSB_TREE_SMS");
+    // groups come in multiples of 8 SMs on sm_90+; measured over whole games at 4 096 leaves per flush: 8 SMs 25.6 M rollouts/s,
+    // 16 SMs 26.7 M, 32 SMs 26.3 M (the waves below the root spread over the group's warps)
+    const unsigned int want = ev && atoi(ev) > 0 ? (unsigned)atoi(ev) : 16u;
+    if (((fn_split)p[2])(&tree_res, &groups, &all, &play_res, 0u, want) != CUDA_SUCCESS || groups != 1) return;
+    if (tree_res.sm.smCount == 0 || play_res.sm.smCount < 64) return;
+    CUdevResourceDesc dtree, dplay;
+    if (((fn_desc)p[3])(&dtree, &tree_res, 1) != CUDA_SUCCESS || ((fn_desc)p[3])(&dplay, &play_res, 1) != CUDA_SUCCESS) return;
+    if (((fn_gctx)p[4])(&t->part_tree_ctx, dtree, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    if (((fn_gctx)p[4])(&t->part_play_ctx, dplay, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return;
+    CUstream st = nullptr, sp = nullptr;
+    if (((fn_gstream)p[5])(&st, t->part_tree_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return;
+    if (((fn_gstream)p[5])(&sp, t->part_play_ctx, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return;
+    t->part_tree_stream = (cudaStream_t)st; t->part_play_stream = (cudaStream_t)sp;
+    t->part_tree_sms = (int)tree_res.sm.smCount; t->part_play_sms = (int)play_res.sm.smCount;
+    int per_sm = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_select_kernel, SELECT_THREADS, 0);
+    t->part_select_blocks = t->part_tree_sms * (per_sm < 1 ? 1 : per_sm);
+    if (t->part_select_blocks > t->select_blocks) t->part_select_blocks = t->select_blocks;
+    t->part_ok = true;
+    if (getenv("MCTSB_TREE_DEBUG")) fprintf(stderr, "tree: SM partition %d (tree) + %d (playouts), selection grid %d\n", t->part_tree_sms, t->part_play_sms, t->part_select_blocks);
 }
 
 }  // namespace
@@ -275,6 +335,16 @@ int mctsb_tree_destroy(mctsb_tree *t) {
     cudaStreamSynchronize(t->b->stream);
     for (int i = 0; i < t->n_allocs; i++) cudaFree(t->allocs[i]);
     if (t->tree_stream) { cudaStreamSynchronize(t->tree_stream); cudaStreamDestroy(t->tree_stream); }
+    if (t->part_tree_stream) { cudaStreamSynchronize(t->part_tree_stream); cudaStreamDestroy(t->part_tree_stream); }
+    if (t->part_play_stream) { cudaStreamSynchronize(t->part_play_stream); cudaStreamDestroy(t->part_play_stream); }
+    if (t->part_tree_ctx || t->part_play_ctx) {
+        typedef CUresult (*fn_gdestroy)(CUgreenCtx);
+        void *p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuGreenCtxDestroy", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess && p) {
+            if (t->part_tree_ctx) ((fn_gdestroy)p)(t->part_tree_ctx);
+            if (t->part_play_ctx) ((fn_gdestroy)p)(t->part_play_ctx);
+        }
+    }
     if (t->ev_begin) cudaEventDestroy(t->ev_begin);
     if (t->ev_end) cudaEventDestroy(t->ev_end);
     for (int i = 0; i < 2; i++) { if (t->ev_selected[i]) cudaEventDestroy(t->ev_selected[i]); if (t->ev_played[i]) cudaEventDestroy(t->ev_played[i]); }
@@ -285,6 +355,7 @@ int mctsb_tree_destroy(mctsb_tree *t) {
 int mctsb_tree_set_overlap(mctsb_tree *t, int on) {
     if (!t) return MCTSB_ERR_BAD_ARG;
     t->overlap = on != 0;
+    if (t->overlap && !t->part_tried) { cudaSetDevice(t->b->device); make_partition(t); }
     return MCTSB_OK;
 }
 
@@ -294,7 +365,8 @@ namespace {
 int launch_select(mctsb_tree *t, int slot, uint32_t n, cudaStream_t st) {
     mctsb_backend *b = t->b;
     void *args[] = {(void *)&t->ctx[slot], (void *)&n, (void *)&t->d_leaf_states[slot]};
-    TCK(cudaLaunchCooperativeKernel((const void *)tree_select_kernel, dim3(t->select_blocks), dim3(SELECT_THREADS), args, 0, st));
+    const int blocks = t->overlap && t->part_ok ? t->part_select_blocks : t->select_blocks;
+    TCK(cudaLaunchCooperativeKernel((const void *)tree_select_kernel, dim3(blocks), dim3(SELECT_THREADS), args, 0, st));
     b->launches++;
     return MCTSB_OK;
 }
@@ -305,7 +377,8 @@ int launch_playouts(mctsb_tree *t, int slot, uint32_t n, uint64_t first_id) {   
     RolloutParams p; memset(&p, 0, sizeof p);
     p.states = t->d_leaf_states[slot]; p.n_leaves = n; p.rollouts_per_leaf = t->R; p.n_rollouts = (uint64_t)n * t->R;
     p.seed = b->seed; p.first_rollout_id = first_id; p.sums = t->d_sums[slot]; p.counters = b->d_counters;
-    p.leave_room = t->overlap ? 1u : 0u;
+    if (t->overlap && t->part_ok) p.sm_limit = (uint32_t)t->part_play_sms;        // the playouts have their own SMs: the grid is sized for them
+    else p.leave_room = t->overlap ? 1u : 0u;                                      // shared SMs: the build that leaves a selection warp room
     return mctsb_internal_launch_rollouts(b, MCTSB_GAME_QUORIDOR, t->policy, false, p);
 }
 
@@ -328,7 +401,7 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
     TCK(cudaSetDevice(b->device));
     b->res_game = -1; b->res_leaves = 0;
     t->ms[0] = t->ms[1] = t->ms[2] = t->ms_total = 0.0f;
-    cudaStream_t first_stream = t->overlap ? t->tree_stream : b->stream;      // both modes start with a Selection and end with a Backpropagation
+    cudaStream_t first_stream = !t->overlap ? b->stream : t->part_ok ? t->part_tree_stream : t->tree_stream;      // both modes start with a Selection and end with a Backpropagation
     TCK(cudaEventRecord(t->ev_begin, first_stream));
     const uint32_t n_flushes = (iterations + leaves_per_flush - 1) / leaves_per_flush;
     int status = MCTSB_OK;
@@ -364,7 +437,9 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
         //   S(1)  S(2) B(1)  S(3) B(2) ...  S(n) B(n-1)  B(n)
         // Selection and Backpropagation on the tree's own stream, playouts on the backend's: S(f+1) runs while the
         // playouts of flush f are on the SMs, B(f) as soon as they are done.  Flush f uses slot f & 1 of the per-flush arrays.
-        cudaStream_t ts = t->tree_stream;
+        cudaStream_t ts = t->part_ok ? t->part_tree_stream : t->tree_stream;
+        cudaStream_t own_stream = b->stream;
+        if (t->part_ok) b->stream = t->part_play_stream;   // the rollout launcher works on the handle's stream: for this grow, the partition's
         uint32_t n_prev = 0;
         cudaError_t e = cudaSuccess;
         while (done < iterations && status == MCTSB_OK) {
@@ -394,6 +469,7 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
         if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
         e = cudaStreamSynchronize(ts);
         if (e != cudaSuccess && status == MCTSB_OK) status = fail(b, e, "tree grow");
+        b->stream = own_stream;
     }
     if (status != MCTSB_OK) return status;
     TCK(cudaEventRecord(t->ev_end, first_stream));

@@ -88,9 +88,10 @@ cudaError_t launch_quoridor_lockstep(const RolloutParams &params, bool replay, u
     const int dense = c.dense[r] < 1 ? 1 : c.dense[r], sparse = c.sparse[r] < 1 ? 1 : c.sparse[r];
     RolloutParams p = params;
     unsigned blocks = 0, lanes = 32;
-    ls_grid_shape(p.n_rollouts, c.sms, dense, blocks, lanes);
+    const int sms = params.sm_limit > 0 && (int)params.sm_limit < c.sms ? (int)params.sm_limit : c.sms;
+    ls_grid_shape(p.n_rollouts, sms, dense, blocks, lanes);
     p.lanes_per_batch = lanes;
-    const bool use_sparse = blocks <= (unsigned)(c.sms * sparse) && !params.leave_room;
+    const bool use_sparse = blocks <= (unsigned)(sms * sparse) && !params.leave_room;
     if (use_sparse) {
         if (replay) quoridor_lockstep_kernel<true, LS_BLOCKS_SPARSE><<<blocks, LS_THREADS, LS_SMEM, st>>>(p, work_counter);
         else        quoridor_lockstep_kernel<false, LS_BLOCKS_SPARSE><<<blocks, LS_THREADS, LS_SMEM, st>>>(p, work_counter);

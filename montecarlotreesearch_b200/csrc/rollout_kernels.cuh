@@ -25,6 +25,8 @@ struct RolloutParams {
     unsigned long long *counters;  // [4]: rollouts, plies, flood_steps, flood_queries
     uint32_t lanes_per_batch;      // lockstep kernel: rollouts a warp takes per batch (1..32; set by the launch)
     void *walk;                    // UNI lockstep: hand-over records between the two phases, 48 B per rollout (device)
+    uint32_t sm_limit;             // REF lockstep: SMs the launch may count on (0 = all of the device): the launching stream belongs to a
+                                   // partition of the GPU (device tree with one flush in flight), the persistent grid is sized for it
     uint32_t leave_room;           // REF lockstep: 1 = use the 96-register build even for a small grid, so that a warp of the
                                    // tree's selection kernel (128 registers) fits in every SM sub-partition next to it
 };
