@@ -243,7 +243,7 @@ void make_partition(mctsb_tree *t) {
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_select_kernel, SELECT_THREADS, 0);
     t->part_select_blocks = t->part_tree_sms * (per_sm < 1 ? 1 : per_sm);
-    if (t->part_select_blocks > t->select_blocks) t->part_select_blocks = t->select_blocks;
+    { const char *eb = getenv("MCTSB_TREE_SELECT_BLOCKS"); if (eb && atoi(eb) > 0 && atoi(eb) < t->part_select_blocks) t->part_select_blocks = atoi(eb); }
     t->part_ok = true;
     if (getenv("MCTSB_TREE_DEBUG")) fprintf(stderr, "tree: SM partition %d (tree) + %d (playouts), selection grid %d\n", t->part_tree_sms, t->part_play_sms, t->part_select_blocks);
 }
@@ -324,7 +324,10 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, b->device);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tree_select_kernel, SELECT_THREADS, 0);
     if (!coop || per_sm < 1 || dev_sms < 1) { snprintf(b->cuda_err, sizeof b->cuda_err, "cooperative launch not available"); mctsb_tree_destroy(t); return MCTSB_ERR_CUDA; }
-    t->select_blocks = dev_sms;
+    // one-warp CTAs, four per SM: the waves below the root hold hundreds of items in the middle of a game (measured over
+    // whole games at 4 096 leaves per flush: 1 / 2 / 4 / 8 CTAs per SM = 1.84 / 1.73 / 1.68 / 1.69 ms of Selection per flush)
+    t->select_blocks = dev_sms * (per_sm < 4 ? per_sm : 4);
+    { const char *eb = getenv("MCTSB_TREE_BLOCKS_PER_SM"); if (eb && atoi(eb) > 0 && atoi(eb) <= per_sm) t->select_blocks = dev_sms * atoi(eb); }
     *out = t;
     return MCTSB_OK;
 }
