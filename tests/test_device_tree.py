@@ -200,7 +200,7 @@ def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0):
     base_id = 1 << 41
     host.mcts_host_set_next_rollout_id(base_id)
     ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, policy=policy)
-    dt = m.DeviceTree(be, root, R, K, policy=policy)
+    dt = m.DeviceTree(be, root, R, K, policy=policy, max_nodes=1 << 23)
     done = 0
     for f in range(flushes):
         n = K if not (tail and f == flushes - 1) else tail
@@ -225,7 +225,7 @@ def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("R,K,flushes", [(4, 1, 30), (4, 16, 20), (16, 256, 10), (16, 4096, 6), (1, 8192, 4)])
+@pytest.mark.parametrize("R,K,flushes", [(4, 1, 30), (4, 16, 20), (16, 256, 10), (16, 4096, 6), (1, 8192, 4), (1, 40000, 3)])
 def test_device_tree_equals_host_tree_on_gpu(host, R, K, flushes):
     info = compare_gpu(host, m.quoridor_opening(), R, K, flushes, tail=max(1, K // 3))
     assert info["flags"] == 0 and info["flushes"] == flushes
