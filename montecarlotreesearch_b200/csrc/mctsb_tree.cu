@@ -45,6 +45,7 @@ __global__ void __launch_bounds__(SELECT_THREADS, 16) tree_select_kernel(TreeCtx
     if (gtid < nch) {
         const uint32_t c = gtid;
         TreeItem r; r.node = t.ctl->root; r.start = c * t.chunk; r.count = n - r.start < t.chunk ? n - r.start : t.chunk; r.level = 0; r.n0 = 0; r.pad = 0;
+        r.has_prev = c > 0 ? 1u : 0u; r.next = c + 1 < nch ? (c + 1) * t.items_per_chunk + 1u : 0u;          // the root's items, chunk after chunk
         t.items[(size_t)c * t.items_per_chunk] = r; t.n_items[c] = 1;
     }
     for (uint32_t k = gtid; k < nch * (uint32_t)TR_MAX_LEVELS; k += gthreads) t.level_items[k] = 0u;
@@ -84,13 +85,16 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_results_kernel(TreeCtx t, u
     tree_backprop_created(t, d, w);
 }
 
-// one launch per chunk, in order: a node's results are added in selection order, and a node is in several chunks
-__global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, const double *w, uint32_t chunk) {
+// a node's results are added in selection order and a node may be in several chunks: its items are chained, the warp
+// that finds the first one walks the chain
+__global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, const double *w, uint32_t nch) {
     const int lane = threadIdx.x & 31;
     const uint32_t warp = (blockIdx.x * TREE_THREADS + threadIdx.x) >> 5, nwarps = gridDim.x * TREE_WARPS;
-    const uint32_t n_items = t.n_items[chunk];
-    const TreeItem *items = t.items + (size_t)chunk * t.items_per_chunk;
-    for (uint32_t i = warp; i < n_items; i += nwarps) tree_backprop_item(t, items[i], lane, w);
+    for (uint32_t c = 0; c < nch; c++) {
+        const uint32_t n_items = t.n_items[c], base = c * t.items_per_chunk;
+        for (uint32_t i = warp; i < n_items; i += nwarps)
+            if (!t.items[base + i].has_prev) tree_backprop_chain(t, base + i, lane, w);
+    }
 }
 
 int fail(mctsb_backend *b, cudaError_t e, const char *what) {
@@ -164,6 +168,7 @@ int write_node(mctsb_tree *t, uint32_t id, const mctsb_qstate &st) {
     TCK(cudaMemcpy(P.n_moves + id, &unlisted, 2, cudaMemcpyHostToDevice));
     TCK(cudaMemcpy(P.move + id, &nomove, 1, cudaMemcpyHostToDevice));
     TCK(cudaMemcpy(P.flags + id, &flags, 1, cudaMemcpyHostToDevice));
+    TCK(cudaMemcpy(P.last_stamp + id, &zero32, 4, cudaMemcpyHostToDevice));
     return MCTSB_OK;
 }
 
@@ -273,7 +278,7 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     TTRY(dev_alloc(t, &c.pool.score, N)); TTRY(dev_alloc(t, &c.pool.sims, N)); TTRY(dev_alloc(t, &c.pool.virt, N));
     TTRY(dev_alloc(t, &c.pool.size, N)); TTRY(dev_alloc(t, &c.pool.parent, N)); TTRY(dev_alloc(t, &c.pool.first_child, N));
     TTRY(dev_alloc(t, &c.pool.n_children, N)); TTRY(dev_alloc(t, &c.pool.n_moves, N)); TTRY(dev_alloc(t, &c.pool.move, N));
-    TTRY(dev_alloc(t, &c.pool.flags, N));
+    TTRY(dev_alloc(t, &c.pool.flags, N)); TTRY(dev_alloc(t, &c.pool.last_item, N)); TTRY(dev_alloc(t, &c.pool.last_stamp, N));
     TTRY(dev_alloc(t, &c.ctl, 1));
     c.K = t->K; c.pool_cap = (uint32_t)max_nodes; c.R = t->R; c.c = uct_c;
     // chunks of 256 descents (measured best over whole games at 4 096 leaves per flush: 23.7 M rollouts/s against 22.5 M
@@ -367,6 +372,7 @@ namespace {
 // the launches of one flush, split so that the two modes can order them differently
 int launch_select(mctsb_tree *t, int slot, uint32_t n, cudaStream_t st) {
     mctsb_backend *b = t->b;
+    t->ctx[slot].stamp = (uint32_t)(t->flushes + 1);      // flush numbers start at 1 (0 = "no item yet" in the pool)
     void *args[] = {(void *)&t->ctx[slot], (void *)&n, (void *)&t->d_leaf_states[slot]};
     const int blocks = t->overlap && t->part_ok ? t->part_select_blocks : t->select_blocks;
     TCK(cudaLaunchCooperativeKernel((const void *)tree_select_kernel, dim3(blocks), dim3(SELECT_THREADS), args, 0, st));
@@ -389,9 +395,9 @@ int launch_backprop(mctsb_tree *t, int slot, uint32_t n, cudaStream_t st) {
     mctsb_backend *b = t->b;
     tree_results_kernel<<<(n + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, st>>>(t->ctx[slot], n, t->d_sums[slot], t->d_w[slot]);
     const uint32_t nch = (n + t->ctx[slot].chunk - 1) / t->ctx[slot].chunk;
-    for (uint32_t c = 0; c < nch; c++) tree_backprop_kernel<<<t->select_blocks, TREE_THREADS, 0, st>>>(t->ctx[slot], t->d_w[slot], c);
+    tree_backprop_kernel<<<t->select_blocks / 2, TREE_THREADS, 0, st>>>(t->ctx[slot], t->d_w[slot], nch);
     TCK(cudaGetLastError());
-    b->launches += 1 + nch;
+    b->launches += 2;
     return MCTSB_OK;
 }
 

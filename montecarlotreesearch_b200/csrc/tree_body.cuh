@@ -112,9 +112,14 @@ struct TreePool {
     uint16_t *n_children, *n_moves;
     uint8_t *move;                    // canonical id of the move that led here
     uint8_t *flags;
+    uint32_t *last_item, *last_stamp; // the node's latest item (flat index in its flush slot) and the flush that made it: a node
+                                      // that is in several chunks of a flush has its items chained in chunk order
 };
 
-struct TreeItem { int32_t node; uint32_t start, count, level; uint32_t n0, pad; };   // n0 = the node's simulations (finished + in flight) before these descents; set by the parent, unused at the root
+// n0 = the node's simulations (finished + in flight) before these descents (set by the parent, unused at the root);
+// next = flat index + 1 of the node's item in a later chunk of the same flush (0 = none), has_prev = it is not the first:
+// Backpropagation walks a node's items in this order, one warp per chain
+struct TreeItem { int32_t node; uint32_t start, count, level; uint32_t n0, next, has_prev, pad; };
 
 struct TreeCtl {                      // lives in device memory
     uint32_t pool_top;                // next free node id
@@ -141,6 +146,7 @@ struct TreeCtx {                      // the pool and the per-flush arrays of ON
                                       // NEXT level while everybody reads the ones of the level just closed — never the same word
     TreeItem *items; uint32_t items_per_chunk;   // chunk c owns items[c * items_per_chunk ...]
     uint32_t chunk;                   // descents per chunk
+    uint32_t stamp;                   // number of this flush (never 0)
     uint32_t *idx;                    // [TR_MAX_LEVELS][K]: idx[l*K + p] = descent number, lists of level l items
     uint8_t *choice;                  // [K] scratch: child picked by the step at list position p
     int32_t *leaf_of;                 // [K] node every descent ended at
@@ -527,7 +533,7 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
         ls_store_qstate(P.state, (uint64_t)cid, packed);
         P.score[cid] = 0.0; P.sims[cid] = 0ull; P.virt[cid] = R; P.size[cid] = 0u;
         P.parent[cid] = X; P.first_child[cid] = -1; P.n_children[cid] = 0; P.n_moves[cid] = TR_UNLISTED;
-        P.move[cid] = (uint8_t)q_move_to_id(mv); P.flags[cid] = q_winner(ns) ? TR_FLAG_TERMINAL : 0;
+        P.move[cid] = (uint8_t)q_move_to_id(mv); P.flags[cid] = q_winner(ns) ? TR_FLAG_TERMINAL : 0; P.last_stamp[cid] = 0u;
         const uint32_t d = my_idx[e];
         t.leaf_of[d] = cid; t.created[d] = 1;
     }
@@ -605,7 +611,12 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
         const uint32_t has = LS_BALLOT(cnt[q] != 0u);
         if (cnt[q] != 0u) {
             TreeItem ni; ni.node = first + lane + 32 * q; ni.start = off[q]; ni.count = cnt[q]; ni.level = it.level + 1; ni.n0 = W.vis0[lane + 32 * q]; ni.pad = 0u;
-            chunk_items[ibase + LS_POPC(has & ((1u << lane) - 1u))] = ni;
+            // chain it behind the child's item of an earlier chunk of this flush, if there is one (made in an earlier wave)
+            const uint32_t slot_i = ibase + LS_POPC(has & ((1u << lane) - 1u)), flat = chunk_id * t.items_per_chunk + slot_i;
+            ni.next = 0u; ni.has_prev = 0u;
+            if (P.last_stamp[ni.node] == t.stamp) { t.items[P.last_item[ni.node]].next = flat + 1u; ni.has_prev = 1u; }
+            P.last_item[ni.node] = flat; P.last_stamp[ni.node] = t.stamp;
+            chunk_items[slot_i] = ni;
         }
         ibase += LS_POPC(has);
     }
@@ -630,6 +641,16 @@ LS_DEV void tree_backprop_item(const TreeCtx &t, const TreeItem it, const int la
         P.virt[X] -= it.count * t.R;
         const bool own = (P.flags[X] & TR_FLAG_TERMINAL) || P.n_moves[X] == 0;   // the events of such an item are X's own leaf events
         if (!own) P.size[X] += it.count;                     // every event came up from a child (mcts.cpp:88)
+    }
+}
+// one warp walks the items of one node, chunk after chunk
+LS_DEV void tree_backprop_chain(const TreeCtx &t, uint32_t flat, const int lane, const double *w) {
+    for (;;) {
+        const TreeItem it = t.items[flat];
+        tree_backprop_item(t, it, lane, w);
+        LS_SYNCWARP();
+        if (it.next == 0u) break;
+        flat = it.next - 1u;
     }
 }
 #endif   // LS_WARP == 32

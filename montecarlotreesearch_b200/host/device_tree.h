@@ -18,7 +18,7 @@ class MCTS_device_tree {
     mutable Quoridor_state *current;        // cache for get_current_state()
     void check(int status, const char *what) const;
 public:
-    // max_nodes: node pool (86 bytes each; a node reserves ids for all its children when it is first expanded)
+    // max_nodes: node pool (94 bytes each; a node reserves ids for all its children when it is first expanded)
     MCTS_device_tree(const Quoridor_state &starting_state, CudaRolloutBackend *backend, MCTS_batching batching,
                      uint64_t max_nodes = 1ull << 24, double uct_c = 1.41);
     ~MCTS_device_tree();

@@ -132,7 +132,7 @@ def main():
     ap.add_argument("--check-agreement-across-ranks", type=int, default=1)
     ap.add_argument("--device-tree", type=int, default=0,
                     help="1 = the tree itself lives on the GPU (mctsb_tree_*: Selection, Expansion and Backpropagation as kernels); under torchrun one tree per GPU, merged per move by mctsb_tree_merge_root")
-    ap.add_argument("--device-tree-nodes", type=int, default=1 << 26, help="node pool of the device tree (86 bytes per node)")
+    ap.add_argument("--device-tree-nodes", type=int, default=1 << 26, help="node pool of the device tree (94 bytes per node)")
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     args = ap.parse_args()
 

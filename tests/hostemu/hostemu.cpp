@@ -251,6 +251,7 @@ struct EmuTree {
     std::vector<mctsb_qstate> state; std::vector<uint64_t> lh, lv; std::vector<double> score; std::vector<unsigned long long> sims;
     std::vector<uint32_t> virt, size; std::vector<int32_t> parent, first_child; std::vector<uint16_t> n_children, n_moves;
     std::vector<uint8_t> move, flags;
+    std::vector<uint32_t> last_item, last_stamp; uint32_t flush_no = 0;
     std::vector<double> logtab;
 };
 struct EmuTreeLaunch { EmuTree *T; int slot; std::vector<TreeItem> work; std::vector<uint32_t> next_base; const double *w; TreeWarpSmem *wsm; };
@@ -262,7 +263,7 @@ static void emu_tree_select_thread(void *a) {
 static void emu_tree_backprop_thread(void *a) {
     EmuTreeLaunch *L = (EmuTreeLaunch *)a;
     const int warp = simt::tid() >> 5, lane = simt::tid() & 31, nwarps = 4;
-    for (size_t i = warp; i < L->work.size(); i += nwarps) tree_backprop_item(L->T->t[L->slot], L->work[i], lane, L->w);
+    for (size_t i = warp; i < L->next_base.size(); i += nwarps) tree_backprop_chain(L->T->t[L->slot], L->next_base[i], lane, L->w);
 }
 
 void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t pool_cap, double c, uint32_t logtab_n, uint32_t chunk) {
@@ -270,7 +271,7 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
     EmuTree *T = new EmuTree();
     T->state.resize(pool_cap); T->lh.resize(pool_cap); T->lv.resize(pool_cap); T->score.resize(pool_cap); T->sims.resize(pool_cap);
     T->virt.resize(pool_cap); T->size.resize(pool_cap); T->parent.resize(pool_cap); T->first_child.resize(pool_cap);
-    T->n_children.resize(pool_cap); T->n_moves.resize(pool_cap); T->move.resize(pool_cap); T->flags.resize(pool_cap);
+    T->n_children.resize(pool_cap); T->n_moves.resize(pool_cap); T->move.resize(pool_cap); T->flags.resize(pool_cap); T->last_item.assign(pool_cap, 0); T->last_stamp.assign(pool_cap, 0);
     T->logtab.resize(logtab_n);
     for (uint32_t m = 0; m < logtab_n; m++) T->logtab[m] = log((double)((unsigned long long)m * R));
     for (int k = 0; k < 2; k++) {
@@ -282,6 +283,7 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
         t.pool.state = T->state.data(); t.pool.lh = T->lh.data(); t.pool.lv = T->lv.data(); t.pool.score = T->score.data(); t.pool.sims = T->sims.data();
         t.pool.virt = T->virt.data(); t.pool.size = T->size.data(); t.pool.parent = T->parent.data(); t.pool.first_child = T->first_child.data();
         t.pool.n_children = T->n_children.data(); t.pool.n_moves = T->n_moves.data(); t.pool.move = T->move.data(); t.pool.flags = T->flags.data();
+        t.pool.last_item = T->last_item.data(); t.pool.last_stamp = T->last_stamp.data();
         t.ctl = &T->ctl; t.n_items = S.n_items; t.level_items = S.level_items.data(); t.items = S.items.data(); t.items_per_chunk = chunk * (uint32_t)TR_MAX_LEVELS; t.chunk = chunk; t.idx = S.idx.data(); t.choice = S.choice.data();
         t.leaf_of = S.leaf_of.data(); t.created = S.created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
         t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
@@ -289,7 +291,7 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
     memset(&T->ctl, 0, sizeof T->ctl);
     QState s; q_unpack(s, *root);
     T->state[0] = *root; T->score[0] = 0; T->sims[0] = 0; T->virt[0] = 0; T->size[0] = 0; T->parent[0] = -1; T->first_child[0] = -1;
-    T->n_children[0] = 0; T->n_moves[0] = TR_UNLISTED; T->move[0] = 0xff; T->flags[0] = q_winner(s) ? TR_FLAG_TERMINAL : 0;
+    T->n_children[0] = 0; T->n_moves[0] = TR_UNLISTED; T->move[0] = 0xff; T->flags[0] = q_winner(s) ? TR_FLAG_TERMINAL : 0; T->last_stamp[0] = 0;
     T->ctl.pool_top = 1; T->ctl.root = 0;
     return T;
 }
@@ -302,11 +304,13 @@ int emu_tree_select(void *h, int slot, uint32_t n, mctsb_qstate *leaf_states) {
     if (n == 0 || n > T->t[0].K || slot < 0 || slot > 1) return -1;
     EmuSlot &S = T->slot[slot];
     for (uint32_t d = 0; d < n; d++) S.idx[d] = d;
+    T->t[slot].stamp = ++T->flush_no;
     const TreeCtx &t = T->t[slot];
     const uint32_t nch = (n + t.chunk - 1) / t.chunk;
     std::vector<uint32_t> cbegin(nch, 0), cend(nch, 1);
     for (uint32_t c = 0; c < nch; c++) {
         TreeItem r; r.node = T->ctl.root; r.start = c * t.chunk; r.count = n - r.start < t.chunk ? n - r.start : t.chunk; r.level = 0; r.n0 = 0; r.pad = 0;
+        r.has_prev = c > 0 ? 1u : 0u; r.next = c + 1 < nch ? (c + 1) * t.items_per_chunk + 1u : 0u;
         S.items[(size_t)c * t.items_per_chunk] = r; S.n_items[c] = 1;
     }
     std::fill(S.level_items.begin(), S.level_items.end(), 0u);
@@ -340,11 +344,13 @@ int emu_tree_backprop(void *h, int slot, const mctsb_leaf_sum *sums) {
     for (uint32_t d = 0; d < S.n_last; d++) tree_backprop_created(T->t[slot], d, w.data());
     const TreeCtx &t = T->t[slot];
     const uint32_t nch = (S.n_last + t.chunk - 1) / t.chunk;
-    for (uint32_t c = 0; c < nch; c++) {                   // chunk by chunk: a node's results are added in selection order
-        EmuTreeLaunch L{T, slot, {}, {}, w.data(), nullptr};
-        for (uint32_t i = 0; i < S.n_items[c]; i++) L.work.push_back(S.items[(size_t)c * t.items_per_chunk + i]);
-        simt::launch(1, 128, emu_tree_backprop_thread, &L);
-    }
+    // one launch: the heads of the chains (a node's items, chunk after chunk), in reversed order for good measure
+    EmuTreeLaunch L{T, slot, {}, {}, w.data(), nullptr};
+    for (uint32_t c = 0; c < nch; c++)
+        for (uint32_t i = 0; i < S.n_items[c]; i++)
+            if (!S.items[(size_t)c * t.items_per_chunk + i].has_prev) L.next_base.push_back(c * t.items_per_chunk + i);
+    std::reverse(L.next_base.begin(), L.next_base.end());
+    simt::launch(1, 128, emu_tree_backprop_thread, &L);
     return (int)T->ctl.error;
 }
 
