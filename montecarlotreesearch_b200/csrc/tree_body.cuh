@@ -1,10 +1,10 @@
 // tree_body.cuh — the search tree resident in HBM: Selection, Expansion and Backpropagation of
 // MCTS_tree::grow_tree (reference mcts/src/mcts.cpp:182-210) for Quoridor, as warp-level device code.
 //
-// Why.  The host tree (host/mcts.cpp) costs ~1.2 us per iteration on one CPU thread; a flush of K = 4 096 leaves
-// x 16 playouts keeps a B200 busy for 0.8 ms but the host needs 4.9 ms to select it.  Here the tree never leaves
-// the device: one launch selects a whole flush, the rollout kernel reads the leaf positions where they lie,
-// and one launch back-propagates — the host only queues launches.
+// Why.  The host tree (host/mcts.cpp) costs ~1.2 us per iteration on one CPU thread; in the middle of a game a
+// flush of K = 4 096 leaves x 16 playouts keeps a B200 busy for 0.6 ms but the host needs 4.9 ms to select it.
+// Here the tree never leaves the device: one launch selects a whole flush, the rollout kernel reads the leaf
+// positions where they lie, and one launch back-propagates — the host only queues launches.
 //
 // Semantics = the host tree's, statistic for statistic (tests: same nodes, same order, same doubles):
 //   select      mcts.cpp:161-171  walk down by select_best_child until a node is terminal or not fully expanded
@@ -15,16 +15,17 @@
 //
 // How K sequential selections run in parallel and still give the sequential result: the decision taken at a
 // node depends only on that node's children (statistics + virtual losses) and on how many earlier descents of
-// the flush passed through the node.  So the flush is processed level by level: an ITEM = (node, the ordered
-// list of descents that reach it).  One warp plays the item's descents in order — the children's statistics live
-// in registers (child i on lane i % 32), a step is one multiply-add per child, a warp maximum and a vote — and
-// hands every child the ordered sub-list of descents it received: the items of the next level, all independent.
-// The root is one serial item of K steps; below it the tree fans out over all warps.
+// the flush passed through the node.  So the unit of work is an ITEM = (node, the ordered list of descents that
+// reach it).  One warp plays the item's descents in order (tr_select_steps: a step is one multiply-add per child,
+// a warp maximum and a vote) and hands every child the ordered sub-list of descents it received: the items of the
+// next level, all independent.  The flush is cut into chunks of descents staggered by one level (TreeCtx::chunk),
+// so the root's chain of K picks and the chains of the levels below it overlap in time.
 //
-// Exactness.  The ranking pass is float (like the host's); whenever more than one child comes within 1e-5 of the
-// maximum the candidates are evaluated with the reference's own double expression (IEEE division and square root,
-// no contraction) and the first strict maximum wins.  ln N comes from a table the host fills with ITS libm
-// (N is always a multiple of R), so the doubles are the host's bit for bit.  Scores are summed per node in
+// Exactness.  The ranking pass is float with a proven error budget; whenever more than one child comes within its
+// margin of the maximum, candidates with identical statistics are settled by index, the others by a second pass in
+// double, and what that cannot separate by the reference's own expression (IEEE division and square root, no
+// contraction) — first strict maximum, as the host tree decides.  ln N comes from a table the host fills with ITS libm
+// (N is always a multiple of R), so those doubles are the host's bit for bit.  Scores are summed per node in
 // selection order, sequentially, as the host does.
 #pragma once
 #include "quoridor_lockstep_body.cuh"      // the LS_* warp primitives (device / tests/hostemu) and qcore.cuh
