@@ -188,8 +188,12 @@ def compare_gpu_overlapped(host, root, R, K, flushes, policy=0):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("partition", [True, False])
 @pytest.mark.parametrize("R,K,flushes", [(4, 16, 12), (16, 1024, 6), (16, 4096, 5), (256, 256, 5)])
-def test_device_tree_with_one_flush_in_flight_equals_host_tree_on_gpu(host, R, K, flushes):
+def test_device_tree_with_one_flush_in_flight_equals_host_tree_on_gpu(host, R, K, flushes, partition, monkeypatch):
+    """partition: the tree's kernels on SMs of their own (green contexts) / both kinds of kernels on all SMs, two plain streams"""
+    if not partition:
+        monkeypatch.setenv("MCTSB_TREE_NO_PARTITION", "1")
     info = compare_gpu_overlapped(host, m.quoridor_opening(), R, K, flushes)
     assert info["flags"] == 0
 
