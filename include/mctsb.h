@@ -258,7 +258,8 @@ int mctsb_allreduce_root_stats_group(mctsb_backend **handles, double **stats, in
  * for node and double for double: selections are made in the same order with the same virtual losses, UCT ties are
  * settled by the reference's double expression (ln N from the host's libm), scores are summed in selection order.
  * Leaf d of a flush draws from Philox streams first_rollout_id + d*rollouts_per_leaf + r, as mctsb_submit numbers them.
- *   max_nodes: node pool (94 bytes per node; a node reserves ids for all its children when it is first expanded).
+ *   max_nodes: node pool (94 bytes per node, allocated twice; a node reserves ids for all its children when it is first
+ *   expanded; mctsb_tree_advance reclaims the subtrees it drops by copying the kept one into the second pool).
  * Not thread-safe; uses the stream of `b`, which must outlive the tree and must not have a submit pending. */
 typedef struct mctsb_tree mctsb_tree;
 typedef struct mctsb_tree_info {

@@ -97,6 +97,36 @@ __global__ void __launch_bounds__(TREE_THREADS) tree_backprop_kernel(TreeCtx t, 
     }
 }
 
+// advance_tree drops every subtree but one (mcts.cpp:132-157: `delete child`).  Here the pool is a bump allocator, so
+// the kept subtree is COPIED, level by level, into the second pool and the two pools change places: one thread per
+// live node copies its fields, reserves the ids of its children's block in the new pool (a block stays n_moves
+// consecutive ids) and queues its expanded children for the next level.
+struct TreeGcEntry { uint32_t old_id, new_id; int32_t new_parent; };
+__global__ void __launch_bounds__(TREE_THREADS) tree_gc_level_kernel(TreePool from, TreePool to, const TreeGcEntry *cur, uint32_t n_cur,
+                                                                    TreeGcEntry *next, uint32_t next_cap, uint32_t *counters /* [0] to_top, [1] n_next, [2] overflow */) {
+    const uint32_t i = blockIdx.x * TREE_THREADS + threadIdx.x;
+    if (i >= n_cur) return;
+    const TreeGcEntry e = cur[i];
+    const uint32_t o = e.old_id, n = e.new_id;
+    ls_store_qstate(to.state, n, tr_load_qstate(from.state, o));
+    to.lh[n] = from.lh[o]; to.lv[n] = from.lv[o]; to.score[n] = from.score[o]; to.sims[n] = from.sims[o]; to.virt[n] = from.virt[o];
+    to.size[n] = from.size[o]; to.parent[n] = e.new_parent; to.move[n] = from.move[o]; to.flags[n] = from.flags[o]; to.last_stamp[n] = 0u;
+    const uint16_t nc = from.n_children[o], nm = from.n_moves[o];
+    to.n_children[n] = nc; to.n_moves[n] = nm;
+    const int32_t fc = from.first_child[o];
+    int32_t nf = -1;
+    if (fc >= 0 && nm != TR_UNLISTED && nm > 0) {
+        nf = (int32_t)atomicAdd(&counters[0], (uint32_t)nm);
+        if (nc > 0) {
+            const uint32_t pos = atomicAdd(&counters[1], (uint32_t)nc);
+            if (pos + nc <= next_cap) {
+                for (uint32_t k = 0; k < nc; k++) { TreeGcEntry c; c.old_id = (uint32_t)fc + k; c.new_id = (uint32_t)nf + k; c.new_parent = (int32_t)n; next[pos + k] = c; }
+            } else atomicOr(&counters[2], 1u);
+        }
+    }
+    to.first_child[n] = nf;
+}
+
 int fail(mctsb_backend *b, cudaError_t e, const char *what) {
     if (b) snprintf(b->cuda_err, sizeof b->cuda_err, "%s: %s", what, cudaGetErrorString(e));
     return e == cudaErrorMemoryAllocation ? MCTSB_ERR_OOM : MCTSB_ERR_CUDA;
@@ -110,9 +140,12 @@ struct mctsb_tree {
     int policy;
     uint32_t R, K; uint64_t pool_cap; double c;
     TreeCtx ctx[2];                     // device pointers; one set of per-flush arrays per flush slot
+    TreePool spare;                     // the second pool: advance_tree copies the kept subtree into it and swaps
+    TreeGcEntry *d_gc[2]; uint32_t gc_cap; uint32_t *d_gc_counters;
+    uint64_t collections;
     mctsb_qstate *d_leaf_states[2]; mctsb_leaf_sum *d_sums[2]; double *d_w[2];
     double *d_logtab;
-    void *allocs[64]; int n_allocs;
+    void *allocs[96]; int n_allocs;
     int select_blocks;
     bool overlap;                       // select flush f+1 while the playouts of flush f run (host tree: MCTS_batching::overlap)
     cudaStream_t tree_stream;           // Selection / Backpropagation kernels in overlap mode (the playouts stay on the backend's stream)
@@ -207,6 +240,37 @@ int read_root(mctsb_tree *t, RootView &v) {
 
 namespace {
 
+// The kept subtree (root = `root`) moves into the spare pool; afterwards the root is node 0 and pool_top is what the
+// subtree needs.  Called between grows (no simulation in flight).
+int collect(mctsb_tree *t, int32_t root, uint32_t *new_top) {
+    mctsb_backend *b = t->b;
+    cudaStream_t st = b->stream;
+    const TreePool from = t->ctx[0].pool, to = t->spare;
+    const TreeGcEntry first = {(uint32_t)root, 0u, -1};
+    uint32_t counters[4] = {1u, 0u, 0u, 0u};                 // the root takes id 0
+    TCK(cudaMemcpyAsync(t->d_gc[0], &first, sizeof first, cudaMemcpyHostToDevice, st));
+    TCK(cudaMemcpyAsync(t->d_gc_counters, counters, sizeof counters, cudaMemcpyHostToDevice, st));
+    uint32_t n_cur = 1;
+    int cur = 0;
+    while (n_cur > 0) {
+        tree_gc_level_kernel<<<(n_cur + TREE_THREADS - 1) / TREE_THREADS, TREE_THREADS, 0, st>>>(from, to, t->d_gc[cur], n_cur, t->d_gc[cur ^ 1], t->gc_cap, t->d_gc_counters);
+        TCK(cudaGetLastError());
+        b->launches++;
+        TCK(cudaMemcpyAsync(counters, t->d_gc_counters, sizeof counters, cudaMemcpyDeviceToHost, st));
+        TCK(cudaStreamSynchronize(st));
+        if (counters[2]) { snprintf(b->cuda_err, sizeof b->cuda_err, "device tree: a level of the kept subtree is wider than the collector's queue"); return MCTSB_ERR_TREE_FULL; }
+        n_cur = counters[1];
+        const uint32_t zero = 0;
+        TCK(cudaMemcpyAsync(t->d_gc_counters + 1, &zero, 4, cudaMemcpyHostToDevice, st));
+        cur ^= 1;
+    }
+    *new_top = counters[0];
+    for (int k = 0; k < 2; k++) t->ctx[k].pool = to;
+    t->spare = from;
+    t->collections++;
+    return MCTSB_OK;
+}
+
 // Split the device's SMs into a small group for the tree and the rest for the playouts (CUDA driver API, green
 // contexts; entry points through cudaGetDriverEntryPoint so that the library does not link libcuda).  Any failure
 // leaves part_ok false: the caller then runs both kinds of kernels on all SMs, as before.
@@ -280,6 +344,17 @@ int mctsb_tree_create(mctsb_backend *b, mctsb_tree **out, const mctsb_qstate *ro
     TTRY(dev_alloc(t, &c.pool.n_children, N)); TTRY(dev_alloc(t, &c.pool.n_moves, N)); TTRY(dev_alloc(t, &c.pool.move, N));
     TTRY(dev_alloc(t, &c.pool.flags, N)); TTRY(dev_alloc(t, &c.pool.last_item, N)); TTRY(dev_alloc(t, &c.pool.last_stamp, N));
     TTRY(dev_alloc(t, &c.ctl, 1));
+    {
+        TreePool &q = t->spare;
+        TTRY(dev_alloc(t, &q.state, N)); TTRY(dev_alloc(t, &q.lh, N)); TTRY(dev_alloc(t, &q.lv, N));
+        TTRY(dev_alloc(t, &q.score, N)); TTRY(dev_alloc(t, &q.sims, N)); TTRY(dev_alloc(t, &q.virt, N));
+        TTRY(dev_alloc(t, &q.size, N)); TTRY(dev_alloc(t, &q.parent, N)); TTRY(dev_alloc(t, &q.first_child, N));
+        TTRY(dev_alloc(t, &q.n_children, N)); TTRY(dev_alloc(t, &q.n_moves, N)); TTRY(dev_alloc(t, &q.move, N));
+        TTRY(dev_alloc(t, &q.flags, N)); TTRY(dev_alloc(t, &q.last_item, N)); TTRY(dev_alloc(t, &q.last_stamp, N));
+        t->gc_cap = (uint32_t)(N < (1u << 24) ? N : (1u << 24));       // widest level of a kept subtree (nodes that exist, not reserved ids)
+        TTRY(dev_alloc(t, &t->d_gc[0], (size_t)t->gc_cap)); TTRY(dev_alloc(t, &t->d_gc[1], (size_t)t->gc_cap));
+        TTRY(dev_alloc(t, &t->d_gc_counters, 4));
+    }
     c.K = t->K; c.pool_cap = (uint32_t)max_nodes; c.R = t->R; c.c = uct_c;
     // chunks of 256 descents (measured best over whole games at 4 096 leaves per flush: 23.7 M rollouts/s against 22.5 M
     // at 512 and 19.0 M at 1 024; more for flushes beyond 64 x 256), a whole number of warps' worth each
@@ -580,6 +655,18 @@ int mctsb_tree_advance(mctsb_tree *t, int32_t move_id) {
         s = write_node(t, (uint32_t)next, st);
         if (s != MCTSB_OK) return s;
         const uint32_t top = v.ctl.pool_top + 1;
+        TCK(cudaMemcpy(&t->ctx[0].ctl->pool_top, &top, 4, cudaMemcpyHostToDevice));
+    }
+    uint32_t top = next >= (int32_t)v.ctl.pool_top ? v.ctl.pool_top + 1 : v.ctl.pool_top;
+    // the dropped subtrees are reclaimed by copying the kept one into the spare pool — once the pool is a quarter full
+    // (MCTSB_TREE_GC=always / never for tests and measurements)
+    const char *gc = getenv("MCTSB_TREE_GC");
+    const bool want = gc && gc[0] == 'a' ? true : gc && gc[0] == 'n' ? false : (uint64_t)top * 4 > t->pool_cap;
+    if (want) {
+        uint32_t new_top = 0;
+        s = collect(t, next, &new_top);
+        if (s != MCTSB_OK) return s;
+        next = 0; top = new_top;
         TCK(cudaMemcpy(&t->ctx[0].ctl->pool_top, &top, 4, cudaMemcpyHostToDevice));
     }
     TCK(cudaMemcpy(&t->ctx[0].ctl->root, &next, 4, cudaMemcpyHostToDevice));

@@ -198,13 +198,13 @@ def test_device_tree_with_one_flush_in_flight_equals_host_tree_on_gpu(host, R, K
     assert info["flags"] == 0
 
 
-def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0):
+def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0, max_nodes=1 << 23):
     """device tree vs host tree (both playing their rollouts on the GPU, same Philox ids): identical after every grow"""
     be = m.RolloutBackend(0, m.DEFAULT_SEED)
     base_id = 1 << 41
     host.mcts_host_set_next_rollout_id(base_id)
     ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, policy=policy)
-    dt = m.DeviceTree(be, root, R, K, policy=policy, max_nodes=1 << 23)
+    dt = m.DeviceTree(be, root, R, K, policy=policy, max_nodes=max_nodes)
     done = 0
     for f in range(flushes):
         n = K if not (tail and f == flushes - 1) else tail
@@ -358,3 +358,20 @@ def test_root_merge_of_device_trees_equals_the_host_trees_merge(host):
         assert len({t.best_move() for t in trees}) == 1
         assert int(kids[0][1].sum()) == n * 512 * 8
         [t.close() for t in trees]; [b_.close() for b_ in bes]
+
+
+@pytest.mark.gpu
+def test_advance_tree_reclaims_the_dropped_subtrees(host, monkeypatch):
+    """advance_tree on the device copies the kept subtree into the spare pool (the dropped ones are gone, mcts.cpp:132-157):
+    the tree stays the host tree's after every collection, and a pool far too small for the whole game is enough"""
+    monkeypatch.setenv("MCTSB_TREE_GC", "always")
+    info = compare_gpu(host, m.quoridor_opening(), 4, 256, 12, advance_every=1)
+    assert info["flags"] == 0 and info["nodes_used"] < 60000         # one move's subtree, not twelve moves' worth of ids
+    monkeypatch.delenv("MCTSB_TREE_GC")
+    # default policy (collect once a quarter of the pool is used): 30 moves x 1 024 iterations need ~1 M ids, the pool has 150 000
+    info = compare_gpu(host, m.quoridor_opening(), 4, 256, 120, advance_every=4, max_nodes=150000)
+    assert info["flags"] == 0 and info["nodes_used"] <= 150000
+    monkeypatch.setenv("MCTSB_TREE_GC", "never")
+    with pytest.raises(m.BackendError) as e:
+        compare_gpu(host, m.quoridor_opening(), 4, 256, 120, advance_every=4, max_nodes=150000)
+    assert e.value.status == 9

@@ -69,12 +69,40 @@ class StockRepl:
             self.p.kill()
 
 
+class DeviceTreePlayer:
+    """the tree resident in HBM (mctsb_tree_*) behind the three calls the match makes"""
+
+    def __init__(self, m, args, seed):
+        self.be = m.RolloutBackend(0, seed)
+        self.tree = m.DeviceTree(self.be, m.quoridor_opening(), args.rollouts_per_leaf, args.leaves_per_flush, max_nodes=1 << 26)
+        self.tree.set_overlap(True)
+        self.R, self.next_id = args.rollouts_per_leaf, 0
+
+    def grow(self, iters):
+        self.tree.grow(iters, self.next_id)
+        self.next_id += iters * self.R
+
+    def best_move(self):
+        return self.tree.best_move()
+
+    def advance(self, mv):
+        self.tree.advance(mv)
+        s = self.tree.root_state()
+        return int(s["wx"]) == 8 or int(s["bx"]) == 0
+
+    def close(self):
+        self.tree.close(); self.be.close()
+
+
 def play(args, host, m, Session, ours_is_white, game_no):
     stock = StockRepl(args.stock)
-    tree = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
-                   leaves_per_flush=args.leaves_per_flush, device=0, seed=args.seed + game_no)
-    tree.set_overlap(2)
-    tree.set_gpu_expand(True)
+    if args.device_tree:
+        tree = DeviceTreePlayer(m, args, args.seed + game_no)
+    else:
+        tree = Session(host, m.GAME_QUORIDOR, m.quoridor_opening(), rollouts_per_leaf=args.rollouts_per_leaf,
+                       leaves_per_flush=args.leaves_per_flush, device=0, seed=args.seed + game_no)
+        tree.set_overlap(2)
+        tree.set_gpu_expand(True)
     moves, t_ours, t_stock, winner = [], [], [], None
     white_to_move = True
     while winner is None and len(moves) < args.max_moves:
@@ -112,6 +140,7 @@ def main():
     ap.add_argument("--rollouts-per-leaf", type=int, default=1024)
     ap.add_argument("--leaves-per-flush", type=int, default=64)
     ap.add_argument("--max-moves", type=int, default=300)
+    ap.add_argument("--device-tree", type=int, default=0, help="1 = our tree lives on the GPU (mctsb_tree_*), one flush in flight")
     ap.add_argument("--seed", type=lambda x: int(x, 0), default=0x2026101900000001)
     ap.add_argument("--stock", default=os.path.join(ROOT, "oracle", "_ref", "quoridor_stock"))
     args = ap.parse_args()
@@ -120,9 +149,10 @@ def main():
     host = load()
     games = [play(args, host, m, Session, g % 2 == 0, g) for g in range(args.games)]
     print(json.dumps({
-        "what": "B200 host tree (%d iterations x %d rollouts per move, flushes of %d leaves, 2 in flight, GPU-prepared expansion) vs the "
+        "what": "B200 %s (%d iterations x %d rollouts per move, flushes of %d leaves) vs the "
                 "reference's stock Quoridor program (20 000 iterations x 4 rollouts or 15 s per move) over its own text protocol"
-                % (args.iters, args.rollouts_per_leaf, args.leaves_per_flush),
+                % ("tree in HBM (mctsb_tree_*, one flush in flight)" if args.device_tree else "host tree (2 flushes in flight, GPU-prepared expansion)",
+                   args.iters, args.rollouts_per_leaf, args.leaves_per_flush),
         "games": games, "ours_won": sum(1 for g in games if g["ours_won"]), "played": len(games)}))
 
 
