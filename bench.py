@@ -354,12 +354,13 @@ def main():
     states_host = np.ascontiguousarray(state)
     merged(be.rollout_batch(G, P, states_host, per_leaf, first_id(1000))[1])
     barrier()
-    e2e_s = 0.0
+    e2e_s, e2e_score = 0.0, 0.0
     for k in range(args.steps):
         be.flush_l2()
         t0 = time.perf_counter()
-        _, sums = be.rollout_batch(G, P, states_host, per_leaf, first_id(2000 + k))    # host buffers in, H2D, kernel, D2H, host sums out
-        merged(sums)                                                                   # ... and the job-wide sums on every rank
+        # the SAME rollout ids as the `value` steps: the same playouts, plus the copies of a call with host buffers
+        _, sums = be.rollout_batch(G, P, states_host, per_leaf, first_id(args.warmup + k))    # host buffers in, H2D, kernel, D2H, host sums out
+        e2e_score += score_of(merged(sums))                                                   # ... and the job-wide result on every rank, as in a `value` step
         e2e_s += time.perf_counter() - t0
     t0 = time.perf_counter()
     barrier()
@@ -513,7 +514,8 @@ def main():
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 32 * n_leaves * world, "d2h_bytes_per_step": 24 * n_leaves * world,
                 "note": "mctsb_rollout_batch with host buffers" + ("" if world == 1 else " + the cross-rank merge, every step") +
-                        "; at N=1 it differs from value only by launch + copy latency (tens of microseconds per 28 ms step) and runs other rollout ids"},
+                        "; the same rollout ids as the value steps (the same playouts): it differs from value by the launch and copy latency of a call with host buffers (tens of microseconds per 28 ms step)",
+                "mean_score": e2e_score / total_rollouts},
         "gpu_launches": int(launches),
         "clocks": sampler.summary(),
         "mean_score": mean_score,
