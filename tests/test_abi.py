@@ -62,3 +62,17 @@ def test_no_device_means_no_compute(lib):
     with pytest.raises(m.BackendError) as e:
         m.RolloutBackend()
     assert e.value.status == 1
+
+
+def test_tree_entry_points_refuse_to_run_without_a_backend(lib):
+    """the device-resident tree hangs off a backend handle; without one (no device: no handle) every entry point is refused"""
+    import numpy as np
+    t = C.c_void_p()
+    root = np.ascontiguousarray(m.quoridor_opening())
+    assert lib.mctsb_tree_create(None, C.byref(t), root.ctypes.data, 0, 16, 4096, 1 << 20, 1.41) == 3      # MCTSB_ERR_BAD_ARG
+    assert not t.value
+    mv = C.c_int32(0)
+    assert lib.mctsb_tree_grow(None, 16, 16, 0) == 3 and lib.mctsb_tree_best_move(None, C.byref(mv)) == 3
+    assert lib.mctsb_tree_advance(None, 13) == 3 and lib.mctsb_tree_merge_root(None) == 3 and lib.mctsb_tree_set_overlap(None, 1) == 3
+    assert lib.mctsb_tree_destroy(None) == 0
+    assert b"device-resident tree" in lib.mctsb_strerror(9)
