@@ -285,6 +285,9 @@ int mctsb_tree_grow(mctsb_tree *t, uint32_t iterations, uint32_t leaves_per_flus
  * results arrive) — the order of the host tree with MCTS_batching::overlap, one flush in flight; off (default):
  * every flush is back-propagated before the next one is selected. */
 int mctsb_tree_set_overlap(mctsb_tree *t, int on);
+/* on: the tree expands generate_good_moves (Quoridor.cpp:518-592, the reference's actions_to_try without TEST_ALL_MOVES,
+ * :618-627) instead of generate_all_moves — Quoridor_state::set_good_moves_only of the host tree.  Before the first grow. */
+int mctsb_tree_set_good_moves(mctsb_tree *t, int on);
 int mctsb_tree_get_info(mctsb_tree *t, mctsb_tree_info *info);
 /* root children in creation (= actions_to_try) order: canonical move id, simulations, score; returns the count in *n */
 int mctsb_tree_root_children(mctsb_tree *t, int32_t *move_ids, uint64_t *sims, double *scores, int max_children, int *n);

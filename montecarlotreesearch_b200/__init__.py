@@ -40,7 +40,7 @@ EXPORTS = [
     "mctsb_comm_unique_id", "mctsb_comm_init_rank", "mctsb_comm_init_all", "mctsb_comm_destroy", "mctsb_comm_info",
     "mctsb_allreduce_root_stats", "mctsb_allreduce_leaf_sums", "mctsb_allreduce_root_stats_group",
     "mctsb_tree_create", "mctsb_tree_destroy", "mctsb_tree_grow", "mctsb_tree_get_info", "mctsb_tree_root_children",
-    "mctsb_tree_best_move", "mctsb_tree_advance", "mctsb_tree_root_state", "mctsb_tree_dump", "mctsb_tree_set_overlap", "mctsb_tree_merge_root",
+    "mctsb_tree_best_move", "mctsb_tree_advance", "mctsb_tree_root_state", "mctsb_tree_dump", "mctsb_tree_set_overlap", "mctsb_tree_merge_root", "mctsb_tree_set_good_moves",
 ]
 TREE_INFO_DTYPE = np.dtype([("root_sims", "<u8"), ("root_score", "<f8"), ("root_size", "<u4"), ("root_children", "<u4"),
                             ("nodes_used", "<u4"), ("deepest_level", "<u4"), ("exact_evals", "<u4"), ("flags", "<u4"),
@@ -116,6 +116,7 @@ def load_library():
     L.mctsb_tree_grow.argtypes = [vp, u32, u32, u64]
     L.mctsb_tree_set_overlap.argtypes = [vp, i32]
     L.mctsb_tree_merge_root.argtypes = [vp]
+    L.mctsb_tree_set_good_moves.argtypes = [vp, i32]
     L.mctsb_tree_get_info.argtypes = [vp, vp]
     L.mctsb_tree_root_children.argtypes = [vp, vp, vp, vp, i32, C.POINTER(i32)]
     L.mctsb_tree_best_move.argtypes = [vp, C.POINTER(C.c_int32)]
@@ -338,6 +339,10 @@ class DeviceTree:
         if getattr(self, "h", None):
             self.lib.mctsb_tree_destroy(self.h)
             self.h = None
+
+    def set_good_moves_only(self, on=True):
+        """before the first grow: expand generate_good_moves (Quoridor.cpp:518-592) instead of all legal moves"""
+        self.be._ck(self.lib.mctsb_tree_set_good_moves(self.h, int(bool(on))))
 
     def set_overlap(self, on=True):
         """select flush f+1 while the playouts of flush f run (one flush in flight, as MCTS_batching::overlap)"""

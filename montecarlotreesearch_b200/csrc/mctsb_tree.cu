@@ -435,6 +435,13 @@ int mctsb_tree_destroy(mctsb_tree *t) {
     return MCTSB_OK;
 }
 
+int mctsb_tree_set_good_moves(mctsb_tree *t, int on) {
+    if (!t) return MCTSB_ERR_BAD_ARG;
+    if (t->flushes > 0) return MCTSB_ERR_BUSY;            // the move lists of a grown tree are what they are
+    for (int k = 0; k < 2; k++) t->ctx[k].good_moves = on ? 1u : 0u;
+    return MCTSB_OK;
+}
+
 int mctsb_tree_set_overlap(mctsb_tree *t, int on) {
     if (!t) return MCTSB_ERR_BAD_ARG;
     t->overlap = on != 0;

@@ -148,6 +148,7 @@ struct TreeCtx {                      // the pool and the per-flush arrays of ON
     TreeItem *items; uint32_t items_per_chunk;   // chunk c owns items[c * items_per_chunk ...]
     uint32_t chunk;                   // descents per chunk
     uint32_t stamp;                   // number of this flush (never 0)
+    uint32_t good_moves;              // 1 = the tree expands generate_good_moves (Quoridor.cpp:518-592) instead of generate_all_moves
     uint32_t *idx;                    // [TR_MAX_LEVELS][K]: idx[l*K + p] = descent number, lists of level l items
     uint8_t *choice;                  // [K] scratch: child picked by the step at list position p
     int32_t *leaf_of;                 // [K] node every descent ended at
@@ -243,12 +244,39 @@ LS_DEV void tr_list_moves(const QState &s, int lane, uint64_t &lh, uint64_t &lv)
     lv = (uint64_t)bal[1] | ((uint64_t)bal[3] << 32);
 }
 
+// generate_good_moves by the warp (as quoridor_goodmoves_kernel): lane l measures the walls anchored at l and l + 32 in
+// both orientations, lane 0 makes the reference's sequential pass; the ordered list lands in W.list, its length in W.list_n.
+// The list is not stored with the node (144 bytes each): a node that is expanded again builds it again.
+template <class WS>
+LS_DEV int tr_good_moves(QState &s, int lane, WS &W) {
+    uint64_t ch, cv;
+    q_cheap_wall_masks(s, ch, cv);
+    const int p = s.turn, e = 1 - p;
+    LS_UNROLL1
+    for (int j = 0; j < 4; j++) {
+        const int a = 32 * (j >> 1) + lane, k = 2 * a + (j & 1);
+        int pe = -1, po = -1;
+        if ((((j & 1) ? cv : ch) >> a) & 1ull) { pe = q_sp_with_wall(s, e, k, nullptr); po = q_sp_with_wall(s, p, k, nullptr); }
+        W.pe[k] = (int8_t)pe; W.po[k] = (int8_t)po;
+    }
+    LS_SYNCWARP();
+    if (lane == 0) {
+        const bool walls = (ch | cv) != 0;
+        const int our_path = walls ? q_sp(s, p, nullptr) : 0, enemy_path = walls ? q_sp(s, e, nullptr) : 0;
+        W.list_n = q_good_moves_select(s, q_step_mask(s), ch, cv, our_path, enemy_path, W.pe, W.po, W.list);
+    }
+    LS_SYNCWARP();
+    return W.list_n;
+}
+
 // ---- Selection + Expansion of one item (all 32 lanes of a warp; W = the warp's shared memory) ------------------
 struct TreeWarpSmem {
     double sc[32 * TR_SLOTS], vis[32 * TR_SLOTS];       // per child: score, simulations finished + in flight
     uint32_t vq[32 * TR_SLOTS], cnt[32 * TR_SLOTS];     // simulations in flight, descents handed to the child by this item
     uint32_t real[32 * TR_SLOTS];                       // finished simulations (constant while the item is processed)
     uint32_t vis0[32 * TR_SLOTS];                       // simulations finished + in flight when the item began
+    int8_t pe[128], po[128];                            // good-moves trees: both players' path lengths with every candidate wall
+    uint8_t list[MCTSB_Q_GOOD_MAX]; int32_t list_n;     // ... and the node's ordered move list
     uint32_t cursor[32 * TR_SLOTS];                     // hand-down: next free place of the child's list
 };
 #if LS_WARP == 32
@@ -487,9 +515,10 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     LS_SYNCWARP();
     // --- move list on first use ---
     const uint32_t steps = q_step_mask(s);
+    bool have_list = false;
     if (n_moves == TR_UNLISTED) {
-        tr_list_moves(s, lane, lh, lv);
-        n_moves = popc32(steps) + popc64(lh) + popc64(lv);
+        if (t.good_moves) { n_moves = tr_good_moves(s, lane, W); have_list = true; lh = lv = 0ull; }
+        else { tr_list_moves(s, lane, lh, lv); n_moves = popc32(steps) + popc64(lh) + popc64(lv); }
         if (lane == 0) { P.lh[X] = lh; P.lv[X] = lv; P.n_moves[X] = (uint16_t)n_moves; }
     }
     if (n_moves == 0) {                                   // no legal move and not terminal: plays out where it stands
@@ -525,9 +554,12 @@ LS_DEV void tree_select_item(const TreeCtx &t, const TreeItem it, const int lane
     // --- Expansion: while untried moves remain every descent that reaches X makes the next child ---
     const uint32_t untried = (uint32_t)(n_moves - nc);
     const uint32_t ne = it.count < untried ? it.count : untried;
+    if (t.good_moves && ne > 0u && !have_list) tr_good_moves(s, lane, W);     // the ordered list, for the children made now
     for (uint32_t e = lane; e < ne; e += 32) {
         const int i = nc + (int)e, cid = first + i;
-        const int mv = q_nth_move(s, steps, lh, lv, i);
+        int mv;                                             // encoded as q_nth_move returns it: cell, or 128 + wall
+        if (t.good_moves) { const int id = W.list[i]; mv = id < 81 ? id : id < 145 ? 128 + 2 * (id - 81) : 128 + 2 * (id - 145) + 1; }
+        else mv = q_nth_move(s, steps, lh, lv, i);
         QState ns = s;
         if (mv < 81) q_play_step(ns, mv); else q_play_wall(ns, mv - 128);
         mctsb_qstate packed; q_pack(ns, packed);

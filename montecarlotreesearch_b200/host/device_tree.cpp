@@ -21,6 +21,8 @@ MCTS_device_tree::MCTS_device_tree(const Quoridor_state &starting_state, CudaRol
     const uint32_t K = batching.leaves_per_flush == 0 ? 1 : batching.leaves_per_flush;
     check(mctsb_tree_create(backend->raw(), &tree, &root, starting_state.gpu_policy_id(), batching.rollouts_per_leaf, K, max_nodes, uct_c), "mctsb_tree_create");
     check(mctsb_tree_set_overlap(tree, batching.overlap ? 1 : 0), "mctsb_tree_set_overlap");
+    // the state's own choice of actions_to_try travels with it, as it does from node to node on the host
+    check(mctsb_tree_set_good_moves(tree, starting_state.get_good_moves_only() ? 1 : 0), "mctsb_tree_set_good_moves");
 }
 
 MCTS_device_tree::~MCTS_device_tree() {

@@ -2,7 +2,8 @@
 // advance_tree, get_size, get_current_state) over the search tree that lives in HBM (include/mctsb.h, mctsb_tree_*).
 // Same searches as MCTS_tree with MCTS_batching{rollouts_per_leaf, leaves_per_flush, overlap}: node for node and
 // double for double (tests/test_device_tree.py), but Selection, Expansion and Backpropagation run as kernels next to
-// the playouts and the host thread only queues launches.  Quoridor trees over generate_all_moves.
+// the playouts and the host thread only queues launches.  Quoridor trees (generate_all_moves, or generate_good_moves when
+// the starting state says so: Quoridor_state::set_good_moves_only).
 #ifndef MCTS_DEVICE_TREE_H
 #define MCTS_DEVICE_TREE_H
 

@@ -31,6 +31,7 @@ class EmuLib:
             L.emu_tree_create.restype = vp
             L.emu_tree_create.argtypes = [vp, C.c_uint32, C.c_uint32, C.c_uint32, C.c_double, C.c_uint32, C.c_uint32]
             L.emu_tree_destroy.argtypes = [vp]
+            L.emu_tree_set_good_moves.argtypes = [vp, C.c_int]
             L.emu_tree_select.argtypes = [vp, C.c_int, C.c_uint32, vp]
             L.emu_tree_backprop.argtypes = [vp, C.c_int, vp]
             L.emu_tree_dump.restype = C.c_uint64
@@ -184,6 +185,9 @@ class EmuTree:
         if self.h:
             self.lib.emu_tree_destroy(self.h)
             self.h = None
+
+    def set_good_moves_only(self, on=True):
+        self.lib.emu_tree_set_good_moves(self.h, int(bool(on)))
 
     def select(self, n, slot=0):
         """Selection + Expansion of a flush of n descents into flush slot 0 / 1 -> (leaf positions, error bits)"""

@@ -286,7 +286,7 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
         t.pool.last_item = T->last_item.data(); t.pool.last_stamp = T->last_stamp.data();
         t.ctl = &T->ctl; t.n_items = S.n_items; t.level_items = S.level_items.data(); t.items = S.items.data(); t.items_per_chunk = chunk * (uint32_t)TR_MAX_LEVELS; t.chunk = chunk; t.idx = S.idx.data(); t.choice = S.choice.data();
         t.leaf_of = S.leaf_of.data(); t.created = S.created.data(); t.K = K; t.pool_cap = pool_cap; t.R = R; t.c = c;
-        t.logtab = T->logtab.data(); t.logtab_n = logtab_n;
+        t.logtab = T->logtab.data(); t.logtab_n = logtab_n; t.good_moves = 0u; t.stamp = 0u;
     }
     memset(&T->ctl, 0, sizeof T->ctl);
     QState s; q_unpack(s, *root);
@@ -296,6 +296,7 @@ void *emu_tree_create(const mctsb_qstate *root, uint32_t R, uint32_t K, uint32_t
     return T;
 }
 void emu_tree_destroy(void *h) { delete (EmuTree *)h; }
+void emu_tree_set_good_moves(void *h, int on) { EmuTree *T = (EmuTree *)h; T->t[0].good_moves = T->t[1].good_moves = on ? 1u : 0u; }
 
 // Selection + Expansion of one flush of n descents into flush slot `slot`; leaf_states[d] = position of the leaf
 // descent d ended at

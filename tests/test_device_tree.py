@@ -31,7 +31,7 @@ def fake_sum(state_bytes, first_id, R):
     return a % (R << 29), b % ((R << 28) + 1)
 
 
-def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, chunk=64):
+def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, chunk=64, good_moves=False):
     """grow the host tree and the emulated device tree side by side; compare after every flush"""
     from tests.hostemu.emulib import EmuTree
     to_double = emu32.lib.emu_leaf_sum_to_double
@@ -54,6 +54,8 @@ def drive_both(host, emu32, root, R, K, flushes, port=None, advance_every=0, chu
     host.mcts_host_set_next_rollout_id(base_id)
     ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, callback=cb)
     dt = EmuTree(emu32, root, R, K, chunk=max(chunk, (K + 63) // 64 // 32 * 32 + 32))
+    if good_moves:
+        ht.set_good_moves_only(True); dt.set_good_moves_only(True)
     done = 0
     for f in range(flushes):
         n = K if not isinstance(flushes, list) else K
@@ -198,13 +200,15 @@ def test_device_tree_with_one_flush_in_flight_equals_host_tree_on_gpu(host, R, K
     assert info["flags"] == 0
 
 
-def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0, max_nodes=1 << 23):
+def compare_gpu(host, root, R, K, flushes, policy=0, advance_every=0, tail=0, max_nodes=1 << 23, good_moves=False):
     """device tree vs host tree (both playing their rollouts on the GPU, same Philox ids): identical after every grow"""
     be = m.RolloutBackend(0, m.DEFAULT_SEED)
     base_id = 1 << 41
     host.mcts_host_set_next_rollout_id(base_id)
     ht = Session(host, m.GAME_QUORIDOR, root, rollouts_per_leaf=R, leaves_per_flush=K, policy=policy)
     dt = m.DeviceTree(be, root, R, K, policy=policy, max_nodes=max_nodes)
+    if good_moves:
+        ht.set_good_moves_only(True); dt.set_good_moves_only(True)
     done = 0
     for f in range(flushes):
         n = K if not (tail and f == flushes - 1) else tail
@@ -375,3 +379,28 @@ def test_advance_tree_reclaims_the_dropped_subtrees(host, monkeypatch):
     with pytest.raises(m.BackendError) as e:
         compare_gpu(host, m.quoridor_opening(), 4, 256, 120, advance_every=4, max_nodes=150000)
     assert e.value.status == 9
+
+
+def test_emulated_device_tree_over_good_moves(host, emu32):
+    """generate_good_moves (Quoridor.cpp:518-592) as the tree's actions_to_try: Quoridor_state::set_good_moves_only on the
+    host, mctsb_tree_set_good_moves on the device — the ordered list is rebuilt by the warp whenever a node is expanded"""
+    from tests.util import golden
+    corpus = golden("corpus_q.npy")
+    for root in (m.quoridor_opening(), corpus[7], corpus[1234]):
+        st, _ = drive_both(host, emu32, root, 2, 64, 6, advance_every=3, chunk=32, good_moves=True)
+        assert st["error"] == 0
+
+
+@pytest.mark.gpu
+def test_device_tree_over_good_moves_on_gpu(host):
+    from tests.util import golden
+    corpus = golden("corpus_q.npy")
+    for root in (m.quoridor_opening(), corpus[7], corpus[4000]):
+        info = compare_gpu(host, root, 8, 512, 8, advance_every=2, good_moves=True)
+        assert info["flags"] == 0
+    be = m.RolloutBackend(0, m.DEFAULT_SEED)
+    t = m.DeviceTree(be, m.quoridor_opening(), 4, 64)
+    t.grow(64, 0)
+    with pytest.raises(m.BackendError):
+        t.set_good_moves_only(True)                              # not on a grown tree
+    t.close(); be.close()
