@@ -101,7 +101,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "150"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             time.sleep(0.15)          # let the first sample land before the region starts
         except Exception:
