@@ -366,22 +366,29 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
     uint32_t my_choice = 0;
     const unsigned long long m0 = st.n0 / R;
     const bool on_grid = m0 * R == st.n0;
+    // the steps in blocks of 32: c*sqrt(ln N) of a block's steps is computed by its 32 lanes at once, and a step fetches the
+    // coefficient of the NEXT one while its own multiply-adds are in flight
     LS_UNROLL1
-    for (uint32_t j = st.ne; j < st.count; j++) {
-        const uint32_t rel = (j - st.ne) & 31u;
-        if (rel == 0u) {                                   // c*sqrt(ln N) of the next 32 steps, one per lane
-            const float np = (float)(st.n0 + (unsigned long long)(j + (uint32_t)lane) * R);
+    for (uint32_t jb = st.ne; jb < st.count; jb += 32u) {
+        {
+            const float np = (float)(st.n0 + (unsigned long long)(jb + (uint32_t)lane) * R);
             coef_lane = t.c > 0 ? cf * TR_FSQRT(TR_LOGF(np)) : 0.0f;
-            lp_lane = t.c > 0 ? tr_log_parent(t, st.n0, m0, on_grid, j + (uint32_t)lane) : 0.0;    // the exact ln N, should a tie need it
+            lp_lane = t.c > 0 ? tr_log_parent(t, st.n0, m0, on_grid, jb + (uint32_t)lane) : 0.0;    // the exact ln N, should a tie need it
             cs_lane = t.c > 0 ? t.c * TR_DSQRT(lp_lane) : 0.0;
         }
+        const uint32_t nrel = st.count - jb < 32u ? st.count - jb : 32u;
+        float coef_next = LS_SHFL(coef_lane, 0);
+        LS_UNROLL1
+        for (uint32_t rel = 0; rel < nrel; rel++) {
+        const uint32_t j = jb + rel;
         int pick;                                          // child index
         if (nc == 1) pick = 0;
         else {
-            const float coef = LS_SHFL(coef_lane, (int)rel);
+            const float coef = coef_next;
             float a[NS];
 #pragma unroll
             for (int q = 0; q < NS; q++) a[q] = TR_FMAF(coef, is[q], ex[q]);
+            coef_next = LS_SHFL(coef_lane, (int)((rel + 1u) & 31u));
             float amax = a[0];
 #pragma unroll
             for (int q = 1; q < NS; q++) amax = fmaxf(amax, a[q]);
@@ -476,10 +483,9 @@ LS_DEV void tr_select_steps(const TreeCtx &t, TreeWarpSmem &W, const int lane, c
                 }
         }
         if ((int)rel == lane) my_choice = (uint32_t)pick;
-        if (rel == 31u || j + 1 == st.count) {             // 32 choices at a time go to memory
-            const uint32_t base = j - rel;
-            if ((uint32_t)lane <= rel) t.choice[st.start + base + lane] = (uint8_t)my_choice;
+        (void)j;
         }
+        if ((uint32_t)lane < nrel) t.choice[st.start + jb + lane] = (uint8_t)my_choice;      // 32 choices at a time go to memory
     }
     // how many descents every child received (the hand-down reads it)
 #pragma unroll
